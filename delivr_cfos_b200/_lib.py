@@ -1,0 +1,239 @@
+"""ctypes binding of libdelivr_b200.so (include/delivr_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or the device is
+not sm_100, every entry point raises.  PyTorch is used by callers only for
+device memory / streams / torch.distributed plumbing; the library itself has
+no torch dependency.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdelivr_b200.so")
+
+c_i32, c_i64, c_f32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+
+
+class DlvError(RuntimeError):
+    pass
+
+
+class SegParams(ctypes.Structure):
+    _fields_ = [
+        ("shape_pad", c_i64 * 3), ("shape_real", c_i64 * 3), ("roi", c_i32 * 3), ("overlap", c_f32),
+        ("tta", c_i32), ("threshold", c_f32), ("erosion_iters", c_i32), ("erosion_block_planes", c_i64),
+        ("blend_mode", c_i32), ("window_batch", c_i32), ("skip_empty", c_i32), ("flip_dim", c_i32),
+    ]
+
+
+class SegStats(ctypes.Structure):
+    _fields_ = [
+        ("windows_total", c_i64), ("windows_active", c_i64), ("passes", c_i64), ("kernel_launches", c_i64),
+        ("ms_unet", ctypes.c_double), ("ms_finalise", ctypes.c_double), ("ms_conv", ctypes.c_double),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class Table(ctypes.Structure):
+    _fields_ = [("n", c_i64), ("voxel_counts", ctypes.POINTER(ctypes.c_uint64)),
+                ("sums", ctypes.POINTER(ctypes.c_uint64)), ("bbox", ctypes.POINTER(c_i64))]
+
+
+# every symbol include/delivr_b200.h declares (tests check the .so exports exactly these)
+EXPORTS = [
+    "dlv_abi_version", "dlv_init", "dlv_destroy", "dlv_last_error", "dlv_launch_count", "dlv_stream",
+    "dlv_synchronize", "dlv_set_conv_timing", "dlv_load_weights", "dlv_segment", "dlv_ccl", "dlv_table_free",
+    "dlv_ccl_last_timing", "dlv_unet_forward", "dlv_op_conv3d", "dlv_op_deconv", "dlv_op_finalise",
+]
+
+_lib = None
+
+
+def load_library():
+    """dlopen the extension; raises DlvError (never falls back) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DlvError(f"{LIB_PATH} is missing - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       f"or `make -C delivr_cfos_b200/csrc`; there is no CPU fallback")
+    L = ctypes.CDLL(LIB_PATH)
+    P = ctypes.POINTER
+    L.dlv_abi_version.restype = ctypes.c_int
+    L.dlv_init.restype = ctypes.c_int
+    L.dlv_init.argtypes = [ctypes.c_int, P(c_vp)]
+    L.dlv_destroy.restype = None
+    L.dlv_destroy.argtypes = [c_vp]
+    L.dlv_last_error.restype = ctypes.c_char_p
+    L.dlv_last_error.argtypes = [c_vp]
+    L.dlv_launch_count.restype = c_i64
+    L.dlv_launch_count.argtypes = [c_vp]
+    L.dlv_stream.restype = c_vp
+    L.dlv_stream.argtypes = [c_vp]
+    L.dlv_synchronize.restype = ctypes.c_int
+    L.dlv_synchronize.argtypes = [c_vp]
+    L.dlv_set_conv_timing.restype = ctypes.c_int
+    L.dlv_set_conv_timing.argtypes = [c_vp, ctypes.c_int]
+    L.dlv_load_weights.restype = ctypes.c_int
+    L.dlv_load_weights.argtypes = [c_vp, ctypes.c_int, P(ctypes.c_char_p), P(c_vp), P(c_i64)]
+    L.dlv_segment.restype = ctypes.c_int
+    L.dlv_segment.argtypes = [c_vp, c_vp, P(SegParams), c_vp, c_vp, c_vp, P(SegStats)]
+    L.dlv_ccl.restype = ctypes.c_int
+    L.dlv_ccl.argtypes = [c_vp, c_vp, P(c_i64), ctypes.c_int, c_vp, P(P(Table))]
+    L.dlv_table_free.restype = None
+    L.dlv_table_free.argtypes = [P(Table)]
+    L.dlv_ccl_last_timing.restype = ctypes.c_int
+    L.dlv_ccl_last_timing.argtypes = [c_vp, P(ctypes.c_double), P(c_i64)]
+    L.dlv_unet_forward.restype = ctypes.c_int
+    L.dlv_unet_forward.argtypes = [c_vp, c_vp, ctypes.c_int, P(c_i32), c_vp]
+    L.dlv_op_conv3d.restype = ctypes.c_int
+    L.dlv_op_conv3d.argtypes = [c_vp, ctypes.c_char_p, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]
+    L.dlv_op_deconv.restype = ctypes.c_int
+    L.dlv_op_deconv.argtypes = [c_vp, ctypes.c_char_p, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp]
+    L.dlv_op_finalise.restype = ctypes.c_int
+    L.dlv_op_finalise.argtypes = [c_vp, c_vp, c_vp, P(c_i64), P(c_i64), c_f32, ctypes.c_int, c_i64, c_vp, c_vp]
+    if L.dlv_abi_version() != 1:
+        raise DlvError("libdelivr_b200.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+def _ptr(x):
+    """Device/host address of a torch tensor, numpy array or None."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        if not x.flags["C_CONTIGUOUS"]:
+            raise ValueError("array must be C-contiguous")
+        return x.ctypes.data
+    if hasattr(x, "data_ptr"):
+        if not x.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        return x.data_ptr()
+    return int(x)
+
+
+class Context:
+    """One GPU context (``dlv_ctx``).  Raises DlvError on any failure."""
+
+    def __init__(self, device=0):
+        self._L = load_library()
+        h = c_vp()
+        rc = self._L.dlv_init(int(device), ctypes.byref(h))
+        self._h = h
+        if rc != 0:
+            msg = self._L.dlv_last_error(h).decode() if h else "no CUDA device / dlv_init failed"
+            if h:
+                self._L.dlv_destroy(h)
+            self._h = None
+            raise DlvError(f"dlv_init({device}) failed ({rc}): {msg}")
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.dlv_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise DlvError(f"{what} failed ({rc}): {self._L.dlv_last_error(self._h).decode()}")
+
+    @property
+    def launches(self):
+        return int(self._L.dlv_launch_count(self._h))
+
+    def synchronize(self):
+        self._check(self._L.dlv_synchronize(self._h), "dlv_synchronize")
+
+    def set_conv_timing(self, enable):
+        self._check(self._L.dlv_set_conv_timing(self._h, int(bool(enable))), "dlv_set_conv_timing")
+
+    # ---- weights (inference.py:190-200,217-222)
+    def load_weights(self, state_dict):
+        """state_dict: mapping name -> array-like fp32 (torch tensors or numpy), checkpoint["state_dict"]."""
+        names, arrs = [], []
+        for k, v in state_dict.items():
+            a = v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)
+            names.append(k.encode())
+            arrs.append(np.ascontiguousarray(a, dtype=np.float32))
+        n = len(names)
+        c_names = (ctypes.c_char_p * n)(*names)
+        c_ptrs = (c_vp * n)(*[a.ctypes.data for a in arrs])
+        c_numel = (c_i64 * n)(*[a.size for a in arrs])
+        self._check(self._L.dlv_load_weights(self._h, n, c_names, c_ptrs, c_numel), "dlv_load_weights")
+
+    def load_checkpoint(self, path):
+        import torch
+        ck = torch.load(path, map_location="cpu", weights_only=True)
+        self.load_weights(ck["state_dict"])
+
+    # ---- segmentation
+    def segment(self, volume, shape_pad, shape_real, roi, binaries_out, overlap=0.5, tta=False, threshold=0.5,
+                erosion_iters=30, erosion_block_planes=0, blend_mode=0, window_batch=0, skip_empty=True,
+                flip_dim=None, avg_logits_out=None, sigmoid_out=None):
+        p = SegParams()
+        p.shape_pad[:] = [int(s) for s in shape_pad]
+        p.shape_real[:] = [int(s) for s in shape_real]
+        p.roi[:] = [int(s) for s in roi]
+        p.overlap, p.tta, p.threshold = float(overlap), int(bool(tta)), float(threshold)
+        p.erosion_iters, p.erosion_block_planes = int(erosion_iters), int(erosion_block_planes)
+        p.blend_mode, p.window_batch, p.skip_empty = int(blend_mode), int(window_batch), int(bool(skip_empty))
+        p.flip_dim = int(flip_dim or 0)
+        st = SegStats()
+        rc = self._L.dlv_segment(self._h, _ptr(volume), ctypes.byref(p), _ptr(binaries_out), _ptr(avg_logits_out),
+                                 _ptr(sigmoid_out), ctypes.byref(st))
+        self._check(rc, "dlv_segment")
+        return st.as_dict()
+
+    # ---- connected components (count_blobs.py:61,85)
+    def ccl(self, mask, shape, labels_out=None):
+        """-> dict(n, voxel_counts uint64[N+1], sums uint64[N+1,3], bounding_boxes int64[N+1,6], centroids f64[N+1,3])."""
+        shp = (c_i64 * 3)(*[int(s) for s in shape])
+        tp = ctypes.POINTER(Table)()
+        self._check(self._L.dlv_ccl(self._h, _ptr(mask), shp, 26, _ptr(labels_out), ctypes.byref(tp)), "dlv_ccl")
+        try:
+            t = tp.contents
+            n = int(t.n)
+            counts = np.ctypeslib.as_array(t.voxel_counts, shape=(n + 1,)).copy()
+            sums = np.ctypeslib.as_array(t.sums, shape=(n + 1, 3)).copy()
+            bbox = np.ctypeslib.as_array(t.bbox, shape=(n + 1, 6)).copy()
+        finally:
+            self._L.dlv_table_free(tp)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            # cc3d's centroid definition: sum(coord) / count, one fp64 divide (count_blobs.py:85)
+            cent = sums.astype(np.float64) / counts.astype(np.float64)[:, None]
+        return {"n": n, "voxel_counts": counts, "sums": sums, "bounding_boxes": bbox, "centroids": cent}
+
+    def ccl_last_timing(self):
+        ms, ln = ctypes.c_double(), c_i64()
+        self._check(self._L.dlv_ccl_last_timing(self._h, ctypes.byref(ms), ctypes.byref(ln)), "dlv_ccl_last_timing")
+        return ms.value, ln.value
+
+    # ---- operator-level entry points (device pointers)
+    def unet_forward(self, windows_u16, roi, logits_out):
+        nwin = int(windows_u16.shape[0])
+        r = (c_i32 * 3)(*[int(s) for s in roi])
+        self._check(self._L.dlv_unet_forward(self._h, _ptr(windows_u16), nwin, r, _ptr(logits_out)), "dlv_unet_forward")
+
+    def op_conv3d(self, layer, x, y_out, stats_out):
+        n, _, D, H, W = [int(s) for s in x.shape]
+        self._check(self._L.dlv_op_conv3d(self._h, layer.encode(), _ptr(x), n, D, H, W, _ptr(y_out), _ptr(stats_out)),
+                    "dlv_op_conv3d")
+
+    def op_deconv(self, upcat, x, y_out):
+        n, _, D, H, W = [int(s) for s in x.shape]
+        self._check(self._L.dlv_op_deconv(self._h, upcat.encode(), _ptr(x), n, D, H, W, _ptr(y_out)), "dlv_op_deconv")
+
+    def op_finalise(self, avg_logits, volume, shape_pad, shape_real, binaries_out, threshold=0.5, erosion_iters=30,
+                    erosion_block_planes=0, sigmoid_out=None):
+        sp = (c_i64 * 3)(*[int(s) for s in shape_pad])
+        sr = (c_i64 * 3)(*[int(s) for s in shape_real])
+        self._check(self._L.dlv_op_finalise(self._h, _ptr(avg_logits), _ptr(volume), sp, sr, float(threshold),
+                                            int(erosion_iters), int(erosion_block_planes), _ptr(binaries_out),
+                                            _ptr(sigmoid_out)), "dlv_op_finalise")

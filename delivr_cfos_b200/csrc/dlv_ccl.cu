@@ -1,0 +1,424 @@
+// dlv_ccl.cu - 26-connected 3-D connected-component labelling + per-component statistics on the GPU.
+//
+// Replaces cc3d.connected_components(bin_img, return_N=True) and cc3d.statistics(labels) of the reference
+// (count_blobs.py:61,64,85; connected-components-3d 3.12.3).  Output contract: labels 1..N numbered by each
+// component's first voxel in C-order raster scan; table rows 0..N with exact integer counts / coordinate sums /
+// inclusive bounding boxes.
+//
+// Algorithm (HBM-bound integer work, no tensor cores):
+//   P1 init      read the uint8 mask once, emit a 1-bit/voxel bitmask and the label array (0 for background,
+//                1 + linear index of the start of the voxel's x-run inside its 32-voxel word otherwise).
+//                This is the only pass that touches every label (4 B/voxel write).
+//   P2 merge     one thread per bitmask word: for every x-run, union (lock-free atomicMin union-find, root =
+//                smallest linear index = first voxel in raster order) with the runs it touches in the 4 raster-
+//                predecessor rows (y-1 | z-1,y-1 | z-1,y | z-1,y+1; x-range widened by 1) and the previous word.
+//   P3 compress  every run start resolves its root; roots are flagged in a second bitmask.
+//   P4 scan      exclusive prefix sum over popcounts of the root bitmask -> rank of every root = final label.
+//   P5 relabel   every run looks up its root's rank, rewrites its voxels, and reduces count / sum z,y,x / bbox
+//                once per run (closed-form arithmetic series along x) with 64-bit atomics.
+#include <limits.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "dlv_common.cuh"
+#include "dlv_internal.h"
+
+namespace dlv {
+
+struct CclGeom {
+    int64_t Z, Y, X;
+    int64_t rows;      // Z*Y
+    int W;             // bitmask words per row
+};
+
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) { return __ldcg(p); }
+
+// labels are 1-based voxel indices; L[l-1] is the parent of l
+__device__ __forceinline__ uint32_t uf_find(uint32_t* L, uint32_t l) {
+    uint32_t p;
+    while ((p = ld_cg_u32(L + (l - 1))) != l) l = p;
+    return l;
+}
+__device__ __forceinline__ void uf_union(uint32_t* L, uint32_t a, uint32_t b) {
+    while (true) {
+        a = uf_find(L, a);
+        b = uf_find(L, b);
+        if (a == b) return;
+        if (a < b) { uint32_t t = a; a = b; b = t; }
+        const uint32_t old = atomicMin(L + (a - 1), b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+struct BgBox { int zmin, zmax, ymin, ymax, xmin, xmax; };
+
+// ---- P1: mask -> bitmask + initial labels (+ bounding box of the background for table row 0)
+// One warp handles 128 consecutive voxels of a row per iteration (4 per lane, 16 B label stores).
+__global__ void ccl_init_kernel(const uint8_t* __restrict__ mask, CclGeom g, uint32_t* __restrict__ bits,
+                                uint32_t* __restrict__ L, int* __restrict__ bgbox) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    const int segs = (g.W + 3) / 4;                       // 128-voxel segments per row
+    const int64_t total = g.rows * segs;
+    const bool vec = (g.X % 4) == 0;
+    BgBox bb = {INT_MAX, -1, INT_MAX, -1, INT_MAX, -1};
+    for (int64_t it = warp_global; it < total; it += nwarps) {
+        const int64_t r = it / segs;
+        const int sg = static_cast<int>(it - r * segs);
+        const int64_t x0 = static_cast<int64_t>(sg) * 128 + lane * 4;
+        const int64_t base = r * g.X;
+        uint32_t nib = 0;
+        if (vec) {
+            if (x0 < g.X) {
+                const uint32_t m = *reinterpret_cast<const uint32_t*>(mask + base + x0);
+                nib = ((m & 0xFFu) ? 1u : 0u) | ((m & 0xFF00u) ? 2u : 0u) | ((m & 0xFF0000u) ? 4u : 0u) | ((m & 0xFF000000u) ? 8u : 0u);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (x0 + j < g.X && mask[base + x0 + j]) nib |= 1u << j;
+        }
+        // assemble the 32-bit word of this lane's 8-lane group
+        uint32_t word = nib << (4 * (lane & 7));
+        word |= __shfl_xor_sync(0xffffffffu, word, 1);
+        word |= __shfl_xor_sync(0xffffffffu, word, 2);
+        word |= __shfl_xor_sync(0xffffffffu, word, 4);
+        const int wi = sg * 4 + (lane >> 3);
+        if ((lane & 7) == 0 && wi < g.W) bits[r * g.W + wi] = word;
+        if (x0 < g.X) {
+            const uint32_t wbase = static_cast<uint32_t>(base + static_cast<int64_t>(wi) * 32);   // 0-based index of bit 0
+            uint32_t lab[4];
+            int nbg = 0, bx0 = INT_MAX, bx1 = -1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int b = 4 * (lane & 7) + j;
+                if ((word >> b) & 1u) {
+                    const uint32_t zeros_below = ~word & ((1u << b) - 1u);
+                    const int s = zeros_below ? (32 - __clz(zeros_below)) : 0;
+                    lab[j] = wbase + s + 1u;
+                } else {
+                    lab[j] = 0u;
+                    if (x0 + j < g.X) { ++nbg; bx0 = min(bx0, static_cast<int>(x0 + j)); bx1 = max(bx1, static_cast<int>(x0 + j)); }
+                }
+            }
+            if (vec) {
+                *reinterpret_cast<uint4*>(L + base + x0) = make_uint4(lab[0], lab[1], lab[2], lab[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (x0 + j < g.X) L[base + x0 + j] = lab[j];
+            }
+            if (nbg) {
+                const int z = static_cast<int>(r / g.Y), y = static_cast<int>(r - static_cast<int64_t>(z) * g.Y);
+                bb.zmin = min(bb.zmin, z); bb.zmax = max(bb.zmax, z);
+                bb.ymin = min(bb.ymin, y); bb.ymax = max(bb.ymax, y);
+                bb.xmin = min(bb.xmin, bx0); bb.xmax = max(bb.xmax, bx1);
+            }
+        }
+    }
+    // warp-reduce the background box, one set of atomics per warp
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        bb.zmin = min(bb.zmin, __shfl_xor_sync(0xffffffffu, bb.zmin, o)); bb.zmax = max(bb.zmax, __shfl_xor_sync(0xffffffffu, bb.zmax, o));
+        bb.ymin = min(bb.ymin, __shfl_xor_sync(0xffffffffu, bb.ymin, o)); bb.ymax = max(bb.ymax, __shfl_xor_sync(0xffffffffu, bb.ymax, o));
+        bb.xmin = min(bb.xmin, __shfl_xor_sync(0xffffffffu, bb.xmin, o)); bb.xmax = max(bb.xmax, __shfl_xor_sync(0xffffffffu, bb.xmax, o));
+    }
+    if (lane == 0 && bb.zmax >= 0) {
+        atomicMin(bgbox + 0, bb.zmin); atomicMax(bgbox + 1, bb.zmax);
+        atomicMin(bgbox + 2, bb.ymin); atomicMax(bgbox + 3, bb.ymax);
+        atomicMin(bgbox + 4, bb.xmin); atomicMax(bgbox + 5, bb.xmax);
+    }
+}
+
+// iterate the runs (maximal groups of consecutive set bits) of a 64-bit pattern
+#define DLV_FOR_RUNS64(pattern, a, len)                                                    \
+    for (unsigned long long _m = (pattern); _m;)                                           \
+        for (int a = __ffsll(static_cast<long long>(_m)) - 1,                              \
+                 len = (~(_m >> a) == 0ull) ? (64 - a) : (__ffsll(static_cast<long long>(~(_m >> a))) - 1), _once = 1; \
+             _once; _once = 0, _m &= ~((len >= 64 ? ~0ull : ((1ull << len) - 1ull)) << a))
+
+// ---- P2: unions between touching runs
+__global__ void ccl_merge_kernel(CclGeom g, const uint32_t* __restrict__ bits, uint32_t* __restrict__ L) {
+    const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= g.rows * g.W) return;
+    const int64_t r = t / g.W;
+    const int w = static_cast<int>(t - r * g.W);
+    const uint32_t cur = bits[t];
+    if (!cur) return;
+    const int64_t z = r / g.Y, y = r - z * g.Y;
+    const uint32_t vbase = static_cast<uint32_t>(r * g.X + static_cast<int64_t>(w) * 32) + 1u;   // label of bit 0
+    // same row, previous word
+    if ((cur & 1u) && w > 0 && (bits[t - 1] >> 31)) uf_union(L, vbase, vbase - 1u);
+    // raster-predecessor rows
+    int64_t nrows[4];
+    int nn = 0;
+    if (y > 0) nrows[nn++] = r - 1;
+    if (z > 0) {
+        if (y > 0) nrows[nn++] = r - g.Y - 1;
+        nrows[nn++] = r - g.Y;
+        if (y + 1 < g.Y) nrows[nn++] = r - g.Y + 1;
+    }
+    for (int k = 0; k < nn; ++k) {
+        const uint32_t* nb = bits + nrows[k] * g.W;
+        const uint32_t c = nb[w];
+        const uint32_t p = (w > 0) ? nb[w - 1] : 0u;
+        const uint32_t q = (w + 1 < g.W) ? nb[w + 1] : 0u;
+        // bit i of comb <-> neighbour-row voxel x = w*32 + i - 1, i in [0, 34)
+        const unsigned long long comb = (static_cast<unsigned long long>(c) << 1) | (p >> 31) | (static_cast<unsigned long long>(q & 1u) << 33);
+        if (!comb) continue;
+        const uint32_t nbase = static_cast<uint32_t>(nrows[k] * g.X + static_cast<int64_t>(w) * 32);   // label of neighbour bit i is nbase + i
+        DLV_FOR_RUNS64(static_cast<unsigned long long>(cur), a, len) {
+            // run [a, a+len) of the current word touches neighbour bits [a, a+len+2) of comb
+            const unsigned long long span = ((len + 2 >= 64) ? ~0ull : ((1ull << (len + 2)) - 1ull)) << a;
+            DLV_FOR_RUNS64(comb & span, i, ilen) {
+                (void)ilen;
+                uf_union(L, vbase + a, nbase + i);
+            }
+        }
+    }
+}
+
+// ---- P3: resolve roots per run, flag roots
+__global__ void ccl_compress_kernel(CclGeom g, const uint32_t* __restrict__ bits, uint32_t* __restrict__ L,
+                                    uint32_t* __restrict__ rootbits) {
+    const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= g.rows * g.W) return;
+    const uint32_t cur = bits[t];
+    uint32_t rb = 0;
+    if (cur) {
+        const int64_t r = t / g.W;
+        const int w = static_cast<int>(t - r * g.W);
+        const int64_t vb0 = r * g.X + static_cast<int64_t>(w) * 32;     // 0-based index of bit 0
+        DLV_FOR_RUNS64(static_cast<unsigned long long>(cur), a, len) {
+            const uint32_t lbl = static_cast<uint32_t>(vb0 + a) + 1u;
+            const uint32_t root = uf_find(L, lbl);
+            if (root == lbl) rb |= 1u << a;
+            else L[vb0 + a] = root;          // shortcut; only run starts are ever traversed
+        }
+    }
+    rootbits[t] = rb;
+}
+
+// ---- P4: exclusive scan of popcounts (three small kernels)
+constexpr int kScanBlock = 1024;
+__global__ void scan_block_sums_kernel(const uint32_t* __restrict__ rootbits, int64_t nwords, uint32_t* __restrict__ bsum) {
+    __shared__ uint32_t sh[32];
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * kScanBlock + threadIdx.x;
+    uint32_t v = (i < nwords) ? __popc(rootbits[i]) : 0u;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = sh[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) bsum[blockIdx.x] = v;
+    }
+}
+__device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t v, uint32_t* sh, uint32_t* total) {
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) sh[wp] = inc;
+    __syncthreads();
+    if (wp == 0) {
+        uint32_t s = sh[lane], si = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, si, o);
+            if (lane >= o) si += n;
+        }
+        sh[lane] = si - s;
+        if (lane == 31) *total = si;
+    }
+    __syncthreads();
+    const uint32_t r = sh[wp] + inc - v;
+    __syncthreads();
+    return r;
+}
+__global__ void scan_of_block_sums_kernel(uint32_t* __restrict__ bsum, int64_t nb, uint32_t* __restrict__ n_out) {
+    __shared__ uint32_t sh[32];
+    __shared__ uint32_t tot;
+    uint32_t carry = 0;
+    for (int64_t base = 0; base < nb; base += kScanBlock) {
+        const int64_t i = base + threadIdx.x;
+        const uint32_t v = (i < nb) ? bsum[i] : 0u;
+        const uint32_t e = block_excl_scan_1024(v, sh, &tot);
+        if (i < nb) bsum[i] = carry + e;
+        carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_out = carry;
+}
+__global__ void scan_apply_kernel(const uint32_t* __restrict__ rootbits, int64_t nwords, const uint32_t* __restrict__ bsum,
+                                  uint32_t* __restrict__ wprefix) {
+    __shared__ uint32_t sh[32];
+    __shared__ uint32_t tot;
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * kScanBlock + threadIdx.x;
+    const uint32_t v = (i < nwords) ? __popc(rootbits[i]) : 0u;
+    const uint32_t e = block_excl_scan_1024(v, sh, &tot);
+    if (i < nwords) wprefix[i] = bsum[blockIdx.x] + e;
+}
+
+// ---- P5: final labels + statistics, one reduction per x-run
+__global__ void ccl_relabel_stats_kernel(CclGeom g, const uint32_t* __restrict__ bits, uint32_t* __restrict__ L,
+                                         const uint32_t* __restrict__ rootbits, const uint32_t* __restrict__ wprefix,
+                                         unsigned long long* __restrict__ cnt, unsigned long long* __restrict__ sums,
+                                         int* __restrict__ bbox) {
+    const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= g.rows * g.W) return;
+    const uint32_t cur = bits[t];
+    if (!cur) return;
+    const int64_t r = t / g.W;
+    const int w = static_cast<int>(t - r * g.W);
+    const int z = static_cast<int>(r / g.Y), y = static_cast<int>(r - static_cast<int64_t>(z) * g.Y);
+    const int64_t vb0 = r * g.X + static_cast<int64_t>(w) * 32;
+    DLV_FOR_RUNS64(static_cast<unsigned long long>(cur), a, len) {
+        const uint32_t lbl = static_cast<uint32_t>(vb0 + a) + 1u;
+        const uint32_t root = ((rootbits[t] >> a) & 1u) ? lbl : L[vb0 + a];
+        const int64_t ri = static_cast<int64_t>(root) - 1;
+        const int64_t rr = ri / g.X;
+        const int rx = static_cast<int>(ri - rr * g.X);
+        const int64_t rw = rr * g.W + (rx >> 5);
+        const uint32_t rank = wprefix[rw] + __popc(rootbits[rw] & ((1u << (rx & 31)) - 1u)) + 1u;
+        for (int j = 0; j < len; ++j) L[vb0 + a + j] = rank;
+        const int xa = w * 32 + a, xb = xa + len - 1;
+        atomicAdd(cnt + rank, static_cast<unsigned long long>(len));
+        atomicAdd(sums + 3ull * rank + 0, static_cast<unsigned long long>(z) * len);
+        atomicAdd(sums + 3ull * rank + 1, static_cast<unsigned long long>(y) * len);
+        atomicAdd(sums + 3ull * rank + 2, static_cast<unsigned long long>(xa + xb) * len / 2ull);
+        int* b = bbox + 6ull * rank;
+        atomicMin(b + 0, z); atomicMax(b + 1, z);
+        atomicMin(b + 2, y); atomicMax(b + 3, y);
+        atomicMin(b + 4, xa); atomicMax(b + 5, xb);
+    }
+}
+
+__global__ void bbox_init_kernel(int* __restrict__ bbox, int64_t rows, int Z, int Y, int X) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    int* b = bbox + 6 * i;
+    b[0] = Z; b[1] = -1; b[2] = Y; b[3] = -1; b[4] = X; b[5] = -1;
+}
+
+static unsigned nblocks(int64_t n, int bs) { return static_cast<unsigned>((n + bs - 1) / bs); }
+
+int ccl_run(Ctx* ctx, const uint8_t* mask, const int64_t shape[3], uint32_t* L, dlv_table** table_out) {
+    *table_out = nullptr;
+    CclGeom g;
+    g.Z = shape[0]; g.Y = shape[1]; g.X = shape[2];
+    if (g.Z < 0 || g.Y < 0 || g.X < 0) { set_error(ctx, "dlv_ccl: negative shape"); return DLV_ERR_ARG; }
+    const int64_t n = g.Z * g.Y * g.X;
+    if (n >= 0xFFFFFFFFLL || g.Z > INT_MAX || g.Y > INT_MAX || g.X > INT_MAX) {
+        set_error(ctx, "dlv_ccl: %lld voxels exceed the 32-bit label space of one slab; split along z", (long long)n);
+        return DLV_ERR_UNSUPPORTED;
+    }
+    g.rows = g.Z * g.Y;
+    g.W = static_cast<int>((g.X + 31) / 32);
+    const int64_t nwords = g.rows * g.W;
+    dlv_table* T = static_cast<dlv_table*>(calloc(1, sizeof(dlv_table)));
+    uint32_t N = 0;
+    int bg[6] = {static_cast<int>(g.Z), -1, static_cast<int>(g.Y), -1, static_cast<int>(g.X), -1};
+    uint32_t *bits = nullptr, *rootbits = nullptr, *wprefix = nullptr, *bsum = nullptr, *n_dev = nullptr;
+    int* bg_dev = nullptr;
+    unsigned long long *cnt = nullptr, *sums = nullptr;
+    int* bbox = nullptr;
+    int rc = 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr;
+    float ms_a = 0.f, ms_b = 0.f;
+    int64_t launches = 0;
+#define CK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error(ctx, "dlv_ccl: %s: %s", #expr, cudaGetErrorString(_e)); rc = DLV_ERR_CUDA; goto done; } } while (0)
+    if (n > 0) {
+        const int64_t nb = (nwords + kScanBlock - 1) / kScanBlock;
+        CK(cudaMalloc(&bits, nwords * 4));
+        CK(cudaMalloc(&rootbits, nwords * 4));
+        CK(cudaMalloc(&wprefix, nwords * 4));
+        CK(cudaMalloc(&bsum, nb * 4));
+        CK(cudaMalloc(&n_dev, 4));
+        CK(cudaMalloc(&bg_dev, 6 * sizeof(int)));
+        CK(cudaMemcpyAsync(bg_dev, bg, sizeof(bg), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2)); CK(cudaEventCreate(&e3));
+        CK(cudaEventRecord(e0, ctx->stream));
+        {
+            const int64_t total_warps = g.rows * ((g.W + 3) / 4);
+            const unsigned grid = static_cast<unsigned>(std::min<int64_t>((total_warps + 7) / 8, static_cast<int64_t>(ctx->num_sms) * 32));
+            ccl_init_kernel<<<grid, 256, 0, ctx->stream>>>(mask, g, bits, L, bg_dev);
+        }
+        ccl_merge_kernel<<<nblocks(nwords, 256), 256, 0, ctx->stream>>>(g, bits, L);
+        ccl_compress_kernel<<<nblocks(nwords, 256), 256, 0, ctx->stream>>>(g, bits, L, rootbits);
+        scan_block_sums_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, ctx->stream>>>(rootbits, nwords, bsum);
+        scan_of_block_sums_kernel<<<1, kScanBlock, 0, ctx->stream>>>(bsum, nb, n_dev);
+        scan_apply_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, ctx->stream>>>(rootbits, nwords, bsum, wprefix);
+        launches += 6;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(e1, ctx->stream));
+        CK(cudaMemcpyAsync(&N, n_dev, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(bg, bg_dev, sizeof(bg), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    {
+        const size_t rows = static_cast<size_t>(N) + 1;
+        T->n = N;
+        T->voxel_counts = static_cast<uint64_t*>(calloc(rows, sizeof(uint64_t)));
+        T->sums = static_cast<uint64_t*>(calloc(rows * 3, sizeof(uint64_t)));
+        T->bbox = static_cast<int64_t*>(calloc(rows * 6, sizeof(int64_t)));
+        if (!T->voxel_counts || !T->sums || !T->bbox) { set_error(ctx, "dlv_ccl: host table allocation failed"); rc = DLV_ERR_ARG; goto done; }
+        std::vector<int> hb(rows * 6);
+        if (n > 0) {
+            CK(cudaMalloc(&cnt, rows * 8));
+            CK(cudaMalloc(&sums, rows * 24));
+            CK(cudaMalloc(&bbox, rows * 24));
+            CK(cudaMemsetAsync(cnt, 0, rows * 8, ctx->stream));
+            CK(cudaMemsetAsync(sums, 0, rows * 24, ctx->stream));
+            CK(cudaEventRecord(e2, ctx->stream));
+            bbox_init_kernel<<<nblocks(rows, 256), 256, 0, ctx->stream>>>(bbox, rows, static_cast<int>(g.Z), static_cast<int>(g.Y), static_cast<int>(g.X));
+            ccl_relabel_stats_kernel<<<nblocks(nwords, 256), 256, 0, ctx->stream>>>(g, bits, L, rootbits, wprefix, cnt, sums, bbox);
+            launches += 2;
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(e3, ctx->stream));
+            CK(cudaMemcpyAsync(T->voxel_counts, cnt, rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(T->sums, sums, rows * 24, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(hb.data(), bbox, rows * 24, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            CK(cudaEventElapsedTime(&ms_a, e0, e1));
+            CK(cudaEventElapsedTime(&ms_b, e2, e3));
+        } else {
+            for (size_t i = 0; i < rows; ++i) { hb[6 * i] = g.Z; hb[6 * i + 1] = -1; hb[6 * i + 2] = g.Y; hb[6 * i + 3] = -1; hb[6 * i + 4] = g.X; hb[6 * i + 5] = -1; }
+        }
+        for (size_t i = 0; i < rows * 6; ++i) T->bbox[i] = hb[i];
+        // row 0 = background: everything that is not foreground (exact integer identities)
+        uint64_t fg = 0, sz = 0, sy = 0, sx = 0;
+        for (size_t i = 1; i < rows; ++i) { fg += T->voxel_counts[i]; sz += T->sums[3 * i]; sy += T->sums[3 * i + 1]; sx += T->sums[3 * i + 2]; }
+        const uint64_t uz = g.Z, uy = g.Y, ux = g.X;
+        T->voxel_counts[0] = static_cast<uint64_t>(n) - fg;
+        T->sums[0] = (uz ? uy * ux * (uz * (uz - 1) / 2) : 0) - sz;
+        T->sums[1] = (uy ? uz * ux * (uy * (uy - 1) / 2) : 0) - sy;
+        T->sums[2] = (ux ? uz * uy * (ux * (ux - 1) / 2) : 0) - sx;
+        for (int k = 0; k < 6; ++k) T->bbox[k] = bg[k];
+    }
+    ctx->ccl_ms = ms_a + ms_b;
+    ctx->ccl_launches = launches;
+    ctx->launches += launches;
+done:
+#undef CK
+    cudaFree(bits); cudaFree(rootbits); cudaFree(wprefix); cudaFree(bsum); cudaFree(n_dev); cudaFree(bg_dev);
+    cudaFree(cnt); cudaFree(sums); cudaFree(bbox);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (e2) cudaEventDestroy(e2);
+    if (e3) cudaEventDestroy(e3);
+    if (rc) { dlv_table_free(T); return rc; }
+    *table_out = T;
+    return 0;
+}
+
+}  // namespace dlv

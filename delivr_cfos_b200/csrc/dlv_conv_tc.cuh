@@ -1,0 +1,244 @@
+// dlv_conv_tc.cuh - the tcgen05/TMEM implicit-GEMM kernel behind every dense contraction of the U-Net.
+//
+// Replaces the cuDNN conv3d / conv_transpose3d calls issued from predictor(window_data)
+// (inference/sliding_window_inferer.py:222; MONAI BasicUNet instantiated at inference/inference.py:190-197).
+//
+// GEMM view (per work item):  D[128*T positions][NBLK couts] += A[positions][16 cin] * W[16 cin][NBLK]
+// summed over KB cin blocks and NTAPS taps.
+//   * A operand: the zero-haloed position-linear activation layout (dlv_internal.h, struct Level) is
+//     staged once per cin block by TMA bulk copies as [dz run][k chunk][RL positions][8 ch] - which IS the
+//     canonical K-major no-swizzle UMMA layout (8 positions x 16 B core matrices, SBO 128 B, LBO = RL*16 B).
+//     A tap (dz,dy,dx) is therefore nothing but a +16 B * (dy*Xp + dx) bump of the descriptor start address
+//     inside the dz run: 27 taps re-use one staged tile, nothing is re-fetched or im2col'ed.
+//   * B operand: weights pre-packed on the host into the same canonical layout, one bulk copy per stage.
+//   * D: fp32 accumulators in TMEM, T tiles x NBLK columns, double-buffered (2 x 256 columns) so the
+//     epilogue of item i overlaps the MMAs of item i+1.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warps 2-5 = epilogue
+// (TMEM -> registers -> bf16 global stores + InstanceNorm partial sums).
+#pragma once
+#include "dlv_common.cuh"
+
+namespace dlv {
+
+constexpr int kConvThreads = 192;
+constexpr int kConvStages = 2;
+constexpr int kTmemCols = 512;
+constexpr uint32_t kSmemLimit = 232448;   // 227 KB opt-in maximum per CTA
+
+enum ConvMode { kModeConvStats = 0, kModeDeconvScatter = 1 };
+
+struct ConvArgs {
+    const __nv_bfloat16* in0;   // first cin chunks (skip tensor for concatenated inputs)
+    const __nv_bfloat16* in1;   // remaining chunks (upsampled tensor) or nullptr
+    int nch0;                   // chunks held by in0
+    int64_t inS;                // positions per chunk of the inputs
+    int in_guard;
+    const __nv_bfloat16* w;     // packed weights [KB][NB][NTAPS][2][NBLK][8]
+    __nv_bfloat16* out;         // raw conv output (mode 0) / upsampled activation (mode 1)
+    int64_t outS;
+    int out_guard;
+    double* stats;              // mode 0: [nwin][cout][2] sum, sum of squares
+    const float* bias;          // mode 1: [cout]
+    int Z, Y, X, Yp, Xp, YpXp, Vp;
+    int64_t NP;                 // nwin * Vp positions to cover
+    int KB, NB, T, RL, H;
+    int nitems, items_per_cta;
+    uint32_t a_bytes, w_bytes, stage_bytes;
+    int cout;
+    int oYp, oXp, oVp;          // mode 1: geometry of the finer output level
+};
+
+template <int NBLK, int NTAPS, int MODE>
+__global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int NRUNS = (NTAPS == 27) ? 3 : 1;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kConvStages * p.stage_bytes);
+    uint64_t* full = bars;                       // [stages] TMA -> MMA
+    uint64_t* empty = bars + kConvStages;        // [stages] MMA -> TMA
+    uint64_t* tfull = bars + 2 * kConvStages;    // [2] MMA -> epilogue
+    uint64_t* tempty = tfull + 2;                // [2] epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kConvStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int item0 = blockIdx.x * p.items_per_cta;
+    const int item1 = min(p.nitems, item0 + p.items_per_cta);
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        int stage = 0; uint32_t phase = 0;
+        for (int item = item0; item < item1; ++item) {
+            const int g = item / p.NB, nb = item - g * p.NB;
+            const int64_t s = static_cast<int64_t>(g) * p.T * 128;
+            for (int kb = 0; kb < p.KB; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* st = smem + stage * p.stage_bytes;
+                if (lane == 0) mbar_arrive_expect_tx(&full[stage], p.a_bytes + p.w_bytes);
+                __syncwarp();
+                if (lane == 0) {
+                    const __nv_bfloat16* wsrc = p.w + (static_cast<int64_t>(kb) * p.NB + nb) * (p.w_bytes / 2);
+                    tma_bulk_g2s(st + p.a_bytes, wsrc, p.w_bytes, &full[stage]);
+                } else if (lane <= NRUNS * 2) {
+                    const int c = lane - 1, d = c >> 1, kc = c & 1;
+                    const int chunk = kb * 2 + kc;
+                    const __nv_bfloat16* base = (chunk < p.nch0) ? p.in0 + static_cast<int64_t>(chunk) * p.inS * 8
+                                                                 : p.in1 + static_cast<int64_t>(chunk - p.nch0) * p.inS * 8;
+                    const int64_t dzoff = (NTAPS == 27) ? static_cast<int64_t>(d - 1) * p.YpXp : 0;
+                    const int64_t pos = p.in_guard + s + dzoff - p.H;
+                    tma_bulk_g2s(st + static_cast<size_t>(c) * p.RL * 16, base + pos * 8, p.RL * 16, &full[stage]);
+                }
+                if (++stage == kConvStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (single thread)
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16_m128(NBLK);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int item = item0; item < item1; ++item, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t dcol = tmem_base + buf * 256;
+                for (int kb = 0; kb < p.KB; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(smem + stage * p.stage_bytes);
+                    const uint32_t w_base = a_base + p.a_bytes;
+#pragma unroll 1
+                    for (int tap = 0; tap < NTAPS; ++tap) {
+                        int d = 0, off = 0;
+                        if (NTAPS == 27) {
+                            const int kz = tap / 9, ky = (tap / 3) % 3, kx = tap % 3;
+                            d = kz;
+                            off = p.H + (ky - 1) * p.Xp + (kx - 1);
+                        }
+                        const uint32_t a_tap = a_base + (static_cast<uint32_t>(d * 2) * p.RL + off) * 16;
+                        const uint64_t bdesc = umma_desc_kmajor_noswz(w_base + tap * (2 * NBLK * 16), NBLK * 16, 128);
+                        const uint32_t acc = (kb | tap) ? 1u : 0u;
+                        for (int t = 0; t < p.T; ++t) {
+                            const uint64_t adesc = umma_desc_kmajor_noswz(a_tap + t * 2048, p.RL * 16, 128);
+                            umma_bf16(dcol + t * NBLK, adesc, bdesc, idesc, acc);
+                        }
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == kConvStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull[buf]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------ epilogue (4 warps = 4 TMEM lane quadrants)
+        const int q = warp & 3;
+        int it = 0;
+        int cur_key = -1;           // win * NB + nb of the running statistics
+        double run_s[NBLK / 32], run_q[NBLK / 32];
+#pragma unroll
+        for (int h = 0; h < NBLK / 32; ++h) { run_s[h] = 0.0; run_q[h] = 0.0; }
+        auto flush = [&]() {
+            if (MODE == kModeConvStats && cur_key >= 0) {
+                const int win = cur_key / p.NB, nb = cur_key - win * p.NB;
+#pragma unroll
+                for (int h = 0; h < NBLK / 32; ++h) {
+                    double* dst = p.stats + (static_cast<int64_t>(win) * p.cout + nb * NBLK + h * 32 + lane) * 2;
+                    atomicAdd(dst, run_s[h]);
+                    atomicAdd(dst + 1, run_q[h]);
+                    run_s[h] = 0.0; run_q[h] = 0.0;
+                }
+            }
+        };
+        for (int item = item0; item < item1; ++item, ++it) {
+            const int g = item / p.NB, nb = item - g * p.NB;
+            const int64_t s = static_cast<int64_t>(g) * p.T * 128;
+            const int buf = it & 1;
+            mbar_wait(&tfull[buf], (it >> 1) & 1);
+            tc_fence_after();
+            for (int t = 0; t < p.T; ++t) {
+                const int64_t P = s + t * 128 + q * 32 + lane;
+                // position -> (win, zp, yp, xp); interior test
+                const int win = static_cast<int>(P / p.Vp);
+                const int pp = static_cast<int>(P - static_cast<int64_t>(win) * p.Vp);
+                const int zp = pp / p.YpXp;
+                const int rr = pp - zp * p.YpXp;
+                const int yp = rr / p.Xp;
+                const int xp = rr - yp * p.Xp;
+                const bool valid = (P < p.NP) && zp >= 1 && zp <= p.Z && yp >= 1 && yp <= p.Y && xp >= 1;
+                const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+                if (vmask == 0) continue;   // warp-uniform: 32 halo positions, nothing to store
+                if (MODE == kModeConvStats) {
+                    const int w0 = __shfl_sync(0xffffffffu, win, __ffs(vmask) - 1);
+                    const int key = w0 * p.NB + nb;
+                    if (key != cur_key) { flush(); cur_key = key; }
+                }
+#pragma unroll
+                for (int h = 0; h < NBLK / 32; ++h) {
+                    float v[32];
+                    tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 256 + t * NBLK + h * 32, v);
+                    if (MODE == kModeConvStats) {
+                        if (valid) {
+                            __nv_bfloat16* o = p.out + (static_cast<int64_t>(nb * (NBLK / 8) + h * 4) * p.outS + p.out_guard + P) * 8;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                uint4 u;
+                                u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                                u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                                u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                                u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                                *reinterpret_cast<uint4*>(o + static_cast<int64_t>(j) * p.outS * 8) = u;
+                            }
+                        }
+                        float sq[32];
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) { v[c] = valid ? v[c] : 0.f; sq[c] = v[c] * v[c]; }
+                        run_s[h] += static_cast<double>(warp_transpose_sum32(v));
+                        run_q[h] += static_cast<double>(warp_transpose_sum32(sq));
+                    } else {
+                        if (valid) {
+                            const int NBc = p.cout / NBLK;
+                            const int abc = nb / NBc, cob = nb - abc * NBc;
+                            const int oz = 2 * (zp - 1) + (abc >> 2) + 1;
+                            const int oy = 2 * (yp - 1) + ((abc >> 1) & 1) + 1;
+                            const int ox = 2 * (xp - 1) + (abc & 1) + 1;
+                            const int64_t Po = static_cast<int64_t>(win) * p.oVp + (static_cast<int64_t>(oz) * p.oYp + oy) * p.oXp + ox;
+                            const float* bs = p.bias + cob * NBLK + h * 32;
+                            __nv_bfloat16* o = p.out + (static_cast<int64_t>(cob * (NBLK / 8) + h * 4) * p.outS + p.out_guard + Po) * 8;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                uint4 u;
+                                u.x = pack_bf16x2(v[8 * j + 0] + __ldg(bs + 8 * j + 0), v[8 * j + 1] + __ldg(bs + 8 * j + 1));
+                                u.y = pack_bf16x2(v[8 * j + 2] + __ldg(bs + 8 * j + 2), v[8 * j + 3] + __ldg(bs + 8 * j + 3));
+                                u.z = pack_bf16x2(v[8 * j + 4] + __ldg(bs + 8 * j + 4), v[8 * j + 5] + __ldg(bs + 8 * j + 5));
+                                u.w = pack_bf16x2(v[8 * j + 6] + __ldg(bs + 8 * j + 6), v[8 * j + 7] + __ldg(bs + 8 * j + 7));
+                                *reinterpret_cast<uint4*>(o + static_cast<int64_t>(j) * p.outS * 8) = u;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[buf]);
+        }
+        flush();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+}  // namespace dlv

@@ -1,0 +1,119 @@
+// dlv_internal.h - host-side structures shared by the translation units of libdelivr_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/delivr_b200.h"
+
+namespace dlv {
+
+typedef __nv_bfloat16 bf16;
+
+// Geometry of one U-Net resolution level for a batch of windows.
+//
+// Activations live in a zero-haloed, channel-chunked, position-linear layout
+//     A[chunk = C/8][S positions][8 channels]   (bf16, 16 B per position and chunk)
+// position P = guard + win*Vp + (zp*Yp + yp)*Xp + xp with zp in [0,Z+2), yp in [0,Y+2),
+// xp in [0,X+1); interior voxel (z,y,x) sits at (z+1, y+1, x+1).  Halo positions and the
+// guard zones are zero and are never written, so a 3x3x3 zero-padded convolution is a 1-D
+// correlation over P with the 27 constant offsets dz*Yp*Xp + dy*Xp + dx (the single x halo
+// column separates consecutive rows).
+struct Level {
+    int Z, Y, X;
+    int Zp, Yp, Xp;
+    int YpXp, Vp;
+    int guard;   // zero positions in front of window 0 (and at least that many + 1024 behind the last)
+    int64_t S;   // positions allocated per chunk
+};
+
+struct ConvLayer {
+    std::string name;
+    int cin = 0;       // real input channels
+    int cin_pad = 0;   // multiple of 16 (one tcgen05 K step)
+    int cout = 0;
+    int nblk = 0;      // MMA N per work item (32 or 64)
+    int NB = 0;        // N blocks per position group (conv: cout/nblk, deconv: 8*cout/nblk)
+    int KB = 0;        // cin_pad / 16
+    int ntaps = 27;    // 27 (3x3x3 conv) or 1 (k2s2 transposed conv, 8 sub-positions folded into NB)
+    bf16* w = nullptr;         // packed operand tiles [KB][NB][ntaps][2][nblk][8]
+    float* gamma = nullptr;    // InstanceNorm affine (conv layers)
+    float* beta = nullptr;
+    float* bias = nullptr;     // transposed-conv bias
+};
+
+struct Net {
+    std::map<std::string, ConvLayer> conv;    // "conv_0.conv_0" ... "upcat_1.convs.conv_1"
+    std::map<std::string, ConvLayer> deconv;  // "upcat_4" ... "upcat_1"
+    float* final_w = nullptr;                 // [32]
+    float final_b = 0.f;
+    bool loaded = false;
+};
+
+struct Engine;  // per-(roi, batch) activation buffers, defined in dlv_unet.cu
+
+struct Ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    char err[1024] = {0};
+    int64_t launches = 0;
+    Net net;
+    Engine* eng = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double conv_ms = 0.0;       // accumulated device time in conv kernels when timing is enabled
+    bool time_convs = false;
+    double ccl_ms = 0.0;
+    int64_t ccl_launches = 0;
+};
+
+void set_error(Ctx* ctx, const char* fmt, ...);
+
+#define DLV_CUDA_OK(ctx, expr)                                                              \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            dlv::set_error((ctx), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),   \
+                           __FILE__, __LINE__);                                             \
+            return -2;                                                                      \
+        }                                                                                   \
+    } while (0)
+
+// dlv_unet.cu
+struct WindowDesc {
+    int32_t oz, oy, ox;   // window origin inside the device-resident slab
+    int32_t flip;         // 0 none, 1 flip z, 2 flip y, 3 flip x (reference flip_dim 2 / 3 / 4)
+};
+int net_load(Ctx* ctx, int n, const char* const* names, const float* const* data, const int64_t* numel);
+void net_free(Ctx* ctx);
+void engine_free(Ctx* ctx);
+int engine_prepare(Ctx* ctx, const int32_t roi[3], int batch);
+int engine_batch_capacity(Ctx* ctx);
+// gather windows described by wd_dev[0..nwin) from a uint16 slab, run the net, blend into acc (fp32, 2 planes sets)
+int engine_run_batch(Ctx* ctx, const uint16_t* slab, int64_t slabY, int64_t slabX, const WindowDesc* wd_dev, int nwin,
+                     int32_t* acc, const float* wz, const float* wy, const float* wx, float* logits_out);
+int windows_active(Ctx* ctx, const uint16_t* slab, int64_t slabY, int64_t slabX, const int32_t* origins_dev, int n,
+                   const int32_t roi[3], int32_t* active_dev);
+int op_conv3d(Ctx* ctx, const char* name, const float* x, int n, int D, int H, int W, float* y, double* stats);
+int op_deconv(Ctx* ctx, const char* name, const float* x, int n, int D, int H, int W, float* y);
+
+// dlv_post.cu
+int post_finalise(Ctx* ctx, const float* avg, const uint16_t* vol, const int64_t sp[3], const int64_t sr[3], float thr,
+                  int iters, int64_t block_planes, uint8_t* bin, float* sig);
+int post_finalise_slab(Ctx* ctx, const float* avg, const uint16_t* vol, int64_t SY, int64_t SX, int64_t nplanes, int64_t gz0,
+                       const int64_t sr[3], float thr, int iters, int64_t block_planes, int64_t oz0, int64_t oz1,
+                       uint8_t* bin, float* sig);
+
+// fixed-point scale of the blend accumulator (logit units of 2^-12; |contribution| clamped to 2000)
+constexpr float kAccScale = 4096.f;
+constexpr float kAccClamp = 2000.f;
+constexpr float kSkipLogit = -1000.f;   // sliding_window_inferer.py:199-200
+
+// dlv_ccl.cu
+int ccl_run(Ctx* ctx, const uint8_t* mask_dev, const int64_t shape[3], uint32_t* labels_dev, dlv_table** table_out);
+
+}  // namespace dlv

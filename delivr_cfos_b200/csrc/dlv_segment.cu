@@ -1,0 +1,288 @@
+// dlv_segment.cu - sliding-window driver: window enumeration, skip rule, batched U-Net passes with the
+// fixed-point overlap blend, analytic averaging, then binarisation (dlv_post.cu).
+//
+// Replaces the compute of run_inference (inference/inference.py:229-329) and sliding_window_inference
+// (inference/sliding_window_inferer.py:102-251) of the reference.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "dlv_common.cuh"
+#include "dlv_internal.h"
+
+namespace dlv {
+
+// ------------------------------------------------------------------- window grid (host)
+// _get_scan_interval (sliding_window_inferer.py:255-276)
+static int scan_interval(int64_t image, int roi, float overlap) {
+    if (roi == image) return roi;
+    const int iv = static_cast<int>(roi * (1.0 - static_cast<double>(overlap)));
+    return iv > 0 ? iv : 1;
+}
+// per-dimension start list of MONAI 1.2.0 dense_patch_slices (sliding_window_inferer.py:143)
+std::vector<int> window_starts(int64_t image, int roi, float overlap) {
+    const int iv = scan_interval(image, roi, overlap);
+    const int64_t num = (image + iv - 1) / iv;
+    int scan_num = 1;
+    for (int64_t d = 0; d < num; ++d)
+        if (d * iv + roi >= image) { scan_num = static_cast<int>(d) + 1; break; }
+    std::vector<int> s;
+    for (int i = 0; i < scan_num; ++i) {
+        int64_t st = static_cast<int64_t>(i) * iv;
+        st -= std::max<int64_t>(st + roi - image, 0);
+        s.push_back(static_cast<int>(st));
+    }
+    return s;
+}
+
+// MONAI compute_importance_map(mode="gaussian", sigma_scale=0.125): separable exp(-x^2 / (2 (0.125 n)^2)),
+// normalised by its maximum; zeros clamped to the smallest non-zero value.  Optional mode (no reference oracle:
+// the reference hard-codes mode='constant', sliding_window_inferer.py:148).
+static std::vector<float> gaussian_1d(int n) {
+    std::vector<float> w(n);
+    const double sigma = 0.125 * n;
+    for (int i = 0; i < n; ++i) {
+        const double x = i - (n - 1) / 2.0;
+        w[i] = static_cast<float>(std::exp(-(x * x) / (2.0 * sigma * sigma)));
+    }
+    return w;
+}
+
+// ------------------------------------------------------------------- averaging (inference.py:285-299)
+// avg = (sum_active w*logit + sum_skipped w*(-1000)) / sum w   over all windows covering the voxel and all passes.
+// Cover ranges per dimension come from small lookup tables; the skipped-window term is evaluated from the
+// window-grid `active` flags instead of being blended, so empty windows cost no HBM traffic.
+struct AvgArgs {
+    int64_t PZ, PY, PX;        // region extent (planes of this slab, padded in-plane extent)
+    int64_t gz0;               // global z of local plane 0
+    const int32_t *lo_z, *hi_z, *lo_y, *hi_y, *lo_x, *hi_x;   // per-coordinate covering window index ranges (global coords)
+    const int32_t *sz, *sy, *sx;                              // window starts
+    int ny, nx;
+    const int32_t* active;     // [nz][ny][nx]
+    const float *wz, *wy, *wx; // gaussian 1-D weights or nullptr
+    int passes;
+};
+
+__global__ void average_kernel(const int32_t* __restrict__ acc, float* __restrict__ avg, AvgArgs a) {
+    const int64_t x = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t y = blockIdx.y, z = blockIdx.z;
+    if (x >= a.PX) return;
+    const int64_t gz = a.gz0 + z;
+    float wsum = 0.f, wskip = 0.f;
+    for (int iz = a.lo_z[gz]; iz <= a.hi_z[gz]; ++iz) {
+        const float fz = a.wz ? a.wz[gz - a.sz[iz]] : 1.f;
+        for (int iy = a.lo_y[y]; iy <= a.hi_y[y]; ++iy) {
+            const float fy = a.wz ? a.wy[y - a.sy[iy]] : 1.f;
+            for (int ix = a.lo_x[x]; ix <= a.hi_x[x]; ++ix) {
+                const float w = fz * fy * (a.wz ? a.wx[x - a.sx[ix]] : 1.f);
+                wsum += w;
+                if (!a.active[(static_cast<int64_t>(iz) * a.ny + iy) * a.nx + ix]) wskip += w;
+            }
+        }
+    }
+    const int64_t i = (z * a.PY + y) * a.PX + x;
+    const float s = static_cast<float>(acc[i]) * (1.f / kAccScale) + kSkipLogit * wskip * a.passes;
+    avg[i] = s / (wsum * a.passes);     // acc and avg may alias (same element, same thread)
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    template <class T> T* as() { return static_cast<T*>(p); }
+};
+static int dev_alloc(Ctx* ctx, DevBuf& b, size_t bytes) {
+    DLV_CUDA_OK(ctx, cudaMalloc(&b.p, bytes ? bytes : 1));
+    return 0;
+}
+template <class T>
+static int dev_upload(Ctx* ctx, DevBuf& b, const std::vector<T>& v) {
+    int rc = dev_alloc(ctx, b, v.size() * sizeof(T));
+    if (rc) return rc;
+    DLV_CUDA_OK(ctx, cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+static bool is_device_ptr(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+static void cover_tables(const std::vector<int>& starts, int roi, int64_t dim, std::vector<int32_t>& lo, std::vector<int32_t>& hi) {
+    lo.assign(dim, 0); hi.assign(dim, -1);
+    const int n = static_cast<int>(starts.size());
+    for (int64_t g = 0; g < dim; ++g) {
+        int l = n, h = -1;
+        for (int i = 0; i < n; ++i)
+            if (starts[i] <= g && g < starts[i] + roi) { l = std::min(l, i); h = std::max(h, i); }
+        lo[g] = l; hi[g] = h;
+    }
+}
+
+// The 13-pass test-time-augmentation plan of inference.py:265-279: one plain pass, then 4 x {plain, flip z, flip y}
+// (the reference adds unseeded N(0, U(0,1e-3)) noise to raw intensities >= 1 in the 12 extra passes; that is below
+// the resolution of the arithmetic and not reproducible, so the passes are evaluated noise-free).
+static const int kTtaFlips[13] = {0, 0, 1, 2, 0, 1, 2, 0, 1, 2, 0, 1, 2};
+
+int segment_run(Ctx* ctx, const void* volume_any, const dlv_seg_params* P, void* binaries_any, void* avg_any, void* sig_any,
+                dlv_seg_stats* st_out) {
+    if (!ctx->net.loaded) { set_error(ctx, "dlv_segment: call dlv_load_weights first"); return DLV_ERR_STATE; }
+    const int64_t PZ = P->shape_pad[0], PY = P->shape_pad[1], PX = P->shape_pad[2];
+    const int64_t Z = P->shape_real[0], Y = P->shape_real[1], X = P->shape_real[2];
+    for (int i = 0; i < 3; ++i) {
+        if (P->roi[i] <= 0 || P->shape_pad[i] < P->roi[i] || P->shape_real[i] <= 0 || P->shape_real[i] > P->shape_pad[i]) {
+            set_error(ctx, "dlv_segment: inconsistent shapes (dim %d: real %lld, padded %lld, roi %d)", i,
+                      (long long)P->shape_real[i], (long long)P->shape_pad[i], P->roi[i]);
+            return DLV_ERR_ARG;
+        }
+    }
+    if (P->overlap < 0.f || P->overlap >= 1.f) { set_error(ctx, "overlap must be >= 0 and < 1."); return DLV_ERR_ARG; }
+    const int batch = P->window_batch > 0 ? P->window_batch : 32;
+    int rc = engine_prepare(ctx, P->roi, batch);
+    if (rc) return rc;
+
+    const size_t nvox_pad = static_cast<size_t>(PZ) * PY * PX;
+    const size_t nvox = static_cast<size_t>(Z) * Y * X;
+
+    // ---- input slab on the device
+    DevBuf slab_own;
+    const uint16_t* slab = static_cast<const uint16_t*>(volume_any);
+    if (!is_device_ptr(volume_any)) {
+        if ((rc = dev_alloc(ctx, slab_own, nvox_pad * 2))) return rc;
+        DLV_CUDA_OK(ctx, cudaMemcpyAsync(slab_own.p, volume_any, nvox_pad * 2, cudaMemcpyHostToDevice, ctx->stream));
+        slab = slab_own.as<uint16_t>();
+    }
+
+    // ---- window grid, z-major / x fastest like dense_patch_slices
+    const std::vector<int> sz = window_starts(PZ, P->roi[0], P->overlap), sy = window_starts(PY, P->roi[1], P->overlap),
+                           sx = window_starts(PX, P->roi[2], P->overlap);
+    const int nz = sz.size(), ny = sy.size(), nx = sx.size();
+    const int64_t nwin = static_cast<int64_t>(nz) * ny * nx;
+    std::vector<int32_t> origins(nwin * 3);
+    for (int iz = 0, w = 0; iz < nz; ++iz)
+        for (int iy = 0; iy < ny; ++iy)
+            for (int ix = 0; ix < nx; ++ix, ++w) { origins[3 * w] = sz[iz]; origins[3 * w + 1] = sy[iy]; origins[3 * w + 2] = sx[ix]; }
+    DevBuf d_orig, d_active;
+    if ((rc = dev_upload(ctx, d_orig, origins))) return rc;
+    if ((rc = dev_alloc(ctx, d_active, nwin * sizeof(int32_t)))) return rc;
+    std::vector<int32_t> active(nwin, 1);
+    if (P->skip_empty) {
+        if ((rc = windows_active(ctx, slab, PY, PX, d_orig.as<int32_t>(), static_cast<int>(nwin), P->roi, d_active.as<int32_t>()))) return rc;
+        DLV_CUDA_OK(ctx, cudaMemcpyAsync(active.data(), d_active.p, nwin * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        DLV_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    } else {
+        DLV_CUDA_OK(ctx, cudaMemcpyAsync(d_active.p, active.data(), nwin * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+
+    // ---- schedule: passes x active windows
+    const int passes = P->tta ? 13 : 1;
+    int single_flip = 0;
+    if (!P->tta && P->flip_dim) {
+        if (P->flip_dim < 2 || P->flip_dim > 4) { set_error(ctx, "flip_dim must be 0, 2 (z), 3 (y) or 4 (x)"); return DLV_ERR_ARG; }
+        single_flip = P->flip_dim - 1;
+    }
+    std::vector<WindowDesc> sched;
+    int64_t nactive = 0;
+    for (int64_t w = 0; w < nwin; ++w) nactive += active[w] != 0;
+    sched.reserve(nactive * passes);
+    for (int ps = 0; ps < passes; ++ps)
+        for (int64_t w = 0; w < nwin; ++w)
+            if (active[w])
+                sched.push_back(WindowDesc{origins[3 * w], origins[3 * w + 1], origins[3 * w + 2], P->tta ? kTtaFlips[ps] : single_flip});
+    DevBuf d_sched;
+    if ((rc = dev_upload(ctx, d_sched, sched))) return rc;
+
+    // ---- blend weights
+    DevBuf d_wz, d_wy, d_wx;
+    const float *wz = nullptr, *wy = nullptr, *wx = nullptr;
+    if (P->blend_mode == 1) {
+        if ((rc = dev_upload(ctx, d_wz, gaussian_1d(P->roi[0])))) return rc;
+        if ((rc = dev_upload(ctx, d_wy, gaussian_1d(P->roi[1])))) return rc;
+        if ((rc = dev_upload(ctx, d_wx, gaussian_1d(P->roi[2])))) return rc;
+        wz = d_wz.as<float>(); wy = d_wy.as<float>(); wx = d_wx.as<float>();
+    } else if (P->blend_mode != 0) {
+        set_error(ctx, "blend_mode must be 0 (constant) or 1 (gaussian)");
+        return DLV_ERR_ARG;
+    }
+
+    // ---- accumulate
+    DevBuf d_acc;
+    if ((rc = dev_alloc(ctx, d_acc, nvox_pad * 4))) return rc;
+    DLV_CUDA_OK(ctx, cudaMemsetAsync(d_acc.p, 0, nvox_pad * 4, ctx->stream));
+    cudaEvent_t e0, e1, e2;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+    const int64_t launches0 = ctx->launches;
+    ctx->conv_ms = 0.0;
+    cudaEventRecord(e0, ctx->stream);
+    for (size_t off = 0; off < sched.size(); off += batch) {
+        const int n = static_cast<int>(std::min<size_t>(batch, sched.size() - off));
+        rc = engine_run_batch(ctx, slab, PY, PX, d_sched.as<WindowDesc>() + off, n, d_acc.as<int32_t>(), wz, wy, wx, nullptr);
+        if (rc) break;
+    }
+    cudaEventRecord(e1, ctx->stream);
+
+    // ---- average (in place: int32 sums -> fp32 logits)
+    DevBuf t_loz, t_hiz, t_loy, t_hiy, t_lox, t_hix, t_sz, t_sy, t_sx;
+    if (rc == 0) {
+        std::vector<int32_t> lo, hi;
+        cover_tables(sz, P->roi[0], PZ, lo, hi);
+        if ((rc = dev_upload(ctx, t_loz, lo)) || (rc = dev_upload(ctx, t_hiz, hi))) return rc;
+        cover_tables(sy, P->roi[1], PY, lo, hi);
+        if ((rc = dev_upload(ctx, t_loy, lo)) || (rc = dev_upload(ctx, t_hiy, hi))) return rc;
+        cover_tables(sx, P->roi[2], PX, lo, hi);
+        if ((rc = dev_upload(ctx, t_lox, lo)) || (rc = dev_upload(ctx, t_hix, hi))) return rc;
+        std::vector<int32_t> s32(sz.begin(), sz.end());
+        if ((rc = dev_upload(ctx, t_sz, s32))) return rc;
+        s32.assign(sy.begin(), sy.end());
+        if ((rc = dev_upload(ctx, t_sy, s32))) return rc;
+        s32.assign(sx.begin(), sx.end());
+        if ((rc = dev_upload(ctx, t_sx, s32))) return rc;
+        AvgArgs a;
+        a.PZ = PZ; a.PY = PY; a.PX = PX; a.gz0 = 0;
+        a.lo_z = t_loz.as<int32_t>(); a.hi_z = t_hiz.as<int32_t>();
+        a.lo_y = t_loy.as<int32_t>(); a.hi_y = t_hiy.as<int32_t>();
+        a.lo_x = t_lox.as<int32_t>(); a.hi_x = t_hix.as<int32_t>();
+        a.sz = t_sz.as<int32_t>(); a.sy = t_sy.as<int32_t>(); a.sx = t_sx.as<int32_t>();
+        a.ny = ny; a.nx = nx; a.active = d_active.as<int32_t>();
+        a.wz = wz; a.wy = wy; a.wx = wx; a.passes = passes;
+        dim3 grid(static_cast<unsigned>((PX + 255) / 256), static_cast<unsigned>(PY), static_cast<unsigned>(PZ));
+        average_kernel<<<grid, 256, 0, ctx->stream>>>(d_acc.as<int32_t>(), d_acc.as<float>(), a);
+        ctx->launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { set_error(ctx, "average kernel: %s", cudaGetErrorString(e)); rc = DLV_ERR_CUDA; }
+    }
+
+    // ---- binarise + eroded-mask gate
+    DevBuf bin_own, sig_own;
+    uint8_t* bin = static_cast<uint8_t*>(binaries_any);
+    float* sig = static_cast<float*>(sig_any);
+    const bool bin_host = !is_device_ptr(binaries_any);
+    const bool sig_host = sig_any && !is_device_ptr(sig_any);
+    if (rc == 0 && bin_host) { if ((rc = dev_alloc(ctx, bin_own, nvox))) return rc; bin = bin_own.as<uint8_t>(); }
+    if (rc == 0 && sig_host) { if ((rc = dev_alloc(ctx, sig_own, nvox * 4))) return rc; sig = sig_own.as<float>(); }
+    if (rc == 0)
+        rc = post_finalise(ctx, d_acc.as<float>(), slab, P->shape_pad, P->shape_real, P->threshold, P->erosion_iters,
+                           P->erosion_block_planes, bin, sig);
+    cudaEventRecord(e2, ctx->stream);
+    if (rc == 0) {
+        if (bin_host) cudaMemcpyAsync(binaries_any, bin, nvox, cudaMemcpyDeviceToHost, ctx->stream);
+        if (sig_host) cudaMemcpyAsync(sig_any, sig, nvox * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (avg_any)
+            cudaMemcpyAsync(avg_any, d_acc.p, nvox_pad * 4, is_device_ptr(avg_any) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (rc == 0 && e != cudaSuccess) { set_error(ctx, "dlv_segment: %s", cudaGetErrorString(e)); rc = DLV_ERR_CUDA; }
+    if (rc == 0 && st_out) {
+        float ms = 0.f;
+        st_out->windows_total = nwin;
+        st_out->windows_active = nactive;
+        st_out->passes = passes;
+        st_out->kernel_launches = ctx->launches - launches0;
+        cudaEventElapsedTime(&ms, e0, e1); st_out->ms_unet = ms;
+        cudaEventElapsedTime(&ms, e1, e2); st_out->ms_finalise = ms;
+        st_out->ms_conv = ctx->conv_ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    return rc;
+}
+
+}  // namespace dlv

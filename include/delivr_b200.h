@@ -1,0 +1,154 @@
+/*
+ * delivr_b200.h - C ABI of libdelivr_b200.so, the B200 (sm_100a) implementation of
+ * DELiVR's blob_detection hot path.
+ *
+ * The reference (erturklab/delivr_cfos) is pure Python; its hot path has no FFI.
+ * Each entry point below names the reference code it replaces (file:line under
+ * the reference tree); INTEGRATION.md shows the ctypes stub a maintainer binds.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative code on failure; the
+ *     message is available from dlv_last_error(ctx) (thread-unsafe per ctx);
+ *   - one ctx per process/GPU, calls on a ctx are serialised by the caller;
+ *   - pointers named *_host are host memory, *_dev device memory on the ctx's
+ *     GPU; `void* any` pointers may be either (resolved with
+ *     cudaPointerGetAttributes);
+ *   - the caller owns every buffer it passes; dlv_table is owned by the
+ *     library until dlv_table_free;
+ *   - there is NO CPU fallback: dlv_init fails unless the device is sm_100.
+ *   - volumes are C-order (Z, Y, X), x fastest.
+ */
+#ifndef DELIVR_B200_H
+#define DELIVR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dlv_ctx dlv_ctx;
+
+#define DLV_OK 0
+#define DLV_ERR_ARG (-1)
+#define DLV_ERR_CUDA (-2)
+#define DLV_ERR_STATE (-3)
+#define DLV_ERR_UNSUPPORTED (-4)
+
+#define DLV_ABI_VERSION 1
+
+/* ---- lifecycle -------------------------------------------------------- */
+int dlv_abi_version(void);
+/* Creates a context on CUDA device `device`. Fails on anything but sm_100. */
+int dlv_init(int device, dlv_ctx** out);
+void dlv_destroy(dlv_ctx* ctx);
+const char* dlv_last_error(const dlv_ctx* ctx);
+/* Number of kernels this library launched on the ctx since creation (bench "gpu_launches"). */
+int64_t dlv_launch_count(const dlv_ctx* ctx);
+/* The CUDA stream all work of this ctx is enqueued on (cudaStream_t as void*). */
+void* dlv_stream(dlv_ctx* ctx);
+int dlv_synchronize(dlv_ctx* ctx);
+/* enable != 0: bracket every convolution launch with CUDA events and accumulate the device time into
+ * dlv_seg_stats.ms_conv (serialises the stream; used by bench.py for the roofline line only). */
+int dlv_set_conv_timing(dlv_ctx* ctx, int enable);
+
+/* ---- network weights --------------------------------------------------
+ * Replaces BasicUNet(...) + load_state_dict(checkpoint["state_dict"])
+ * (inference/inference.py:190-200,217-222).  `names[i]` are the checkpoint keys
+ * (with or without the DataParallel "module." prefix), `data_host[i]` host fp32,
+ * `numel[i]` element counts.  All 82 tensors must be present (strict load).
+ * Weights are repacked to bf16 tcgen05 operand tiles on the device. */
+int dlv_load_weights(dlv_ctx* ctx, int n, const char* const* names, const float* const* data_host,
+                     const int64_t* numel);
+
+/* ---- segmentation: sliding-window U-Net + blend + binarise -------------
+ * Replaces run_inference's compute (inference/inference.py:229-329):
+ * SlidingWindowInferer passes (inference/sliding_window_inferer.py:33-253),
+ * block-wise averaging (inference.py:285-299) and create_nifti_seg
+ * (inference.py:31-95).
+ */
+typedef struct dlv_seg_params {
+    int64_t shape_pad[3];   /* padded volume (Zp,Yp,Xp): multiples of roi (inference.py:229-231) */
+    int64_t shape_real[3];  /* original stack shape (Z,Y,X)                                      */
+    int32_t roi[3];         /* window (inference.py:164-168); each a multiple of 16             */
+    float overlap;          /* 0.5 in the reference (inference.py:125)                          */
+    int32_t tta;            /* 0: one pass; 1: the reference's 13-pass plan (inference.py:265-279),
+                               noise-free (sigma <= 1e-3 on intensities >= 1 is below bf16 resolution) */
+    float threshold;        /* sigmoid threshold, 0.5 (inference.py:120)                        */
+    int32_t erosion_iters;  /* 30 (inference.py:82)                                             */
+    int64_t erosion_block_planes; /* z-extent of the Arrayterator blocks (inference.py:53); <=0: whole volume */
+    int32_t blend_mode;     /* 0 constant (what the reference computes, sliding_window_inferer.py:148);
+                               1 gaussian (MONAI importance map, sigma_scale 0.125) - no reference oracle */
+    int32_t window_batch;   /* windows per launch; <=0: library default                         */
+    int32_t skip_empty;     /* 1: windows whose input max <= 0 get -1000 (sliding_window_inferer.py:198-202,
+                               applied per window)                                */
+    int32_t flip_dim;       /* only when tta == 0: the single pass flips windows along this dim before the net and
+                               back after it (sliding_window_inferer.py:218-219,225-226); 0 none, 2 = z, 3 = y, 4 = x */
+} dlv_seg_params;
+
+typedef struct dlv_seg_stats {
+    int64_t windows_total;
+    int64_t windows_active;
+    int64_t passes;
+    int64_t kernel_launches;
+    double ms_unet;      /* device time in the window loop (gather+convs+norms+blend)        */
+    double ms_finalise;  /* average + sigmoid/threshold + erosion                             */
+    double ms_conv;      /* device time inside the tcgen05 convolution kernels only          */
+} dlv_seg_stats;
+
+/* volume: uint16 (Zp,Yp,Xp) host or device.  binaries_out: uint8 (Z,Y,X) host or device.
+ * avg_logits_out (optional): float32 (Zp,Yp,Xp) averaged logits (reference keeps fp16: inference.py:242-246).
+ * sigmoid_out (optional): float32 (Z,Y,X) (network_output.npy, inference.py:43,72). */
+int dlv_segment(dlv_ctx* ctx, const void* volume_any, const dlv_seg_params* params, void* binaries_out_any,
+                void* avg_logits_out_any, void* sigmoid_out_any, dlv_seg_stats* stats_out);
+
+/* ---- connected components + statistics --------------------------------
+ * Replaces cc3d.connected_components(bin_img, return_N=True) and
+ * cc3d.statistics(labels, no_slice_conversion=True) (count_blobs.py:61,64,85).
+ * 26-connectivity; labels 1..N numbered by each component's first voxel in
+ * C-order raster scan.  Table rows 0..N (row 0 = background), exact integers;
+ * centroid = sum/count is divided in fp64 by the host wrapper.
+ */
+typedef struct dlv_table {
+    int64_t n;              /* number of components N                        */
+    uint64_t* voxel_counts; /* [N+1]                                         */
+    uint64_t* sums;         /* [N+1][3]  sum of z, y, x                      */
+    int64_t* bbox;          /* [N+1][6]  zmin,zmax,ymin,ymax,xmin,xmax incl. */
+} dlv_table;
+
+/* mask: uint8 (Z,Y,X), host or device, non-zero = foreground.
+ * labels_out (optional): uint32 (Z,Y,X), host or device. */
+int dlv_ccl(dlv_ctx* ctx, const void* mask_any, const int64_t shape[3], int connectivity, void* labels_out_any,
+            dlv_table** table_out);
+void dlv_table_free(dlv_table* t);
+/* Device time of the last dlv_ccl call's kernels (ms) and their launch count. */
+int dlv_ccl_last_timing(const dlv_ctx* ctx, double* ms_kernels, int64_t* launches);
+
+/* ---- operator-level entry points --------------------------------------
+ * The same kernels dlv_segment drives, exposed one stage at a time so the
+ * parity tests can check each against the oracle / a torch fp32 reference.
+ * All pointers here are DEVICE pointers. */
+
+/* U-Net forward on `nwin` windows already in device memory:
+ * windows_dev uint16 [nwin][rz][ry][rx] -> logits_dev float32 [nwin][rz][ry][rx].
+ * (predictor(window_data), sliding_window_inferer.py:222) */
+int dlv_unet_forward(dlv_ctx* ctx, const uint16_t* windows_dev, int nwin, const int32_t roi[3], float* logits_dev);
+
+/* One 3x3x3 convolution layer of the loaded net on NCDHW fp32 input (device):
+ * x_dev [n][cin][D][H][W] -> y_dev [n][cout][D][H][W] = raw conv (no bias, pre-norm, bf16-rounded),
+ * stats_dev [n][cout][2] = sum, sum of squares of the fp32 accumulators.  layer_name e.g. "conv_0.conv_1". */
+int dlv_op_conv3d(dlv_ctx* ctx, const char* layer_name, const float* x_dev, int n, int D, int H, int W, float* y_dev,
+                  double* stats_dev);
+/* One k2s2 transposed convolution (+bias) of the loaded net, e.g. "upcat_4": [n][cin][D][H][W] -> [n][cout][2D][2H][2W]. */
+int dlv_op_deconv(dlv_ctx* ctx, const char* upcat_name, const float* x_dev, int n, int D, int H, int W, float* y_dev);
+
+/* binarise + eroded-mask gate (create_nifti_seg, inference.py:60-88) on device buffers:
+ * avg_logits_dev float32 padded (Zp,Yp,Xp); volume_dev uint16 padded; out uint8 (Z,Y,X). */
+int dlv_op_finalise(dlv_ctx* ctx, const float* avg_logits_dev, const uint16_t* volume_dev, const int64_t shape_pad[3],
+                    const int64_t shape_real[3], float threshold, int erosion_iters, int64_t erosion_block_planes,
+                    uint8_t* binaries_dev, float* sigmoid_dev_or_null);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DELIVR_B200_H */

@@ -1,0 +1,76 @@
+"""dlv_ccl vs the plain-C oracle (oracle/ccl_ref.c): labels, N, counts, sums, bboxes bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_common import ctx_with
+from oracle import ccl_ref, pipeline_ref as P
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(mask):
+    from delivr_cfos_b200 import Context
+    ctx = _compare.ctx = getattr(_compare, "ctx", None) or Context(0)
+    mask = np.ascontiguousarray(mask, dtype=np.uint8)
+    lab = np.empty(mask.shape, dtype=np.uint32)
+    t = ctx.ccl(mask, mask.shape, labels_out=lab)
+    rl, rn = ccl_ref.connected_components26(mask)
+    rs = ccl_ref.statistics(rl, rn)
+    assert t["n"] == rn
+    assert np.array_equal(lab, rl)
+    assert np.array_equal(t["voxel_counts"], rs["voxel_counts"])
+    assert np.array_equal(t["sums"], rs["sums"])
+    assert np.array_equal(t["bounding_boxes"], rs["bounding_boxes"])
+    assert np.array_equal(t["centroids"], rs["centroids"], equal_nan=True)
+    # device-pointer path gives the same labels
+    md = torch.from_numpy(mask).cuda()
+    ld = torch.empty(mask.shape, dtype=torch.int32, device="cuda")
+    t2 = ctx.ccl(md, mask.shape, labels_out=ld)
+    assert t2["n"] == rn and np.array_equal(ld.cpu().numpy().view(np.uint32), rl)
+
+
+@pytest.mark.parametrize("shape,kind,p", [
+    ((40, 64, 128), "blobs", 0), ((33, 70, 90), "blobs", 0), ((20, 50, 61), "bernoulli", 0.08),
+    ((16, 40, 200), "bernoulli", 0.5), ((8, 33, 257), "bernoulli", 0.3), ((64, 256, 256), "blobs", 0),
+    ((5, 7, 3), "bernoulli", 0.4), ((1, 1, 1), "bernoulli", 1.0), ((3, 5, 1000), "bernoulli", 0.9),
+])
+def test_ccl_random(shape, kind, p):
+    _compare(P.synth_mask(shape, 1003, kind=kind, p=p))
+
+
+def test_ccl_adversarial():
+    m = np.zeros((6, 6, 70), np.uint8)
+    _compare(m)                                   # empty
+    _compare(np.ones((4, 5, 67), np.uint8))       # full volume: one component
+    m[2, 3, 40] = 1
+    _compare(m)                                   # single voxel
+    d = np.zeros((40, 40, 40), np.uint8)
+    i = np.arange(40)
+    d[i, i, i] = 1                                # pure diagonal: only 26-links
+    d[i, i, 39 - i] = 1
+    _compare(d)
+    c = np.zeros((9, 9, 96), np.uint8)            # comb crossing 32-voxel word borders
+    c[4, 4, :] = 1
+    c[::2, 4, 31] = 1
+    c[4, ::2, 64] = 1
+    c[0, 0, 95] = 1
+    _compare(c)
+    s = np.zeros((12, 12, 12), np.uint8)          # spiral-ish: late merges
+    s[::2, :, 0] = 1; s[:, ::2, 11] = 1; s[5, 5, :] = 1
+    _compare(s)
+    u = np.zeros((3, 40, 130), np.uint8)          # U shapes whose arms meet only at the bottom row
+    u[1, :, ::4] = 1; u[1, 39, :] = 1
+    _compare(u)
+
+
+def test_ccl_csv_drop_last_component():
+    """count_blobs.py:104 iterates range(1, N): the CSV has N-1 rows."""
+    m = P.synth_mask((24, 40, 64), 7)
+    lab, n, st = P.blob_table(m)
+    from delivr_cfos_b200 import Context
+    from delivr_cfos_b200.count_blobs import csv_text
+    ctx = Context(0)
+    t = ctx.ccl(m, m.shape)
+    assert csv_text(t, t["n"]) == P.csv_text(st, n)
+    assert csv_text(t, t["n"]).count("\n") - 1 == n - 1
