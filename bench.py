@@ -1,0 +1,259 @@
+#!/usr/bin/env python
+"""bench.py - DELiVR blob_detection hot path on B200: Gvoxels/s of segmentation + connected components.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|small]
+
+A "step" is one full pass of the hot path over one synthetic uint16 volume: sliding-window 3-D U-Net
+(window 96x96x64, overlap 0.5, one pass) -> averaging -> sigmoid/threshold + eroded-mask gate -> 26-connected
+components + size/centroid table.  Metric: unpadded volume voxels / time (BASELINE.json "Gvoxels/s seg+CC").
+
+* ``value``: volume already resident in HBM, binaries + labels stay on the device, table to host.
+* ``e2e``: the same through host buffers (pinned volume in, binaries + table out), copies inside the timing.
+* ``roofline``: the tcgen05 convolution kernels (the one dense contraction): algorithmic FLOP of the active
+  windows / summed conv-kernel device time, against MEASURED_PEAKS.json bf16_tflops_sustained.
+* ``cpu_baseline`` / ``--impl reference``: the CPU restatement of the reference (oracle/, torch-fp32 U-Net +
+  C erosion/CCL) on a bounded sample of the same workload, all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+MAC_PER_PATCH_VOXEL = 142552          # SURVEY.md section 2.2 (all conv / deconv / 1x1 layers)
+ROI = (96, 96, 64)
+OVERLAP = 0.5
+WORKLOADS = {
+    "cfg2": dict(shape=(256, 2048, 2048), seed=1002, name="cfg2 synthetic 256x2048x2048 uint16 slab"),
+    "cfg1": dict(shape=(64, 512, 512), seed=1001, name="cfg1 synthetic 64x512x512 uint16 volume"),
+    "small": dict(shape=(96, 288, 256), seed=1005, name="small synthetic 96x288x256 uint16 volume"),
+}
+CPU_SAMPLE = (96, 144, 128)           # bounded CPU sample: 1x2x3 = 6 windows of 96x96x64
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1424.2))), float(d.get("hbm_gbs", 6550.4)), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+def state_dict():
+    from oracle import unet_ref  # only to synthesise random-init weights of the architecture when no checkpoint
+    w = os.path.join(ROOT, "baseline", "_ref", "inference_weights.tar")
+    if os.path.exists(w):
+        return torch.load(w, map_location="cpu", weights_only=True)["state_dict"], "shipped inference_weights.tar"
+    return unet_ref.random_state_dict(0), "random-init weights (checkpoint not staged)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in rows for n, v in zip(names, r[5:9]) if v.strip().lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "power_w_max": max(float(r[3]) for r in rows),
+                "samples": len(rows), "reasons": reasons}
+
+
+def cpu_reference_step(sample_vol, net, threads):
+    """One pass of the reference's algorithm on the CPU (oracle port) over a bounded sample. -> seconds."""
+    from oracle import pipeline_ref as P
+    t0 = time.perf_counter()
+    shape = sample_vol.shape
+    avg = P.infer_average(sample_vol, ROI, OVERLAP, net, sw_batch_size=2, tta=False)
+    b = P.create_binaries(avg, sample_vol, shape, 0.5)
+    P.blob_table(b)
+    return time.perf_counter() - t0
+
+
+def make_cpu_sample(seed):
+    from oracle import pipeline_ref as P
+    v = P.synth_volume(CPU_SAMPLE, seed)
+    return np.where(v == 0, 1, v).astype(np.uint16)          # all windows active: worst case per voxel
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (oracle port; the Python reference itself cannot travel to the
+    GPU box and its third-party deps are absent) on the box's host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle import unet_ref
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd, wdesc = state_dict()
+    net = unet_ref.BasicUNet(dropout=0.1)
+    net.load_state_dict(unet_ref.strip_module_prefix(sd), strict=True)
+    net.eval()
+    wl = WORKLOADS[args.workload]
+    vol = make_cpu_sample(wl["seed"])
+    for _ in range(args.warmup):
+        cpu_reference_step(vol, net, threads)
+    ts = [cpu_reference_step(vol, net, threads) for _ in range(args.steps)]
+    t = sum(ts) / len(ts)
+    v = vol.size / t / 1e9
+    sample = f"{CPU_SAMPLE[0]}x{CPU_SAMPLE[1]}x{CPU_SAMPLE[2]} crop-sized volume of the workload (6 windows, all active), 1 pass + binarise + CC"
+    print(json.dumps({
+        "impl": "reference", "metric": "Gvoxels/s seg+CC", "value": v, "unit": "Gvoxels/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": f"synthetic; {wdesc}",
+        "config": {"workload": wl["name"], "window": list(ROI), "overlap": OVERLAP, "tta": False,
+                   "note": "oracle port of the reference CPU path (torch fp32 U-Net, C erosion + CCL as cc3d stand-in)"},
+        "cpu_baseline": {"value": v, "unit": "Gvoxels/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "Gvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    if world > 1 or args.gpus > 1:
+        from delivr_cfos_b200 import slabs
+        return slabs.bench_main(args, rank, local_rank, world)
+
+    from delivr_cfos_b200 import Context
+    from delivr_cfos_b200.synth import synth_volume_cuda
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    wl = WORKLOADS[args.workload]
+    shape = wl["shape"]
+    sd, wdesc = state_dict()
+    ctx = Context(local_rank)
+    ctx.load_weights(sd)
+    vol = synth_volume_cuda(shape, wl["seed"], roi=ROI, device=dev)
+    shape_pad = tuple(vol.shape)
+    nvox = int(np.prod(shape))
+    binaries = torch.empty(shape, dtype=torch.uint8, device=dev)
+    labels = torch.empty(shape, dtype=torch.int32, device=dev)
+    stream = torch.cuda.ExternalStream(ctx._L.dlv_stream(ctx._h), device=dev)
+    from delivr_cfos_b200.inference.inference import erosion_block_planes
+    ebp = erosion_block_planes(shape)
+
+    def step():
+        st = ctx.segment(vol, shape_pad, shape, ROI, binaries, overlap=OVERLAP, erosion_block_planes=ebp)
+        tb = ctx.ccl(binaries, shape, labels_out=labels)
+        return st, tb
+
+    for _ in range(args.warmup):
+        st, tb = step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    l0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        st, tb = step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = ctx.launches - l0
+    clocks = sampler.stop()
+    value = nvox / (ms * 1e-3) / 1e9
+
+    # ---- end to end through host buffers (pinned volume in; binaries + table out)
+    hvol = torch.empty(shape_pad, dtype=torch.uint16).pin_memory()
+    hvol.copy_(vol)
+    hbin = torch.empty(shape, dtype=torch.uint8).pin_memory()
+    torch.cuda.synchronize()
+
+    def step_e2e():
+        ctx.segment(hvol, shape_pad, shape, ROI, hbin, overlap=OVERLAP, erosion_block_planes=ebp)
+        return ctx.ccl(hbin, shape)
+
+    step_e2e()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        t_e2e = step_e2e()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_e2e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / args.steps
+    h2d = int(np.prod(shape_pad)) * 2 + nvox
+    d2h = nvox + (t_e2e["n"] + 1) * (8 + 24 + 24)
+
+    # ---- roofline of the dominant kernel (tcgen05 convolutions): one extra step with per-launch event timing
+    ctx.set_conv_timing(True)
+    st_t = ctx.segment(vol, shape_pad, shape, ROI, binaries, overlap=OVERLAP, erosion_block_planes=ebp)
+    ctx.set_conv_timing(False)
+    conv_ms = st_t["ms_conv"]
+    patch_vox = st_t["windows_active"] * ROI[0] * ROI[1] * ROI[2] * st_t["passes"]
+    flop = 2.0 * MAC_PER_PATCH_VOXEL * patch_vox
+    tf_peak, hbm_peak, peak_kind = peaks()
+    achieved = flop / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    ccl_ms, _ = ctx.ccl_last_timing()
+
+    out = {
+        "metric": "Gvoxels/s seg+CC", "value": value, "unit": "Gvoxels/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": f"synthetic; {wdesc}",
+        "config": {"workload": wl["name"], "window": list(ROI), "overlap": OVERLAP, "tta": False, "blend": "constant",
+                   "windows_total": st["windows_total"], "windows_active": st["windows_active"],
+                   "components": tb["n"], "l2": "inputs larger than L2 (volume + accumulator >> 126 MB)"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "e2e": {"value": nvox / (ms_e2e * 1e-3) / 1e9, "unit": "Gvoxels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (all conv/deconv launches of one step)",
+                     "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
+                     "traffic": None, "peak_kind": f"bf16_tflops_sustained, {peak_kind}",
+                     "conv_ms_per_step": conv_ms, "unet_ms_per_step": st["ms_unet"], "finalise_ms_per_step": st["ms_finalise"],
+                     "ccl_ms_per_step": ccl_ms, "ccl_gbs_algorithmic": 9.0 * nvox / (ccl_ms * 1e-3) / 1e9 if ccl_ms else None,
+                     "ccl_frac_of_hbm": (9.0 * nvox / (ccl_ms * 1e-3) / 1e9 / hbm_peak) if ccl_ms else None},
+    }
+    if not args.no_cpu_baseline:
+        from oracle import unet_ref
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        net = unet_ref.BasicUNet(dropout=0.1)
+        net.load_state_dict(unet_ref.strip_module_prefix(sd), strict=True)
+        net.eval()
+        sv = make_cpu_sample(wl["seed"])
+        t = cpu_reference_step(sv, net, threads)
+        out["cpu_baseline"] = {"value": sv.size / t / 1e9, "unit": "Gvoxels/s", "cores": threads, "kind": "port",
+                               "sample": f"{CPU_SAMPLE[0]}x{CPU_SAMPLE[1]}x{CPU_SAMPLE[2]} volume (6 windows, all active), 1 pass + binarise + CC, {t:.1f} s"}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
