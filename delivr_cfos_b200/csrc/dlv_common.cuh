@@ -16,6 +16,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+// One lane of a fully converged warp.  Unlike `lane == 0`, ptxas knows the elected branch is single-threaded,
+// so tcgen05 operands stay in uniform registers (no per-instruction uniformisation loop).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 
 __device__ __forceinline__ uint4 ld_nc_u4(const void* p) {
     uint4 r;

@@ -103,44 +103,54 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvArgs
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer (single thread)
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16_m128(NBLK);
-            int stage = 0; uint32_t phase = 0;
-            int it = 0;
-            for (int item = item0; item < item1; ++item, ++it) {
-                const int buf = it & 1;
-                mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);
+        // ------------------------------------------------------------ MMA issuer
+        // The whole warp walks the pipeline (waits are warp-uniform); one elected lane issues the MMAs.
+        constexpr uint32_t idesc = umma_idesc_bf16_m128(NBLK);
+        int stage = 0; uint32_t phase = 0;
+        int it = 0;
+        for (int item = item0; item < item1; ++item, ++it) {
+            const int buf = it & 1;
+            mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t dcol = tmem_base + buf * 256;
+            for (int kb = 0; kb < p.KB; ++kb) {
+                mbar_wait(&full[stage], phase);
                 tc_fence_after();
-                const uint32_t dcol = tmem_base + buf * 256;
-                for (int kb = 0; kb < p.KB; ++kb) {
-                    mbar_wait(&full[stage], phase);
-                    tc_fence_after();
+                if (elect_one_sync()) {
                     const uint32_t a_base = smem_u32(smem + stage * p.stage_bytes);
-                    const uint32_t w_base = a_base + p.a_bytes;
+                    uint64_t bdesc = umma_desc_kmajor_noswz(a_base + p.a_bytes, NBLK * 16, 128);
+                    const uint64_t adesc0 = umma_desc_kmajor_noswz(a_base, p.RL * 16, 128);
+                    uint32_t acc = kb ? 1u : 0u;
+                    if (NTAPS == 27) {
+                        // descriptor start-address field is in 16 B units = positions: a tap is a +/- position bump
+                        const int run = 2 * p.RL;
 #pragma unroll 1
-                    for (int tap = 0; tap < NTAPS; ++tap) {
-                        int d = 0, off = 0;
-                        if (NTAPS == 27) {
-                            const int kz = tap / 9, ky = (tap / 3) % 3, kx = tap % 3;
-                            d = kz;
-                            off = p.H + (ky - 1) * p.Xp + (kx - 1);
+                        for (int kz = 0; kz < 3; ++kz) {
+#pragma unroll 1
+                            for (int ky = 0; ky < 3; ++ky) {
+                                const uint64_t arow = adesc0 + static_cast<uint64_t>(kz * run + p.H + (ky - 1) * p.Xp - 1);
+#pragma unroll
+                                for (int kx = 0; kx < 3; ++kx) {
+                                    const uint64_t atap = arow + kx;
+#pragma unroll
+                                    for (int t = 0; t < 8; ++t)
+                                        if (t < p.T) umma_bf16(dcol + t * NBLK, atap + t * 128, bdesc, idesc, acc);
+                                    acc = 1u;
+                                    bdesc += (2 * NBLK * 16) >> 4;
+                                }
+                            }
                         }
-                        const uint32_t a_tap = a_base + (static_cast<uint32_t>(d * 2) * p.RL + off) * 16;
-                        const uint64_t bdesc = umma_desc_kmajor_noswz(w_base + tap * (2 * NBLK * 16), NBLK * 16, 128);
-                        const uint32_t acc = (kb | tap) ? 1u : 0u;
-                        for (int t = 0; t < p.T; ++t) {
-                            const uint64_t adesc = umma_desc_kmajor_noswz(a_tap + t * 2048, p.RL * 16, 128);
-                            umma_bf16(dcol + t * NBLK, adesc, bdesc, idesc, acc);
-                        }
+                    } else {
+#pragma unroll 1
+                        for (int t = 0; t < p.T; ++t) umma_bf16(dcol + t * NBLK, adesc0 + t * 128, bdesc, idesc, acc);
                     }
                     umma_commit(&empty[stage]);
-                    if (++stage == kConvStages) { stage = 0; phase ^= 1; }
+                    if (kb == p.KB - 1) umma_commit(&tfull[buf]);
                 }
-                umma_commit(&tfull[buf]);
+                __syncwarp();
+                if (++stage == kConvStages) { stage = 0; phase ^= 1; }
             }
         }
-        __syncwarp();
     } else {
         // ------------------------------------------------------------ epilogue (4 warps = 4 TMEM lane quadrants)
         const int q = warp & 3;

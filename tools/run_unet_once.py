@@ -14,7 +14,8 @@ roi = (96, 96, 64)
 ctx = Context(0)
 ctx.load_weights(state_dict()[0])
 vol = synth_volume_cuda((96 * n, 96, 64), 5)
-vol = torch.where(vol == 0, torch.full_like(vol, 300), vol).contiguous().view(n, 96, 96, 64)
+v32 = vol.to(torch.int32)
+vol = torch.where(v32 == 0, torch.full_like(v32, 300), v32).to(torch.uint16).contiguous().view(n, 96, 96, 64)
 out = torch.empty((n,) + roi, dtype=torch.float32, device="cuda")
 ctx.unet_forward(vol, roi, out)
 torch.cuda.synchronize()
