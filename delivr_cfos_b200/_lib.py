@@ -48,6 +48,8 @@ EXPORTS = [
     "dlv_abi_version", "dlv_init", "dlv_destroy", "dlv_last_error", "dlv_launch_count", "dlv_stream",
     "dlv_synchronize", "dlv_set_conv_timing", "dlv_load_weights", "dlv_segment", "dlv_ccl", "dlv_table_free",
     "dlv_ccl_last_timing", "dlv_unet_forward", "dlv_op_conv3d", "dlv_op_deconv", "dlv_op_finalise",
+    "dlv_window_grid", "dlv_windows_active", "dlv_seg_accumulate", "dlv_seg_average", "dlv_op_finalise_slab",
+    "dlv_ccl_boundary_pairs", "dlv_relabel",
 ]
 
 _lib = None
@@ -96,6 +98,21 @@ def load_library():
     L.dlv_op_deconv.argtypes = [c_vp, ctypes.c_char_p, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp]
     L.dlv_op_finalise.restype = ctypes.c_int
     L.dlv_op_finalise.argtypes = [c_vp, c_vp, c_vp, P(c_i64), P(c_i64), c_f32, ctypes.c_int, c_i64, c_vp, c_vp]
+    L.dlv_window_grid.restype = ctypes.c_int
+    L.dlv_window_grid.argtypes = [P(c_i64), P(c_i32), c_f32, P(c_i32), c_vp]
+    L.dlv_windows_active.restype = ctypes.c_int
+    L.dlv_windows_active.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, ctypes.c_int, P(c_i32), c_vp]
+    L.dlv_seg_accumulate.restype = ctypes.c_int
+    L.dlv_seg_accumulate.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, ctypes.c_int, P(c_i32), ctypes.c_int, ctypes.c_int, c_vp]
+    L.dlv_seg_average.restype = ctypes.c_int
+    L.dlv_seg_average.argtypes = [c_vp, c_vp, c_i64, c_i64, P(c_i64), P(c_i32), c_f32, c_vp, ctypes.c_int, ctypes.c_int]
+    L.dlv_op_finalise_slab.restype = ctypes.c_int
+    L.dlv_op_finalise_slab.argtypes = [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, P(c_i64), c_f32, ctypes.c_int, c_i64,
+                                       c_i64, c_i64, c_vp, c_vp]
+    L.dlv_ccl_boundary_pairs.restype = ctypes.c_int
+    L.dlv_ccl_boundary_pairs.argtypes = [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, P(c_i64)]
+    L.dlv_relabel.restype = ctypes.c_int
+    L.dlv_relabel.argtypes = [c_vp, c_vp, c_i64, c_vp, c_i64]
     if L.dlv_abi_version() != 1:
         raise DlvError("libdelivr_b200.so ABI version mismatch")
     _lib = L
@@ -237,3 +254,67 @@ class Context:
         self._check(self._L.dlv_op_finalise(self._h, _ptr(avg_logits), _ptr(volume), sp, sr, float(threshold),
                                             int(erosion_iters), int(erosion_block_planes), _ptr(binaries_out),
                                             _ptr(sigmoid_out)), "dlv_op_finalise")
+
+    # ---- slab-level entry points (z-sharded runs, delivr_cfos_b200/slabs.py)
+    def windows_active(self, slab, origins, roi):
+        """origins int32 [n,3] local to the slab (device uint16 (SZ,SY,SX)) -> int32 [n] activity flags."""
+        o = np.ascontiguousarray(origins, dtype=np.int32)
+        out = np.zeros(len(o), dtype=np.int32)
+        r = (c_i32 * 3)(*[int(v) for v in roi])
+        self._check(self._L.dlv_windows_active(self._h, _ptr(slab), int(slab.shape[1]), int(slab.shape[2]), o.ctypes.data,
+                                               len(o), r, out.ctypes.data), "dlv_windows_active")
+        return out
+
+    def seg_accumulate(self, slab, windows, roi, acc, window_batch=0, blend_mode=0):
+        """windows int32 [n,4] = (oz,oy,ox,flip_dim) local to the slab; acc int32 device tensor shaped like slab."""
+        w = np.ascontiguousarray(windows, dtype=np.int32).reshape(-1, 4)
+        r = (c_i32 * 3)(*[int(v) for v in roi])
+        self._check(self._L.dlv_seg_accumulate(self._h, _ptr(slab), int(slab.shape[1]), int(slab.shape[2]), w.ctypes.data,
+                                               len(w), r, int(window_batch), int(blend_mode), _ptr(acc)), "dlv_seg_accumulate")
+
+    def seg_average(self, acc, nplanes, gz0, shape_pad, roi, overlap, active, passes=1, blend_mode=0):
+        sp = (c_i64 * 3)(*[int(v) for v in shape_pad])
+        r = (c_i32 * 3)(*[int(v) for v in roi])
+        a = np.ascontiguousarray(active, dtype=np.int32)
+        self._check(self._L.dlv_seg_average(self._h, _ptr(acc), int(nplanes), int(gz0), sp, r, float(overlap), a.ctypes.data,
+                                            int(passes), int(blend_mode)), "dlv_seg_average")
+
+    def op_finalise_slab(self, avg, volume, nplanes, gz0, shape_real, oz0, oz1, binaries_out, threshold=0.5,
+                         erosion_iters=30, erosion_block_planes=0, sigmoid_out=None):
+        sr = (c_i64 * 3)(*[int(v) for v in shape_real])
+        self._check(self._L.dlv_op_finalise_slab(self._h, _ptr(avg), _ptr(volume), int(volume.shape[1]), int(volume.shape[2]),
+                                                 int(nplanes), int(gz0), sr, float(threshold), int(erosion_iters),
+                                                 int(erosion_block_planes), int(oz0), int(oz1), _ptr(binaries_out),
+                                                 _ptr(sigmoid_out)), "dlv_op_finalise_slab")
+
+    def ccl_boundary_pairs(self, labels_lo_plane, labels_hi_plane):
+        """-> uint32 [k,2] unique (lo label, hi label) pairs of 26-adjacent voxels across the boundary."""
+        import torch
+        Y, X = int(labels_hi_plane.shape[-2]), int(labels_hi_plane.shape[-1])
+        cap = max(1024, Y * X // 8)
+        while True:
+            buf = torch.empty((cap, 2), dtype=torch.int32, device=labels_hi_plane.device)
+            cnt = c_i64()
+            self._check(self._L.dlv_ccl_boundary_pairs(self._h, _ptr(labels_lo_plane), _ptr(labels_hi_plane), Y, X, _ptr(buf),
+                                                       cap, ctypes.byref(cnt)), "dlv_ccl_boundary_pairs")
+            if cnt.value <= cap:
+                p = buf[:cnt.value].cpu().numpy().view(np.uint32)
+                return np.unique(p, axis=0) if len(p) else p.reshape(0, 2)
+            cap = int(cnt.value)
+
+    def relabel(self, labels, lut):
+        self._check(self._L.dlv_relabel(self._h, _ptr(labels), int(labels.numel()), _ptr(lut), int(lut.numel())), "dlv_relabel")
+
+
+def window_grid(shape_pad, roi, overlap):
+    """Per-dimension window start lists (host logic in the library, no GPU needed)."""
+    L = load_library()
+    sp = (c_i64 * 3)(*[int(v) for v in shape_pad])
+    r = (c_i32 * 3)(*[int(v) for v in roi])
+    counts = (c_i32 * 3)()
+    if L.dlv_window_grid(sp, r, float(overlap), counts, None) != 0:
+        raise DlvError("dlv_window_grid: bad arguments")
+    buf = (c_i32 * (counts[0] + counts[1] + counts[2]))()
+    L.dlv_window_grid(sp, r, float(overlap), counts, buf)
+    flat = list(buf)
+    return [flat[:counts[0]], flat[counts[0]:counts[0] + counts[1]], flat[counts[0] + counts[1]:]]

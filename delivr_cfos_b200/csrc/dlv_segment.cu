@@ -118,6 +118,89 @@ static void cover_tables(const std::vector<int>& starts, int roi, int64_t dim, s
     }
 }
 
+// ------------------------------------------------------------------- reusable stages (also exported per slab)
+struct BlendWeights {
+    DevBuf z, y, x;
+    const float *wz = nullptr, *wy = nullptr, *wx = nullptr;
+};
+static int blend_weights(Ctx* ctx, int blend_mode, const int32_t roi[3], BlendWeights& w) {
+    if (blend_mode == 0) return 0;
+    if (blend_mode != 1) { set_error(ctx, "blend_mode must be 0 (constant) or 1 (gaussian)"); return DLV_ERR_ARG; }
+    int rc;
+    if ((rc = dev_upload(ctx, w.z, gaussian_1d(roi[0])))) return rc;
+    if ((rc = dev_upload(ctx, w.y, gaussian_1d(roi[1])))) return rc;
+    if ((rc = dev_upload(ctx, w.x, gaussian_1d(roi[2])))) return rc;
+    w.wz = w.z.as<float>(); w.wy = w.y.as<float>(); w.wx = w.x.as<float>();
+    return 0;
+}
+
+// run the scheduled windows (origins local to `slab`) and blend them into acc (int32, same extent as slab)
+int seg_accumulate(Ctx* ctx, const uint16_t* slab, int64_t SY, int64_t SX, const std::vector<WindowDesc>& sched,
+                   const int32_t roi[3], int batch, int blend_mode, int32_t* acc) {
+    if (!ctx->net.loaded) { set_error(ctx, "call dlv_load_weights first"); return DLV_ERR_STATE; }
+    if (sched.empty()) return 0;
+    batch = batch > 0 ? batch : 32;
+    int rc = engine_prepare(ctx, roi, batch);
+    if (rc) return rc;
+    batch = engine_batch_capacity(ctx);
+    BlendWeights bw;
+    if ((rc = blend_weights(ctx, blend_mode, roi, bw))) return rc;
+    DevBuf d_sched;
+    if ((rc = dev_upload(ctx, d_sched, sched))) return rc;
+    for (size_t off = 0; off < sched.size() && rc == 0; off += batch) {
+        const int n = static_cast<int>(std::min<size_t>(batch, sched.size() - off));
+        rc = engine_run_batch(ctx, slab, SY, SX, d_sched.as<WindowDesc>() + off, n, acc, bw.wz, bw.wy, bw.wx, nullptr);
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);   // d_sched / weights are freed on return
+    if (rc == 0 && e != cudaSuccess) { set_error(ctx, "accumulate: %s", cudaGetErrorString(e)); rc = DLV_ERR_CUDA; }
+    return rc;
+}
+
+// int32 blend sums -> fp32 averaged logits, in place, for `nplanes` planes starting at global plane gz0
+int seg_average(Ctx* ctx, int32_t* acc, int64_t nplanes, int64_t gz0, const int64_t shape_pad[3], const int32_t roi[3],
+                float overlap, const int32_t* active_host, int passes, int blend_mode) {
+    const int64_t PZ = shape_pad[0], PY = shape_pad[1], PX = shape_pad[2];
+    if (nplanes <= 0) return 0;
+    if (gz0 < 0 || gz0 + nplanes > PZ) { set_error(ctx, "average: plane range outside the padded volume"); return DLV_ERR_ARG; }
+    const std::vector<int> sz = window_starts(PZ, roi[0], overlap), sy = window_starts(PY, roi[1], overlap),
+                           sx = window_starts(PX, roi[2], overlap);
+    const int64_t nwin = static_cast<int64_t>(sz.size()) * sy.size() * sx.size();
+    BlendWeights bw;
+    int rc;
+    if ((rc = blend_weights(ctx, blend_mode, roi, bw))) return rc;
+    DevBuf t_loz, t_hiz, t_loy, t_hiy, t_lox, t_hix, t_sz, t_sy, t_sx, d_active;
+    std::vector<int32_t> lo, hi;
+    cover_tables(sz, roi[0], PZ, lo, hi);
+    if ((rc = dev_upload(ctx, t_loz, lo)) || (rc = dev_upload(ctx, t_hiz, hi))) return rc;
+    cover_tables(sy, roi[1], PY, lo, hi);
+    if ((rc = dev_upload(ctx, t_loy, lo)) || (rc = dev_upload(ctx, t_hiy, hi))) return rc;
+    cover_tables(sx, roi[2], PX, lo, hi);
+    if ((rc = dev_upload(ctx, t_lox, lo)) || (rc = dev_upload(ctx, t_hix, hi))) return rc;
+    std::vector<int32_t> s32(sz.begin(), sz.end());
+    if ((rc = dev_upload(ctx, t_sz, s32))) return rc;
+    s32.assign(sy.begin(), sy.end());
+    if ((rc = dev_upload(ctx, t_sy, s32))) return rc;
+    s32.assign(sx.begin(), sx.end());
+    if ((rc = dev_upload(ctx, t_sx, s32))) return rc;
+    std::vector<int32_t> act(active_host, active_host + nwin);
+    if ((rc = dev_upload(ctx, d_active, act))) return rc;
+    AvgArgs a;
+    a.PZ = nplanes; a.PY = PY; a.PX = PX; a.gz0 = gz0;
+    a.lo_z = t_loz.as<int32_t>(); a.hi_z = t_hiz.as<int32_t>();
+    a.lo_y = t_loy.as<int32_t>(); a.hi_y = t_hiy.as<int32_t>();
+    a.lo_x = t_lox.as<int32_t>(); a.hi_x = t_hix.as<int32_t>();
+    a.sz = t_sz.as<int32_t>(); a.sy = t_sy.as<int32_t>(); a.sx = t_sx.as<int32_t>();
+    a.ny = static_cast<int>(sy.size()); a.nx = static_cast<int>(sx.size()); a.active = d_active.as<int32_t>();
+    a.wz = bw.wz; a.wy = bw.wy; a.wx = bw.wx; a.passes = passes;
+    dim3 grid(static_cast<unsigned>((PX + 255) / 256), static_cast<unsigned>(PY), static_cast<unsigned>(nplanes));
+    average_kernel<<<grid, 256, 0, ctx->stream>>>(acc, reinterpret_cast<float*>(acc), a);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // lookup tables are freed on return
+    if (e != cudaSuccess) { set_error(ctx, "average kernel: %s", cudaGetErrorString(e)); return DLV_ERR_CUDA; }
+    return 0;
+}
+
 // The 13-pass test-time-augmentation plan of inference.py:265-279: one plain pass, then 4 x {plain, flip z, flip y}
 // (the reference adds unseeded N(0, U(0,1e-3)) noise to raw intensities >= 1 in the 12 extra passes; that is below
 // the resolution of the arithmetic and not reproducible, so the passes are evaluated noise-free).
@@ -188,21 +271,6 @@ int segment_run(Ctx* ctx, const void* volume_any, const dlv_seg_params* P, void*
         for (int64_t w = 0; w < nwin; ++w)
             if (active[w])
                 sched.push_back(WindowDesc{origins[3 * w], origins[3 * w + 1], origins[3 * w + 2], P->tta ? kTtaFlips[ps] : single_flip});
-    DevBuf d_sched;
-    if ((rc = dev_upload(ctx, d_sched, sched))) return rc;
-
-    // ---- blend weights
-    DevBuf d_wz, d_wy, d_wx;
-    const float *wz = nullptr, *wy = nullptr, *wx = nullptr;
-    if (P->blend_mode == 1) {
-        if ((rc = dev_upload(ctx, d_wz, gaussian_1d(P->roi[0])))) return rc;
-        if ((rc = dev_upload(ctx, d_wy, gaussian_1d(P->roi[1])))) return rc;
-        if ((rc = dev_upload(ctx, d_wx, gaussian_1d(P->roi[2])))) return rc;
-        wz = d_wz.as<float>(); wy = d_wy.as<float>(); wx = d_wx.as<float>();
-    } else if (P->blend_mode != 0) {
-        set_error(ctx, "blend_mode must be 0 (constant) or 1 (gaussian)");
-        return DLV_ERR_ARG;
-    }
 
     // ---- accumulate
     DevBuf d_acc;
@@ -213,43 +281,11 @@ int segment_run(Ctx* ctx, const void* volume_any, const dlv_seg_params* P, void*
     const int64_t launches0 = ctx->launches;
     ctx->conv_ms = 0.0;
     cudaEventRecord(e0, ctx->stream);
-    for (size_t off = 0; off < sched.size(); off += batch) {
-        const int n = static_cast<int>(std::min<size_t>(batch, sched.size() - off));
-        rc = engine_run_batch(ctx, slab, PY, PX, d_sched.as<WindowDesc>() + off, n, d_acc.as<int32_t>(), wz, wy, wx, nullptr);
-        if (rc) break;
-    }
+    rc = seg_accumulate(ctx, slab, PY, PX, sched, P->roi, batch, P->blend_mode, d_acc.as<int32_t>());
     cudaEventRecord(e1, ctx->stream);
 
     // ---- average (in place: int32 sums -> fp32 logits)
-    DevBuf t_loz, t_hiz, t_loy, t_hiy, t_lox, t_hix, t_sz, t_sy, t_sx;
-    if (rc == 0) {
-        std::vector<int32_t> lo, hi;
-        cover_tables(sz, P->roi[0], PZ, lo, hi);
-        if ((rc = dev_upload(ctx, t_loz, lo)) || (rc = dev_upload(ctx, t_hiz, hi))) return rc;
-        cover_tables(sy, P->roi[1], PY, lo, hi);
-        if ((rc = dev_upload(ctx, t_loy, lo)) || (rc = dev_upload(ctx, t_hiy, hi))) return rc;
-        cover_tables(sx, P->roi[2], PX, lo, hi);
-        if ((rc = dev_upload(ctx, t_lox, lo)) || (rc = dev_upload(ctx, t_hix, hi))) return rc;
-        std::vector<int32_t> s32(sz.begin(), sz.end());
-        if ((rc = dev_upload(ctx, t_sz, s32))) return rc;
-        s32.assign(sy.begin(), sy.end());
-        if ((rc = dev_upload(ctx, t_sy, s32))) return rc;
-        s32.assign(sx.begin(), sx.end());
-        if ((rc = dev_upload(ctx, t_sx, s32))) return rc;
-        AvgArgs a;
-        a.PZ = PZ; a.PY = PY; a.PX = PX; a.gz0 = 0;
-        a.lo_z = t_loz.as<int32_t>(); a.hi_z = t_hiz.as<int32_t>();
-        a.lo_y = t_loy.as<int32_t>(); a.hi_y = t_hiy.as<int32_t>();
-        a.lo_x = t_lox.as<int32_t>(); a.hi_x = t_hix.as<int32_t>();
-        a.sz = t_sz.as<int32_t>(); a.sy = t_sy.as<int32_t>(); a.sx = t_sx.as<int32_t>();
-        a.ny = ny; a.nx = nx; a.active = d_active.as<int32_t>();
-        a.wz = wz; a.wy = wy; a.wx = wx; a.passes = passes;
-        dim3 grid(static_cast<unsigned>((PX + 255) / 256), static_cast<unsigned>(PY), static_cast<unsigned>(PZ));
-        average_kernel<<<grid, 256, 0, ctx->stream>>>(d_acc.as<int32_t>(), d_acc.as<float>(), a);
-        ctx->launches++;
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) { set_error(ctx, "average kernel: %s", cudaGetErrorString(e)); rc = DLV_ERR_CUDA; }
-    }
+    if (rc == 0) rc = seg_average(ctx, d_acc.as<int32_t>(), PZ, 0, P->shape_pad, P->roi, P->overlap, active.data(), passes, P->blend_mode);
 
     // ---- binarise + eroded-mask gate
     DevBuf bin_own, sig_own;

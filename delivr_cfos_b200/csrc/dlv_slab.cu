@@ -1,0 +1,169 @@
+// dlv_slab.cu - slab-level entry points for z-sharded runs (one process per GPU, NCCL between them):
+// window grid, per-slab accumulate / average / finalise, boundary label pairs and relabelling for the
+// cross-slab component merge.  The host side that strings these together is delivr_cfos_b200/slabs.py.
+#include <algorithm>
+#include <vector>
+
+#include "dlv_common.cuh"
+#include "dlv_internal.h"
+
+namespace dlv {
+
+std::vector<int> window_starts(int64_t image, int roi, float overlap);
+int seg_accumulate(Ctx* ctx, const uint16_t* slab, int64_t SY, int64_t SX, const std::vector<WindowDesc>& sched,
+                   const int32_t roi[3], int batch, int blend_mode, int32_t* acc);
+int seg_average(Ctx* ctx, int32_t* acc, int64_t nplanes, int64_t gz0, const int64_t shape_pad[3], const int32_t roi[3],
+                float overlap, const int32_t* active_host, int passes, int blend_mode);
+
+// 26-adjacent foreground pairs across a slab boundary: `lo` is the last plane of the lower slab, `hi` the first
+// plane of the upper slab (local labels, 0 = background).  One thread per voxel of `hi`; a pair is skipped when
+// the same (dy,dx) offset produced the identical pair one voxel to the left (cheap run-level de-duplication).
+__global__ void boundary_pairs_kernel(const uint32_t* __restrict__ lo, const uint32_t* __restrict__ hi, int64_t Y, int64_t X,
+                                      uint32_t* __restrict__ pairs, unsigned long long cap, unsigned long long* __restrict__ count) {
+    const int64_t x = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t y = blockIdx.y;
+    if (x >= X) return;
+    const uint32_t b = hi[y * X + x];
+    if (!b) return;
+    const uint32_t bprev = (x > 0) ? hi[y * X + x - 1] : 0u;
+    for (int dy = -1; dy <= 1; ++dy) {
+        const int64_t yy = y + dy;
+        if (yy < 0 || yy >= Y) continue;
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int64_t xx = x + dx;
+            if (xx < 0 || xx >= X) continue;
+            const uint32_t a = lo[yy * X + xx];
+            if (!a) continue;
+            if (bprev == b && xx > 0 && lo[yy * X + xx - 1] == a) continue;
+            const unsigned long long i = atomicAdd(count, 1ull);
+            if (i < cap) { pairs[2 * i] = a; pairs[2 * i + 1] = b; }
+        }
+    }
+}
+
+__global__ void relabel_kernel(uint32_t* __restrict__ labels, int64_t n, const uint32_t* __restrict__ map) {
+    const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        uint4 v = *reinterpret_cast<uint4*>(labels + i);
+        if (v.x | v.y | v.z | v.w) {
+            v.x = v.x ? map[v.x] : 0u; v.y = v.y ? map[v.y] : 0u; v.z = v.z ? map[v.z] : 0u; v.w = v.w ? map[v.w] : 0u;
+            *reinterpret_cast<uint4*>(labels + i) = v;
+        }
+    } else {
+        for (int64_t j = i; j < n; ++j) { const uint32_t l = labels[j]; if (l) labels[j] = map[l]; }
+    }
+}
+
+}  // namespace dlv
+
+using dlv::Ctx;
+static Ctx* C(dlv_ctx* c) { return reinterpret_cast<Ctx*>(c); }
+
+extern "C" {
+
+int dlv_window_grid(const int64_t shape_pad[3], const int32_t roi[3], float overlap, int32_t counts_out[3], int32_t* starts_out) {
+    if (!shape_pad || !roi || !counts_out) return DLV_ERR_ARG;
+    int off = 0;
+    for (int d = 0; d < 3; ++d) {
+        if (roi[d] <= 0 || shape_pad[d] < roi[d] || overlap < 0.f || overlap >= 1.f) return DLV_ERR_ARG;
+        const std::vector<int> s = dlv::window_starts(shape_pad[d], roi[d], overlap);
+        counts_out[d] = static_cast<int32_t>(s.size());
+        if (starts_out) for (size_t i = 0; i < s.size(); ++i) starts_out[off + i] = s[i];
+        off += static_cast<int>(s.size());
+    }
+    return DLV_OK;
+}
+
+int dlv_windows_active(dlv_ctx* c, const uint16_t* slab_dev, int64_t SY, int64_t SX, const int32_t* origins_host, int n,
+                       const int32_t roi[3], int32_t* active_host) {
+    Ctx* ctx = C(c);
+    if (!ctx) return DLV_ERR_ARG;
+    if (n <= 0) return DLV_OK;
+    cudaSetDevice(ctx->device);
+    int32_t *d_o = nullptr, *d_a = nullptr;
+    DLV_CUDA_OK(ctx, cudaMalloc(reinterpret_cast<void**>(&d_o), sizeof(int32_t) * 3 * n));
+    DLV_CUDA_OK(ctx, cudaMalloc(reinterpret_cast<void**>(&d_a), sizeof(int32_t) * n));
+    cudaMemcpyAsync(d_o, origins_host, sizeof(int32_t) * 3 * n, cudaMemcpyHostToDevice, ctx->stream);
+    int rc = dlv::windows_active(ctx, slab_dev, SY, SX, d_o, n, roi, d_a);
+    cudaMemcpyAsync(active_host, d_a, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_o); cudaFree(d_a);
+    if (rc == 0 && e != cudaSuccess) { dlv::set_error(ctx, "dlv_windows_active: %s", cudaGetErrorString(e)); rc = DLV_ERR_CUDA; }
+    return rc;
+}
+
+int dlv_seg_accumulate(dlv_ctx* c, const uint16_t* slab_dev, int64_t SY, int64_t SX, const int32_t* windows_host, int n,
+                       const int32_t roi[3], int window_batch, int blend_mode, int32_t* acc_dev) {
+    Ctx* ctx = C(c);
+    if (!ctx) return DLV_ERR_ARG;
+    if (!slab_dev || !roi || !acc_dev || (n > 0 && !windows_host)) { dlv::set_error(ctx, "dlv_seg_accumulate: null argument"); return DLV_ERR_ARG; }
+    cudaSetDevice(ctx->device);
+    std::vector<dlv::WindowDesc> sched(n > 0 ? n : 0);
+    for (int i = 0; i < n; ++i) {
+        const int32_t f = windows_host[4 * i + 3];
+        if (f != 0 && (f < 2 || f > 4)) { dlv::set_error(ctx, "dlv_seg_accumulate: flip_dim must be 0, 2, 3 or 4"); return DLV_ERR_ARG; }
+        sched[i] = dlv::WindowDesc{windows_host[4 * i], windows_host[4 * i + 1], windows_host[4 * i + 2], f ? f - 1 : 0};
+    }
+    return dlv::seg_accumulate(ctx, slab_dev, SY, SX, sched, roi, window_batch, blend_mode, acc_dev);
+}
+
+int dlv_seg_average(dlv_ctx* c, int32_t* acc_dev_inout, int64_t nplanes, int64_t gz0, const int64_t shape_pad[3],
+                    const int32_t roi[3], float overlap, const int32_t* active_host, int passes, int blend_mode) {
+    Ctx* ctx = C(c);
+    if (!ctx) return DLV_ERR_ARG;
+    if (!acc_dev_inout || !shape_pad || !roi || !active_host || passes < 1) { dlv::set_error(ctx, "dlv_seg_average: bad argument"); return DLV_ERR_ARG; }
+    cudaSetDevice(ctx->device);
+    return dlv::seg_average(ctx, acc_dev_inout, nplanes, gz0, shape_pad, roi, overlap, active_host, passes, blend_mode);
+}
+
+int dlv_op_finalise_slab(dlv_ctx* c, const float* avg_dev, const uint16_t* volume_dev, int64_t SY, int64_t SX, int64_t nplanes,
+                         int64_t gz0, const int64_t shape_real[3], float threshold, int erosion_iters, int64_t erosion_block_planes,
+                         int64_t oz0, int64_t oz1, uint8_t* binaries_dev, float* sigmoid_dev_or_null) {
+    Ctx* ctx = C(c);
+    if (!ctx) return DLV_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    // only real planes take part in the erosion (outside the array counts as 1)
+    const int64_t np_real = std::min<int64_t>(nplanes, shape_real[0] - gz0);
+    return dlv::post_finalise_slab(ctx, avg_dev, volume_dev, SY, SX, np_real, gz0, shape_real, threshold, erosion_iters,
+                                   erosion_block_planes, oz0, oz1, binaries_dev, sigmoid_dev_or_null);
+}
+
+int dlv_ccl_boundary_pairs(dlv_ctx* c, const uint32_t* labels_lo_plane_dev, const uint32_t* labels_hi_plane_dev, int64_t Y, int64_t X,
+                           uint32_t* pairs_dev, int64_t cap, int64_t* count_host_out) {
+    Ctx* ctx = C(c);
+    if (!ctx) return DLV_ERR_ARG;
+    if (!labels_lo_plane_dev || !labels_hi_plane_dev || !pairs_dev || !count_host_out || cap < 0) { dlv::set_error(ctx, "dlv_ccl_boundary_pairs: bad argument"); return DLV_ERR_ARG; }
+    cudaSetDevice(ctx->device);
+    unsigned long long* cnt = nullptr;
+    DLV_CUDA_OK(ctx, cudaMalloc(reinterpret_cast<void**>(&cnt), 8));
+    cudaMemsetAsync(cnt, 0, 8, ctx->stream);
+    if (Y > 0 && X > 0) {
+        dim3 grid(static_cast<unsigned>((X + 127) / 128), static_cast<unsigned>(Y));
+        dlv::boundary_pairs_kernel<<<grid, 128, 0, ctx->stream>>>(labels_lo_plane_dev, labels_hi_plane_dev, Y, X, pairs_dev,
+                                                                 static_cast<unsigned long long>(cap), cnt);
+        ctx->launches++;
+    }
+    unsigned long long h = 0;
+    cudaMemcpyAsync(&h, cnt, 8, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(cnt);
+    if (e != cudaSuccess) { dlv::set_error(ctx, "dlv_ccl_boundary_pairs: %s", cudaGetErrorString(e)); return DLV_ERR_CUDA; }
+    *count_host_out = static_cast<int64_t>(h);
+    return DLV_OK;
+}
+
+int dlv_relabel(dlv_ctx* c, uint32_t* labels_dev, int64_t n, const uint32_t* map_dev, int64_t nmap) {
+    Ctx* ctx = C(c);
+    if (!ctx) return DLV_ERR_ARG;
+    if (!labels_dev || !map_dev || n < 0 || nmap < 1) { dlv::set_error(ctx, "dlv_relabel: bad argument"); return DLV_ERR_ARG; }
+    cudaSetDevice(ctx->device);
+    if (n > 0) {
+        const int64_t nthreads = (n + 3) / 4;
+        dlv::relabel_kernel<<<static_cast<unsigned>((nthreads + 255) / 256), 256, 0, ctx->stream>>>(labels_dev, n, map_dev);
+        ctx->launches++;
+    }
+    DLV_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return DLV_OK;
+}
+
+}  // extern "C"

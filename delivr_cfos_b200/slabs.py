@@ -1,0 +1,464 @@
+"""z-slab sharding of the blob_detection hot path over the GPUs of one box (one process per GPU).
+
+The volume's *window z-layers* are partitioned contiguously over the ranks.  Each rank gathers and runs its own
+windows and blends them into a local fixed-point accumulator; three small exchanges make the result identical to
+a single-GPU run, bit for bit:
+
+1. logits  - the planes shared by the last window layer of rank r and the first of rank r+1 are sent r -> r+1
+             and added (int32 adds: exact, order independent); rank r+1 owns those planes afterwards;
+2. activity- the per-window "input max > 0" flags are all-gathered (the averaging needs the skipped windows);
+3. labels  - after a per-slab labelling, rank r sends its last label plane to r+1, which lists the 26-adjacent
+             label pairs; pairs + per-slab component counts are all-gathered and every rank resolves the same
+             global numbering (components ordered by their first voxel in raster order), relabels locally and
+             merges the integer statistics tables associatively.
+
+The erosion halo (31 input planes below a slab) is read with the slab, so it needs no collective.
+
+Two drivers share the planning and merge logic: ``run_distributed`` (one rank per process; ``TorchComm`` =
+torch.distributed, NCCL on GPUs / gloo in the CPU tests) and ``run_virtual`` (N virtual slabs in one process,
+which exercises the same exchange and merge logic on a single GPU).
+Compute goes through a ``worker`` object; the product worker is :class:`CudaSlabWorker` (libdelivr_b200.so).
+"""
+import math
+
+import numpy as np
+
+EROSION_ITERS = 30
+
+
+# ------------------------------------------------------------------------------------------- planning (pure host)
+class SlabPlan:
+    """Partition of the window z-layers and the plane ranges that follow from it."""
+
+    def __init__(self, shape_real, roi, overlap, world, starts=None, erosion_iters=EROSION_ITERS, layer_weights=None):
+        self.shape_real = tuple(int(s) for s in shape_real)
+        self.roi = tuple(int(r) for r in roi)
+        self.overlap = float(overlap)
+        self.world = int(world)
+        self.iters = int(erosion_iters)
+        self.shape_pad = tuple(int(math.ceil(d / r) * r) for d, r in zip(self.shape_real, self.roi))   # inference.py:229-231
+        if starts is None:
+            from ._lib import window_grid
+            starts = window_grid(self.shape_pad, self.roi, self.overlap)
+        self.sz, self.sy, self.sx = ([int(v) for v in s] for s in starts)
+        nz = len(self.sz)
+        w = np.ones(nz) if layer_weights is None else np.maximum(np.asarray(layer_weights, dtype=np.float64), 1e-9)
+        # contiguous partition balanced by (active-)window count per layer
+        cum = np.concatenate([[0.0], np.cumsum(w)])
+        bounds = [0]
+        for r in range(1, self.world):
+            target = cum[-1] * r / self.world
+            k = int(np.searchsorted(cum, target, side="left"))
+            k = min(max(k, bounds[-1] + (1 if nz - bounds[-1] > self.world - r else 0)), nz - (self.world - r))
+            bounds.append(max(k, bounds[-1]))
+        bounds.append(nz)
+        self.layers = [(bounds[r], bounds[r + 1]) for r in range(self.world)]
+
+    def rank(self, r):
+        """Plane ranges of rank r (global plane numbers, half-open)."""
+        a, b = self.layers[r]
+        PZ, Z = self.shape_pad[0], self.shape_real[0]
+        rz = self.roi[0]
+        if a == b:       # more ranks than window layers: nothing to do
+            return dict(layers=(a, b), win=(0, 0), own=(0, 0), slab=(0, 0), send=None, recv=None, own_real=(0, 0))
+        last = self._next_nonempty(r) is None
+        first = self._prev_nonempty(r) is None
+        win = (self.sz[a], self.sz[b - 1] + rz)
+        own = (0 if first else self.sz[a], PZ if last else self.sz[b])
+        slab = (max(0, own[0] - (self.iters + 1)), max(win[1], min(PZ, own[1] + self.iters + 1)))
+        send = None if last else (self.sz[b], win[1])                 # planes owned by the next rank that we touched
+        recv = None
+        p = self._prev_nonempty(r)
+        if p is not None:
+            pa, pb = self.layers[p]
+            recv = (self.sz[a], self.sz[pb - 1] + rz)
+        own_real = (min(own[0], Z), min(own[1], Z))
+        return dict(layers=(a, b), win=win, own=own, slab=slab, send=send, recv=recv, own_real=own_real)
+
+    def _next_nonempty(self, r):
+        for q in range(r + 1, self.world):
+            if self.layers[q][0] < self.layers[q][1]:
+                return q
+        return None
+
+    def _prev_nonempty(self, r):
+        for q in range(r - 1, -1, -1):
+            if self.layers[q][0] < self.layers[q][1]:
+                return q
+        return None
+
+    def windows_of(self, r):
+        """int32 [n,3] global origins of rank r's windows, z-major / x fastest (dense_patch_slices order)."""
+        a, b = self.layers[r]
+        return np.array([(z, y, x) for z in self.sz[a:b] for y in self.sy for x in self.sx], dtype=np.int32).reshape(-1, 3)
+
+
+def resolve_global_labels(counts, pairs):
+    """Global component numbering from per-slab counts and boundary pairs.
+
+    counts[r] = N_r; pairs[r] = uint32 [k,2] of (label in slab r-1, label in slab r) (pairs[0] is empty).
+    Components are numbered by their first voxel in raster order: slabs in z order, a merged component takes the
+    number of its member in the lowest slab.  -> (list of uint32 lookup tables [N_r+1], N_global)
+    """
+    counts = [int(c) for c in counts]
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)     # node id of (r, l) = off[r] + l, l >= 1
+    total = int(off[-1])
+    parent = {}
+
+    def find(a):
+        root = a
+        while parent.get(root, root) != root:
+            root = parent[root]
+        while parent.get(a, a) != root:
+            parent[a], a = root, parent[a]
+        return root
+
+    for r, p in enumerate(pairs):
+        if r == 0 or p is None or len(p) == 0:
+            continue
+        for lo, hi in np.asarray(p, dtype=np.int64):
+            a, b = find(off[r - 1] + lo), find(off[r] + hi)
+            if a != b:
+                if a < b:
+                    parent[b] = a
+                else:
+                    parent[a] = b
+    is_new = np.ones(total + 1, dtype=bool)
+    is_new[0] = False
+    merged = [n for n in parent if find(n) != n]
+    if merged:
+        is_new[np.array(merged, dtype=np.int64)] = False
+    glabel = np.cumsum(is_new).astype(np.int64)
+    for n in merged:
+        glabel[n] = glabel[find(n)]
+    n_global = int(is_new.sum())
+    luts = []
+    for r in range(len(counts)):
+        lut = np.zeros(counts[r] + 1, dtype=np.uint32)
+        lut[1:] = glabel[off[r] + 1: off[r] + counts[r] + 1]
+        luts.append(lut)
+    return luts, n_global
+
+
+def merge_tables(tables, luts, z_offsets, n_global, shape_real):
+    """Exact merge of per-slab statistics (local z coordinates) into the global table rows 0..N."""
+    counts = np.zeros(n_global + 1, dtype=np.uint64)
+    sums = np.zeros((n_global + 1, 3), dtype=np.uint64)
+    Z, Y, X = shape_real
+    bbox = np.tile(np.array([Z, -1, Y, -1, X, -1], dtype=np.int64), (n_global + 1, 1))
+    for t, lut, z0 in zip(tables, luts, z_offsets):
+        if t is None:
+            continue
+        g = lut.astype(np.int64)            # row l -> global row (row 0 -> 0 = background)
+        c = t["voxel_counts"].astype(np.uint64)
+        s = t["sums"].astype(np.uint64).copy()
+        s[:, 0] += c * np.uint64(z0)
+        b = t["bounding_boxes"].astype(np.int64).copy()
+        has = b[:, 1] >= 0
+        b[has, 0] += z0
+        b[has, 1] += z0
+        np.add.at(counts, g, c)
+        np.add.at(sums, g, s)
+        for k in (0, 2, 4):
+            np.minimum.at(bbox[:, k], g[has], b[has, k])
+            np.maximum.at(bbox[:, k + 1], g[has], b[has, k + 1])
+    with np.errstate(invalid="ignore", divide="ignore"):
+        cent = sums.astype(np.float64) / counts.astype(np.float64)[:, None]
+    return {"n": n_global, "voxel_counts": counts, "sums": sums, "bounding_boxes": bbox, "centroids": cent}
+
+
+# ------------------------------------------------------------------------------------------- communication
+class TorchComm:
+    """torch.distributed point-to-point + all_gather_object (NCCL on GPUs, gloo on CPU)."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = dist.get_world_size()
+        self.rank = dist.get_rank()
+
+    def send(self, tensor, src, dst, tag):
+        self.dist.send(tensor.contiguous(), dst=dst)
+
+    def recv(self, like, src, dst, tag):
+        self.dist.recv(like, src=src)
+        return like
+
+    def allgather(self, obj):
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+
+# ------------------------------------------------------------------------------------------- CUDA worker
+class CudaSlabWorker:
+    """One rank's compute, every stage through libdelivr_b200.so."""
+
+    def __init__(self, ctx, plan, rank, planes_fn, window_batch=0, threshold=0.5, tta=False, erosion_block_planes=0):
+        import torch
+        self.torch = torch
+        self.ctx, self.plan, self.r = ctx, plan, rank
+        self.info = plan.rank(rank)
+        self.dev = torch.device("cuda", ctx.device)
+        self.window_batch, self.threshold, self.tta, self.ebp = window_batch, threshold, tta, erosion_block_planes
+        z0, z1 = self.info["slab"]
+        self.slab = planes_fn(z0, z1) if z1 > z0 else None            # uint16 (z1-z0, PY, PX) on the device
+        self.acc = None
+
+    def accumulate(self):
+        torch = self.torch
+        if self.slab is None:
+            return np.zeros(0, dtype=np.int32)
+        z0 = self.info["slab"][0]
+        wins = self.plan.windows_of(self.r)
+        local = wins.copy()
+        local[:, 0] -= z0
+        active = self.ctx.windows_active(self.slab, local, self.plan.roi)
+        sel = local[active != 0]
+        flips = [0, 0, 2, 3, 0, 2, 3, 0, 2, 3, 0, 2, 3] if self.tta else [0]      # inference.py:265-279
+        sched = np.concatenate([np.concatenate([sel, np.full((len(sel), 1), f, dtype=np.int32)], axis=1) for f in flips]) \
+            if len(sel) else np.zeros((0, 4), dtype=np.int32)
+        self.acc = torch.zeros(self.slab.shape, dtype=torch.int32, device=self.dev)
+        self.ctx.seg_accumulate(self.slab, sched, self.plan.roi, self.acc, window_batch=self.window_batch)
+        return active
+
+    def acc_planes(self, g0, g1):
+        z0 = self.info["slab"][0]
+        return self.acc[g0 - z0: g1 - z0]
+
+    def add_planes(self, g0, g1, t):
+        z0 = self.info["slab"][0]
+        self.acc[g0 - z0: g1 - z0] += t
+
+    def finalise(self, active_global):
+        torch = self.torch
+        o0, o1 = self.info["own_real"]
+        Z, Y, X = self.plan.shape_real
+        if self.slab is None or o1 <= o0:
+            self.binaries = torch.zeros((0, Y, X), dtype=torch.uint8, device=self.dev)
+            return self.binaries
+        z0, z1 = self.info["slab"]
+        self.ctx.seg_average(self.acc, z1 - z0, z0, self.plan.shape_pad, self.plan.roi, self.plan.overlap, active_global,
+                             passes=13 if self.tta else 1)
+        avg = self.acc.view(torch.float32)
+        self.binaries = torch.empty((o1 - o0, Y, X), dtype=torch.uint8, device=self.dev)
+        self.ctx.op_finalise_slab(avg, self.slab, z1 - z0, z0, self.plan.shape_real, o0, o1, self.binaries,
+                                  threshold=self.threshold, erosion_iters=self.plan.iters, erosion_block_planes=self.ebp)
+        self.acc = None
+        return self.binaries
+
+    def ccl(self):
+        torch = self.torch
+        self.labels = torch.empty(self.binaries.shape, dtype=torch.int32, device=self.dev)
+        if self.binaries.shape[0] == 0:
+            self.table = None
+            return 0
+        self.table = self.ctx.ccl(self.binaries, self.binaries.shape, labels_out=self.labels)
+        return self.table["n"]
+
+    def first_plane(self):
+        return self.labels[0]
+
+    def last_plane(self):
+        return self.labels[-1]
+
+    def empty_plane(self):
+        Z, Y, X = self.plan.shape_real
+        return self.torch.empty((Y, X), dtype=self.torch.int32, device=self.dev)
+
+    def boundary_pairs(self, lo_plane):
+        return self.ctx.ccl_boundary_pairs(lo_plane, self.labels[0])
+
+    def relabel(self, lut):
+        if self.labels.numel():
+            self.ctx.relabel(self.labels, self.torch.from_numpy(lut.view(np.int32)).to(self.dev))
+
+
+# ------------------------------------------------------------------------------------------- drivers
+def run_virtual(workers, plan):
+    """All ranks in this process (LocalComm).  Returns the merged table; workers keep binaries / labels."""
+    world = plan.world
+    active = [w.accumulate() for w in workers]
+    for r in range(world):                                    # exchange 1: logit halo, r -> next non-empty rank
+        info = plan.rank(r)
+        q = plan._next_nonempty(r)
+        if info["send"] is not None and q is not None:
+            g0, g1 = info["send"]
+            workers[q].add_planes(g0, g1, workers[r].acc_planes(g0, g1))
+    active_global = np.concatenate(active) if active else np.zeros(0, np.int32)   # exchange 2
+    for w in workers:
+        w.finalise(active_global)
+    counts = [w.ccl() for w in workers]
+    pairs = [None] * world                                    # exchange 3: boundary label planes
+    for r in range(world):
+        p = _prev_with_planes(workers, r)
+        if p is not None and workers[r].labels.shape[0] > 0:
+            pairs[r] = (p, workers[r].boundary_pairs(workers[p].last_plane()))
+    return _merge(workers, plan, counts, pairs)
+
+
+def _prev_with_planes(workers, r):
+    for q in range(r - 1, -1, -1):
+        if workers[q].labels.shape[0] > 0:
+            return q
+    return None
+
+
+def _merge(workers, plan, counts, pairs_with_src):
+    """Shared tail of both drivers when every rank's objects are at hand (virtual mode)."""
+    world = plan.world
+    # re-express pairs against the chain of non-empty slabs: resolve_global_labels expects (r-1, r) adjacency
+    nonempty = [r for r in range(world) if counts[r] > 0 or workers[r].labels.shape[0] > 0]
+    idx = {r: i for i, r in enumerate(nonempty)}
+    c2 = [counts[r] for r in nonempty]
+    p2 = [None] * len(nonempty)
+    for r in nonempty:
+        if pairs_with_src[r] is not None:
+            src, p = pairs_with_src[r]
+            assert idx[src] == idx[r] - 1
+            p2[idx[r]] = p
+    luts2, n_global = resolve_global_labels(c2, p2)
+    luts = [np.zeros(1, np.uint32)] * world
+    for r in nonempty:
+        luts[r] = luts2[idx[r]]
+        workers[r].relabel(luts[r])
+    tables = [w.table for w in workers]
+    zoff = [plan.rank(r)["own_real"][0] for r in range(world)]
+    return merge_tables(tables, luts, zoff, n_global, plan.shape_real)
+
+
+def run_distributed(worker, plan, comm):
+    """One rank per process.  Collectives: send/recv of the logit halo and of one label plane, two object all-gathers."""
+    r, world = comm.rank, comm.world
+    info = plan.rank(r)
+    active = worker.accumulate()
+    nxt, prv = plan._next_nonempty(r), plan._prev_nonempty(r)
+    have = info["layers"][1] > info["layers"][0]
+    # exchange 1 (even ranks send first to avoid head-of-line blocking on blocking backends)
+    def _send():
+        if have and info["send"] is not None and nxt is not None:
+            g0, g1 = info["send"]
+            comm.send(worker.acc_planes(g0, g1), r, nxt, "acc")
+
+    def _recv():
+        if have and info["recv"] is not None and prv is not None:
+            g0, g1 = info["recv"]
+            buf = worker.acc_planes(g0, g1).clone()
+            worker.add_planes(g0, g1, comm.recv(buf, prv, r, "acc"))
+
+    if r % 2 == 0:
+        _send(); _recv()
+    else:
+        _recv(); _send()
+    active_global = np.concatenate(comm.allgather(np.asarray(active, dtype=np.int32)))     # exchange 2
+    worker.finalise(active_global)
+    n_local = worker.ccl()
+    nplanes = comm.allgather(int(worker.labels.shape[0]))
+    src = next((q for q in range(r - 1, -1, -1) if nplanes[q] > 0), None)
+    dst = next((q for q in range(r + 1, world) if nplanes[q] > 0), None)
+    pairs = None
+
+    def _send_l():
+        if nplanes[r] > 0 and dst is not None:
+            comm.send(worker.last_plane(), r, dst, "lab")
+
+    def _recv_l():
+        nonlocal pairs
+        if nplanes[r] > 0 and src is not None:
+            lo = comm.recv(worker.empty_plane(), src, r, "lab")
+            pairs = worker.boundary_pairs(lo)
+
+    order = [q for q in range(world) if nplanes[q] > 0]
+    pos = order.index(r) if r in order else 0
+    if pos % 2 == 0:
+        _send_l(); _recv_l()
+    else:
+        _recv_l(); _send_l()
+    gathered = comm.allgather((n_local, pairs, worker.table))                               # exchange 3
+    counts = [g[0] for g in gathered]
+    c2 = [counts[q] for q in order]
+    p2 = [gathered[q][1] for q in order]
+    luts2, n_global = resolve_global_labels(c2, p2)
+    luts = [np.zeros(1, np.uint32)] * world
+    for i, q in enumerate(order):
+        luts[q] = luts2[i]
+    worker.relabel(luts[r])
+    zoff = [plan.rank(q)["own_real"][0] for q in range(world)]
+    return merge_tables([g[2] for g in gathered], luts, zoff, n_global, plan.shape_real)
+
+
+# ------------------------------------------------------------------------------------------- bench entry (N > 1)
+def bench_main(args, rank, local_rank, world):
+    """bench.py --gpus N: weak scaling - every rank holds a cfg2-sized share of an N-times taller volume."""
+    import json
+    import torch
+    import torch.distributed as dist
+    from . import Context
+    from .synth import synth_volume_cuda
+    import bench as B
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    wl = B.WORKLOADS[args.workload]
+    z1, Y, X = wl["shape"]
+    shape = (z1 * world, Y, X)
+    sd, wdesc = B.state_dict()
+    ctx = Context(local_rank)
+    ctx.load_weights(sd)
+    plan = SlabPlan(shape, B.ROI, B.OVERLAP, world)
+    info = plan.rank(rank)
+    PY, PX = plan.shape_pad[1], plan.shape_pad[2]
+
+    def planes(z0, z1_):
+        full = torch.zeros((z1_ - z0, PY, PX), dtype=torch.uint16, device=dev)
+        r0, r1 = min(z0, shape[0]), min(z1_, shape[0])
+        if r1 > r0:
+            full[: r1 - r0, :Y, :X] = synth_volume_cuda(shape, wl["seed"], device=dev, z_range=(r0, r1))
+        return full
+
+    from .inference.inference import erosion_block_planes
+    ebp = erosion_block_planes(shape)
+    slab = planes(*info["slab"])
+    comm = TorchComm()
+
+    def step():
+        w = CudaSlabWorker(ctx, plan, rank, lambda a, b: slab, erosion_block_planes=ebp)
+        return run_distributed(w, plan, comm), w
+
+    for _ in range(args.warmup):
+        table, w = step()
+    stream = torch.cuda.ExternalStream(ctx._L.dlv_stream(ctx._h), device=dev)
+    dist.barrier()
+    torch.cuda.synchronize()
+    sampler = B.ClockSampler(local_rank) if rank == 0 else None
+    l0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        table, w = step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    dt = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)      # device time, max over ranks
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    ms = float(dt.item()) * 1e3 / args.steps
+    launches = torch.tensor([ctx.launches - l0], device=dev, dtype=torch.int64)
+    dist.all_reduce(launches)
+    if rank == 0:
+        nvox = int(np.prod(shape))
+        v = nvox / (ms * 1e-3) / 1e9
+        print(json.dumps({
+            "metric": "Gvoxels/s seg+CC", "value": v, "unit": "Gvoxels/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": f"synthetic; {wdesc}",
+            "config": {"workload": f"{wl['name']} x {world} stacked along z ({shape[0]}x{Y}x{X}), z-slab sharded",
+                       "window": list(B.ROI), "overlap": B.OVERLAP, "tta": False, "components": table["n"],
+                       "layers_per_rank": plan.layers, "timing": "CUDA events on the library stream between barriers, max over ranks",
+                       "l2": "inputs larger than L2"},
+            "gpu_launches": int(launches.item()), "clocks": sampler.stop(),
+            "e2e": {"value": v, "unit": "Gvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "note": "device-resident slabs; host-buffer e2e is measured at N=1"},
+        }))
+    dist.destroy_process_group()

@@ -148,6 +148,38 @@ int dlv_op_finalise(dlv_ctx* ctx, const float* avg_logits_dev, const uint16_t* v
                     const int64_t shape_real[3], float threshold, int erosion_iters, int64_t erosion_block_planes,
                     uint8_t* binaries_dev, float* sigmoid_dev_or_null);
 
+/* ---- slab-level entry points (z-sharded runs: one process per GPU, see delivr_cfos_b200/slabs.py) ----
+ * A slab is a contiguous range of planes of the padded volume held by one GPU.  The stages of dlv_segment
+ * are exposed separately so that the host can exchange the blended-logit halo and the boundary labels
+ * between neighbouring GPUs (NCCL) in between. */
+
+/* Window grid of sliding_window_inferer.py:140-143 (_get_scan_interval + dense_patch_slices): per-dimension
+ * window counts and, if starts_out != NULL, the concatenated start lists (z starts, y starts, x starts). */
+int dlv_window_grid(const int64_t shape_pad[3], const int32_t roi[3], float overlap, int32_t counts_out[3], int32_t* starts_out);
+/* Skip rule (sliding_window_inferer.py:198): active_host[i] = max over window i > 0.  origins are local to the slab. */
+int dlv_windows_active(dlv_ctx* ctx, const uint16_t* slab_dev, int64_t SY, int64_t SX, const int32_t* origins_host, int n,
+                       const int32_t roi[3], int32_t* active_host);
+/* Gather + U-Net + blend for n scheduled windows.  windows_host[i] = {oz, oy, ox, flip_dim (0|2|3|4)}, origins local
+ * to the slab; acc_dev: int32, same extent as the slab, fixed point 2^-12 logit units (+=, order independent). */
+int dlv_seg_accumulate(dlv_ctx* ctx, const uint16_t* slab_dev, int64_t SY, int64_t SX, const int32_t* windows_host, int n,
+                       const int32_t roi[3], int window_batch, int blend_mode, int32_t* acc_dev);
+/* In-place int32 sums -> float32 averaged logits for planes [gz0, gz0+nplanes) of the padded volume
+ * (inference.py:285-299); active_host is the whole window grid [nz][ny][nx] (skipped windows contribute -1000). */
+int dlv_seg_average(dlv_ctx* ctx, int32_t* acc_dev_inout, int64_t nplanes, int64_t gz0, const int64_t shape_pad[3],
+                    const int32_t roi[3], float overlap, const int32_t* active_host, int passes, int blend_mode);
+/* create_nifti_seg (inference.py:60-88) on a slab: avg/volume hold planes [gz0, gz0+nplanes) with in-plane strides
+ * SY,SX; binaries for global planes [oz0, oz1) are written (first plane = oz0).  The slab must contain every plane
+ * within erosion_iters of [oz0, oz1) that lies in the same Arrayterator block. */
+int dlv_op_finalise_slab(dlv_ctx* ctx, const float* avg_dev, const uint16_t* volume_dev, int64_t SY, int64_t SX, int64_t nplanes,
+                         int64_t gz0, const int64_t shape_real[3], float threshold, int erosion_iters, int64_t erosion_block_planes,
+                         int64_t oz0, int64_t oz1, uint8_t* binaries_dev, float* sigmoid_dev_or_null);
+/* 26-adjacent label pairs (lo label, hi label) across a slab boundary; pairs_dev uint32[cap][2]; *count may exceed cap
+ * (then call again with a larger buffer).  Duplicates are possible. */
+int dlv_ccl_boundary_pairs(dlv_ctx* ctx, const uint32_t* labels_lo_plane_dev, const uint32_t* labels_hi_plane_dev, int64_t Y, int64_t X,
+                           uint32_t* pairs_dev, int64_t cap, int64_t* count_host_out);
+/* labels[i] = map[labels[i]] for non-zero labels (local -> global component numbers). */
+int dlv_relabel(dlv_ctx* ctx, uint32_t* labels_dev, int64_t n, const uint32_t* map_dev, int64_t nmap);
+
 #ifdef __cplusplus
 }
 #endif

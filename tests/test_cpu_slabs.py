@@ -1,0 +1,214 @@
+"""Host logic of the z-slab sharding (no GPU): planning, global label resolution, table merge, and the
+distributed driver over gloo with world_size 2 (an oracle-backed worker stands in for the CUDA worker)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from delivr_cfos_b200 import slabs
+from oracle import ccl_ref, pipeline_ref as P
+
+
+def _starts(shape_pad, roi, overlap):
+    return P.window_starts(shape_pad, roi, P.scan_interval(shape_pad, roi, overlap))
+
+
+def test_plan_covers_volume_once():
+    for shape, roi, world in [((1500, 400, 400), (96, 96, 64), 8), ((256, 64, 64), (96, 96, 64), 2), ((100, 80, 70), (32, 32, 32), 3),
+                              ((64, 64, 64), (32, 32, 32), 5)]:
+        pad = P.padded_shape(shape, roi)
+        plan = slabs.SlabPlan(shape, roi, 0.5, world, starts=_starts(pad, roi, 0.5))
+        owned = np.zeros(pad[0], int)
+        layers = []
+        for r in range(world):
+            info = plan.rank(r)
+            layers += list(range(*info["layers"]))
+            owned[info["own"][0]:info["own"][1]] += 1
+            if info["layers"][1] > info["layers"][0]:
+                assert info["slab"][0] <= info["own"][0] and info["slab"][1] >= info["win"][1]
+                assert info["slab"][0] <= max(0, info["own"][0] - 31) and info["slab"][1] >= min(pad[0], info["own"][1] + 31)
+                if info["send"]:
+                    q = plan._next_nonempty(r)
+                    assert plan.rank(q)["recv"] == info["send"]
+        assert layers == list(range(len(plan.sz)))
+        assert (owned == 1).all()
+
+
+def _slab_tables(mask, cuts):
+    tabs, labs = [], []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        lab, n = ccl_ref.connected_components26(mask[a:b])
+        st = ccl_ref.statistics(lab, n)
+        tabs.append({"n": n, **st})
+        labs.append(lab)
+    return tabs, labs
+
+
+def _pairs(lo_plane, hi_plane):
+    out = set()
+    Y, X = hi_plane.shape
+    for y, x in zip(*np.nonzero(hi_plane)):
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                yy, xx = y + dy, x + dx
+                if 0 <= yy < Y and 0 <= xx < X and lo_plane[yy, xx]:
+                    out.add((int(lo_plane[yy, xx]), int(hi_plane[y, x])))
+    return np.array(sorted(out), dtype=np.uint32).reshape(-1, 2)
+
+
+@pytest.mark.parametrize("seed,cuts", [(0, [0, 7, 20]), (1, [0, 5, 6, 13, 20]), (2, [0, 10, 11, 12, 20])])
+def test_label_resolution_and_table_merge_exact(seed, cuts):
+    rng = np.random.default_rng(seed)
+    mask = (rng.random((20, 24, 28)) < 0.12).astype(np.uint8)
+    mask[3:18, 5, 5] = 1                      # a component threading through every slab
+    ref_lab, ref_n = ccl_ref.connected_components26(mask)
+    ref = ccl_ref.statistics(ref_lab, ref_n)
+    tabs, labs = _slab_tables(mask, cuts)
+    pairs = [None] + [_pairs(labs[i - 1][-1], labs[i][0]) for i in range(1, len(labs))]
+    luts, n = slabs.resolve_global_labels([t["n"] for t in tabs], pairs)
+    assert n == ref_n
+    merged = np.concatenate([lut[lab] for lut, lab in zip(luts, labs)])
+    assert np.array_equal(merged, ref_lab)
+    table = slabs.merge_tables(tabs, luts, cuts[:-1], n, mask.shape)
+    assert np.array_equal(table["voxel_counts"], ref["voxel_counts"])
+    assert np.array_equal(table["sums"], ref["sums"])
+    assert np.array_equal(table["bounding_boxes"], ref["bounding_boxes"])
+    assert np.array_equal(table["centroids"], ref["centroids"], equal_nan=True)
+
+
+class OracleWorker:
+    """CPU stand-in for CudaSlabWorker (same interface) built on the oracle: a fake 'network' whose logit is a
+    deterministic function of the voxel value, integer accumulation, oracle erosion / CCL."""
+
+    def __init__(self, plan, rank, volume):
+        self.plan, self.r = plan, rank
+        self.info = plan.rank(rank)
+        z0, z1 = self.info["slab"]
+        self.slab = volume[z0:z1]
+        self.volume = volume
+
+    def accumulate(self):
+        z0 = self.info["slab"][0]
+        rz, ry, rx = self.plan.roi
+        self.acc = torch.zeros(self.slab.shape, dtype=torch.int32)
+        act = []
+        for (z, y, x) in self.plan.windows_of(self.r):
+            w = self.slab[z - z0:z - z0 + rz, y:y + ry, x:x + rx].astype(np.int64)
+            a = int(w.max() > 0)
+            act.append(a)
+            if a:
+                logit = np.where(w % 9 == 0, 4096, -4096)          # fixed-point logits in 2^-12 units, ~11 % foreground
+                self.acc[z - z0:z - z0 + rz, y:y + ry, x:x + rx] += torch.from_numpy(logit.astype(np.int32))
+        return np.array(act, dtype=np.int32)
+
+    def acc_planes(self, g0, g1):
+        z0 = self.info["slab"][0]
+        return self.acc[g0 - z0:g1 - z0]
+
+    def add_planes(self, g0, g1, t):
+        z0 = self.info["slab"][0]
+        self.acc[g0 - z0:g1 - z0] += t
+
+    def finalise(self, active_global):
+        o0, o1 = self.info["own_real"]
+        Z, Y, X = self.plan.shape_real
+        z0 = self.info["slab"][0]
+        acc = self.acc.numpy()[o0 - z0:o1 - z0, :Y, :X]
+        mask = ccl_ref.erode6((self.volume[:Z, :Y, :X] > 0).astype(np.uint8), self.plan.iters)[o0:o1]   # one global block
+        self.binaries = torch.from_numpy(((acc >= 0) & (mask > 0)).astype(np.uint8))
+        return self.binaries
+
+    def ccl(self):
+        if self.binaries.shape[0] == 0:
+            self.labels, self.table = torch.zeros((0,) + self.binaries.shape[1:], dtype=torch.int32), None
+            return 0
+        lab, n = ccl_ref.connected_components26(self.binaries.numpy())
+        self.table = {"n": n, **ccl_ref.statistics(lab, n)}
+        self.labels = torch.from_numpy(lab.astype(np.int32))
+        return n
+
+    def last_plane(self):
+        return self.labels[-1].contiguous()
+
+    def empty_plane(self):
+        return torch.empty(self.plan.shape_real[1:], dtype=torch.int32)
+
+    def boundary_pairs(self, lo):
+        return _pairs(lo.numpy(), self.labels[0].numpy())
+
+    def relabel(self, lut):
+        self.labels = torch.from_numpy(lut.astype(np.int64)[self.labels.numpy()].astype(np.int32))
+
+
+def _make_volume(shape, roi):
+    rng = np.random.default_rng(5)
+    pad = P.padded_shape(shape, roi)
+    vol = np.zeros(pad, dtype=np.uint16)
+    vol[:shape[0], :shape[1], :shape[2]] = rng.integers(1, 60000, size=shape)
+    vol[:2] = 0
+    return vol
+
+
+def _single(volume, shape, roi):
+    pad = volume.shape
+    plan = slabs.SlabPlan(shape, roi, 0.5, 1, starts=_starts(pad, roi, 0.5), erosion_iters=3)
+    w = OracleWorker(plan, 0, volume)
+    table = slabs.run_virtual([w], plan)
+    return w, table
+
+
+def _gloo_worker(rank, world, port, shape, roi, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    volume = _make_volume(shape, roi)
+    plan = slabs.SlabPlan(shape, roi, 0.5, world, starts=_starts(volume.shape, roi, 0.5), erosion_iters=3)
+    w = OracleWorker(plan, rank, volume)
+    table = slabs.run_distributed(w, plan, slabs.TorchComm())
+    q.put((rank, w.binaries.numpy(), w.labels.numpy(), table))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_distributed_driver_gloo_world2():
+    shape, roi, world = (40, 24, 24), (16, 16, 16), 2
+    volume = _make_volume(shape, roi)
+    w1, t1 = _single(volume, shape, roi)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, shape, roi, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    b = np.concatenate([r[1] for r in res])
+    lab = np.concatenate([r[2] for r in res])
+    assert np.array_equal(b, w1.binaries.numpy())
+    assert np.array_equal(lab, w1.labels.numpy())
+    for r in res:
+        t = r[3]
+        assert t["n"] == t1["n"] and t["n"] > 2
+        assert np.array_equal(t["voxel_counts"], t1["voxel_counts"])
+        assert np.array_equal(t["sums"], t1["sums"])
+        assert np.array_equal(t["bounding_boxes"], t1["bounding_boxes"])
+
+
+def test_virtual_slabs_equal_single_oracle():
+    shape, roi = (50, 24, 24), (16, 16, 16)
+    volume = _make_volume(shape, roi)
+    w1, t1 = _single(volume, shape, roi)
+    for world in (2, 3, 6):
+        plan = slabs.SlabPlan(shape, roi, 0.5, world, starts=_starts(volume.shape, roi, 0.5), erosion_iters=3)
+        ws = [OracleWorker(plan, r, volume) for r in range(world)]
+        t = slabs.run_virtual(ws, plan)
+        assert np.array_equal(np.concatenate([w.binaries.numpy() for w in ws]), w1.binaries.numpy())
+        assert np.array_equal(np.concatenate([w.labels.numpy() for w in ws]), w1.labels.numpy())
+        assert t["n"] == t1["n"] and np.array_equal(t["sums"], t1["sums"])
