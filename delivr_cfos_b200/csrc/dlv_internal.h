@@ -19,7 +19,7 @@ typedef __nv_bfloat16 bf16;
 // Activations live in a zero-haloed, channel-chunked, position-linear layout
 //     A[chunk = C/8][S positions][8 channels]   (bf16, 16 B per position and chunk)
 // position P = guard + win*Vp + (zp*Yp + yp)*Xp + xp with zp in [0,Z+2), yp in [0,Y+2),
-// xp in [0,X+1); interior voxel (z,y,x) sits at (z+1, y+1, x+1).  Halo positions and the
+// xp in [0,X+1) and Vp = Zp*Yp*Xp rounded up to a multiple of 128; interior voxel (z,y,x) sits at (z+1, y+1, x+1).  Halo positions and the
 // guard zones are zero and are never written, so a 3x3x3 zero-padded convolution is a 1-D
 // correlation over P with the 27 constant offsets dz*Yp*Xp + dy*Xp + dx (the single x halo
 // column separates consecutive rows).

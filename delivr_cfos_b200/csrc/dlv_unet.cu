@@ -208,7 +208,10 @@ static Level make_level(int Z, int Y, int X, int batch) {
     L.Z = Z; L.Y = Y; L.X = X;
     L.Zp = Z + 2; L.Yp = Y + 2; L.Xp = X + 1;
     L.YpXp = L.Yp * L.Xp;
-    L.Vp = L.Zp * L.YpXp;
+    // window stride in positions, rounded to whole 128-row MMA tiles: every window then sees the same tile /
+    // warp-tile boundaries whatever its slot in the batch, so its InstanceNorm partial sums (fp32 per 32 rows)
+    // are grouped identically -> per-window results do not depend on batch composition or slab partition.
+    L.Vp = ((L.Zp * L.YpXp + 127) / 128) * 128;
     L.guard = ((L.YpXp + L.Xp + 1 + 7) / 8) * 8;
     const int64_t np = static_cast<int64_t>(batch) * L.Vp;
     L.S = L.guard + ((np + 1023) / 1024) * 1024 + L.guard + 1024 + 64;
