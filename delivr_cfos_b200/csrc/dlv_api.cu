@@ -1,6 +1,7 @@
 // dlv_api.cu - context management and the extern "C" surface declared in include/delivr_b200.h
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -53,6 +54,8 @@ int dlv_init(int device, dlv_ctx** out) {
         return DLV_ERR_UNSUPPORTED;
     }
     ctx->num_sms = prop.multiProcessorCount;
+    if (const char* e = getenv("DLV_FUSED")) ctx->use_fused = atoi(e) != 0;
+    if (const char* e = getenv("DLV_IS_T")) ctx->is_tiles = atoi(e);
     DLV_CUDA_OK(ctx, cudaSetDevice(device));
     DLV_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     DLV_CUDA_OK(ctx, cudaEventCreate(&ctx->ev0));

@@ -41,6 +41,7 @@ struct ConvLayer {
     int KB = 0;        // cin_pad / 16
     int ntaps = 27;    // 27 (3x3x3 conv) or 1 (k2s2 transposed conv, 8 sub-positions folded into NB)
     bf16* w = nullptr;         // packed operand tiles [KB][NB][ntaps][2][nblk][8]
+    bf16* w_is = nullptr;      // Cout = 32 conv layers: input-stationary packing [KB][9 (ky,kx)][2][96 = (kz 2,1,0) x 32][8]
     float* gamma = nullptr;    // InstanceNorm affine (conv layers)
     float* beta = nullptr;
     float* bias = nullptr;     // transposed-conv bias
@@ -69,6 +70,8 @@ struct Ctx {
     bool time_convs = false;
     double ccl_ms = 0.0;
     int64_t ccl_launches = 0;
+    bool use_fused = true;      // Cout = 32 layers on the input-stationary fused kernel (DLV_FUSED=0 selects the per-tap kernel)
+    int is_tiles = 0;           // 0 = heuristic; 2 / 4 force the tile count per column (DLV_IS_T)
 };
 
 void set_error(Ctx* ctx, const char* fmt, ...);

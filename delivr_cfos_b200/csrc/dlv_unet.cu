@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 
+#include "dlv_conv_is.cuh"
 #include "dlv_conv_tc.cuh"
 #include "dlv_internal.h"
 
@@ -91,7 +92,7 @@ __global__ void norm_mish_kernel(const __nv_bfloat16* __restrict__ raw, LevelDev
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] = mish_f(fmaf(f[i], a[i], b[i]));
         uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-        *reinterpret_cast<uint4*>(out + cbase + P * 8) = o;
+        if (out) *reinterpret_cast<uint4*>(out + cbase + P * 8) = o;
         // pooling compares the bf16-rounded activations (what the next layer would read)
         m[0] = fmaxf(m[0], bf16_lo(o.x)); m[1] = fmaxf(m[1], bf16_hi(o.x));
         m[2] = fmaxf(m[2], bf16_lo(o.y)); m[3] = fmaxf(m[3], bf16_hi(o.y));
@@ -256,6 +257,32 @@ static int pack_conv(Ctx* ctx, ConvLayer& L, const float* W, bool first) {
     return upload(ctx, pk.data(), pk.size() * sizeof(bf16), reinterpret_cast<void**>(&L.w));
 }
 
+// Cout = 32 layers, input-stationary kernel: W[32][cin][3][3][3] -> [KB][9 (ky,kx)][2][96][8]; the 96 B rows are the
+// three kz blocks in the order of the output planes they feed (z-1: kz = 2, z: kz = 1, z+1: kz = 0).
+static int pack_conv_is(Ctx* ctx, ConvLayer& L, const float* W, bool first) {
+    std::vector<bf16> pk(static_cast<size_t>(L.KB) * 9 * 2 * 96 * 8, to_bf16(0.f));
+    for (int kb = 0; kb < L.KB; ++kb)
+        for (int tap = 0; tap < 9; ++tap)
+            for (int kc = 0; kc < 2; ++kc)
+                for (int row = 0; row < 96; ++row)
+                    for (int e = 0; e < 8; ++e) {
+                        const int kz = 2 - row / 32, co = row % 32, ci = kb * 16 + kc * 8 + e;
+                        const int t27 = kz * 9 + tap;
+                        float v = 0.f;
+                        if (first) {
+                            if (ci < 4) {
+                                const float w = W[static_cast<size_t>(co) * 27 + t27];
+                                const float wh = __bfloat162float(to_bf16(w));
+                                v = (ci < 2) ? wh : (w - wh);
+                            }
+                        } else if (ci < L.cin) {
+                            v = W[(static_cast<size_t>(co) * L.cin + ci) * 27 + t27];
+                        }
+                        pk[((((static_cast<size_t>(kb) * 9 + tap) * 2 + kc) * 96 + row) * 8) + e] = to_bf16(v);
+                    }
+    return upload(ctx, pk.data(), pk.size() * sizeof(bf16), reinterpret_cast<void**>(&L.w_is));
+}
+
 static int pack_deconv(Ctx* ctx, ConvLayer& L, const float* W) {
     // W[cin][cout][2][2][2] (torch ConvTranspose3d) -> [KB][NB = 8*cout/nblk][1][2][nblk][8]
     L.ntaps = 1;
@@ -295,7 +322,7 @@ static const ConvSpec kDeconvs[] = {{"upcat_4", 256, 128}, {"upcat_3", 128, 64},
 void net_free(Ctx* ctx) {
     for (auto* m : {&ctx->net.conv, &ctx->net.deconv})
         for (auto& kv : *m) {
-            cudaFree(kv.second.w); cudaFree(kv.second.gamma); cudaFree(kv.second.beta); cudaFree(kv.second.bias);
+            cudaFree(kv.second.w); cudaFree(kv.second.w_is); cudaFree(kv.second.gamma); cudaFree(kv.second.beta); cudaFree(kv.second.bias);
         }
     ctx->net.conv.clear();
     ctx->net.deconv.clear();
@@ -333,6 +360,7 @@ int net_load(Ctx* ctx, int n, const char* const* names, const float* const* data
         if ((rc = need(L.name + ".adn.N.weight", s.cout, &g))) return rc;
         if ((rc = need(L.name + ".adn.N.bias", s.cout, &be))) return rc;
         if ((rc = pack_conv(ctx, L, w, s.cin == 1))) return rc;
+        if (s.cout == 32 && (rc = pack_conv_is(ctx, L, w, s.cin == 1))) return rc;
         if ((rc = upload(ctx, g, s.cout * sizeof(float), reinterpret_cast<void**>(&L.gamma)))) return rc;
         if ((rc = upload(ctx, be, s.cout * sizeof(float), reinterpret_cast<void**>(&L.beta)))) return rc;
         ctx->net.conv[L.name] = L;
@@ -436,6 +464,121 @@ static int run_conv(Ctx* ctx, const ConvLayer& Ly, const Level& L, int nwin, con
     return rc;
 }
 
+
+// ------------------------------------------------------------------- input-stationary fused conv launcher (Cout = 32)
+struct IsPlan {
+    int T, S, RL, H, NC, NZS, Zs, nstages, nparts;
+    uint32_t stage_bytes, w_bytes, smem;
+};
+
+static bool plan_conv_is(const Ctx* ctx, const ConvLayer& Ly, const Level& L, int nwin, IsPlan& P) {
+    if (Ly.cout != 32 || Ly.ntaps != 27 || !Ly.w_is) return false;
+    const int PL = L.YpXp;
+    P.H = L.Xp + 1;
+    P.w_bytes = static_cast<uint32_t>(Ly.KB) * 9 * 3072;
+    const int nchunks = 2 * Ly.KB;
+    auto fits = [&](int T, int& nst, int& RL, uint32_t& sb) {
+        RL = ((128 * T + 2 * P.H + 7) / 8) * 8;
+        sb = static_cast<uint32_t>(nchunks) * RL * 16;
+        const uint32_t fixed = P.w_bytes + 128 * 4 + 256 * 8 + 256;
+        nst = 0;
+        for (int n = kIsMaxStages; n >= 2; --n)
+            if (fixed + static_cast<uint64_t>(n) * sb <= kSmemLimit) { nst = n; break; }
+        return nst >= 2 && RL <= 16383;
+    };
+    // cost model per tile and k-block: 9 taps x (56 clk for an N = 96 MMA, 88 where the slot ring wraps: 2 of S steps),
+    // times the column quantisation of the plane
+    int bestT = 0; double best = 1e30;
+    for (int T : {4, 2}) {
+        if (ctx->is_tiles && ctx->is_tiles != T) continue;
+        int nst, RL; uint32_t sb;
+        if (!fits(T, nst, RL, sb)) continue;
+        const int S = 16 / T, R = 128 * T;
+        const int NC = (PL + R - 1) / R;
+        const double mma = 9.0 * ((S - 2) * 56.0 + 2 * 88.0) / S;
+        const double cost = mma * (static_cast<double>(NC) * R / PL);
+        if (cost < best) { best = cost; bestT = T; }
+    }
+    if (!bestT) return false;
+    P.T = bestT; P.S = 16 / bestT;
+    fits(P.T, P.nstages, P.RL, P.stage_bytes);
+    P.NC = (PL + 128 * P.T - 1) / (128 * P.T);
+    // z segmentation: balance the persistent grid (each extra segment re-stages ~2 input planes)
+    int bestN = 1; double bestc = 1e30;
+    for (int n = 1; n <= 6 && n <= L.Z; ++n) {
+        const int Zs = (L.Z + n - 1) / n;
+        const int nseg = (L.Z + Zs - 1) / Zs;
+        if (nseg != n) continue;
+        const int64_t items = static_cast<int64_t>(nwin) * P.NC * n;
+        const int64_t waves = (items + ctx->num_sms - 1) / ctx->num_sms;
+        const double c = static_cast<double>(waves) * (Zs + (n > 1 ? 1.5 : 0.0));
+        if (c < bestc) { bestc = c; bestN = n; }
+    }
+    P.NZS = bestN;
+    P.Zs = (L.Z + bestN - 1) / bestN;
+    P.nparts = P.NZS * P.NC;
+    P.smem = kSmemLimit;        // always the full opt-in size: one CTA per SM owns all 512 TMEM columns
+    return true;
+}
+
+static const int kIsMaxParts = 6 * 64;     // upper bound on NZS * NC the partial-sum scratch is sized for
+
+template <int T, int S>
+static int launch_conv_is_t(Ctx* ctx, const IsArgs& a, int grid, uint32_t smem) {
+    auto k = conv_is_kernel<T, S>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        DLV_CUDA_OK(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        attr_set = true;
+    }
+    k<<<grid, kIsThreads, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    DLV_CUDA_OK(ctx, cudaGetLastError());
+    return 0;
+}
+
+// One Cout = 32 conv layer over nwin windows.  `xform`: the leading 4 chunks of in0 hold the RAW output of `prod`
+// (statistics in prod_stats) and get InstanceNorm + Mish applied while being staged.
+static int run_conv_is(Ctx* ctx, const ConvLayer& Ly, const Level& L, int nwin, const bf16* in0, int nch0, const bf16* in1,
+                       const ConvLayer* prod, const double* prod_stats, bf16* out, double* part, double* stats) {
+    IsPlan P;
+    if (!plan_conv_is(ctx, Ly, L, nwin, P) || P.nparts > kIsMaxParts) {
+        set_error(ctx, "conv %s: level %dx%dx%d does not fit the input-stationary kernel", Ly.name.c_str(), L.Z, L.Y, L.X);
+        return DLV_ERR_UNSUPPORTED;
+    }
+    IsArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in0 = in0; a.in1 = in1; a.nch0 = nch0; a.nchunks = 2 * Ly.KB;
+    a.xform_chunks = prod ? 4 : 0;
+    a.in_stats = prod_stats;
+    a.in_gamma = prod ? prod->gamma : nullptr;
+    a.in_beta = prod ? prod->beta : nullptr;
+    a.inS = L.S; a.in_guard = L.guard;
+    a.w = Ly.w_is; a.out = out; a.outS = L.S; a.out_guard = L.guard;
+    a.part = part; a.nparts = P.nparts;
+    a.Z = L.Z; a.Y = L.Y; a.X = L.X; a.Xp = L.Xp; a.PL = L.YpXp; a.Vp = L.Vp;
+    a.KB = Ly.KB; a.NC = P.NC; a.NZS = P.NZS; a.Zs = P.Zs;
+    a.nitems = nwin * P.NC * P.NZS;
+    a.RL = P.RL; a.H = P.H; a.nstages = P.nstages;
+    a.stage_bytes = P.stage_bytes; a.w_bytes = P.w_bytes;
+    a.inv_count = 1.0 / (static_cast<double>(L.Z) * L.Y * L.X);
+    const int grid = std::min(ctx->num_sms, a.nitems);
+    if (ctx->time_convs) cudaEventRecord(ctx->ev0, ctx->stream);
+    int rc = (P.T == 4) ? launch_conv_is_t<4, 4>(ctx, a, grid, P.smem) : launch_conv_is_t<2, 8>(ctx, a, grid, P.smem);
+    if (ctx->time_convs && rc == 0) {
+        cudaEventRecord(ctx->ev1, ctx->stream);
+        cudaEventSynchronize(ctx->ev1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        ctx->conv_ms += ms;
+    }
+    if (rc) return rc;
+    is_reduce_stats_kernel<<<nwin, 64, 0, ctx->stream>>>(part, P.nparts, stats);
+    ctx->launches++;
+    DLV_CUDA_OK(ctx, cudaGetLastError());
+    return 0;
+}
+
 // ------------------------------------------------------------------- engine (activation buffers for one roi/batch)
 struct Engine {
     int roi[3] = {0, 0, 0};
@@ -449,6 +592,7 @@ struct Engine {
     bf16 *p4 = nullptr, *d4a = nullptr, *x4 = nullptr;
     bf16* raw[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // pre-norm conv outputs, one per level
     double* stats = nullptr;     // [18 layers][batch][256][2]
+    double* part = nullptr;      // [batch][kIsMaxParts][64] partial sums of the layer in flight (fused path)
     std::vector<void*> allocs;
 };
 static const int kStatsPerLayer = 256 * 2;
@@ -495,6 +639,9 @@ int engine_prepare(Ctx* ctx, const int32_t roi[3], int batch) {
     DLV_CUDA_OK(ctx, cudaMalloc(&p, sizeof(double) * 18 * batch * kStatsPerLayer));
     e->allocs.push_back(p);
     e->stats = static_cast<double*>(p);
+    DLV_CUDA_OK(ctx, cudaMalloc(&p, sizeof(double) * batch * kIsMaxParts * 64));
+    e->allocs.push_back(p);
+    e->part = static_cast<double*>(p);
     DLV_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -533,6 +680,23 @@ static int deconv_block(Ctx* ctx, Engine* e, const char* name, int lvl_in, int n
     return run_conv(ctx, Ly, e->L[lvl_in], nwin, in, Ly.cin / 8, nullptr, out, e->L[lvl_in - 1], nullptr);
 }
 
+
+// Fused path: the eight Cout = 32 layers (levels 0 and 1) run on the input-stationary kernel, which normalises its
+// input while staging it; only pooled / deconv-input tensors still need an elementwise pass.
+static int fused_block(Ctx* ctx, Engine* e, int layer_idx, const char* name, int lvl, int nwin, const bf16* in0, int nch0,
+                       const bf16* in1, const char* prod_name, int prod_idx, bf16* out) {
+    const ConvLayer& Ly = ctx->net.conv.at(name);
+    const ConvLayer* prod = prod_name ? &ctx->net.conv.at(prod_name) : nullptr;
+    const double* pst = prod_name ? e->stats + static_cast<size_t>(prod_idx) * e->batch * kStatsPerLayer : nullptr;
+    double* st = e->stats + static_cast<size_t>(layer_idx) * e->batch * kStatsPerLayer;
+    return run_conv_is(ctx, Ly, e->L[lvl], nwin, in0, nch0, in1, prod, pst, out, e->part, st);
+}
+static int norm_block(Ctx* ctx, Engine* e, int layer_idx, const char* name, int lvl, int nwin, const bf16* raw, bf16* out, bf16* pooled) {
+    const ConvLayer& Ly = ctx->net.conv.at(name);
+    const double* st = e->stats + static_cast<size_t>(layer_idx) * e->batch * kStatsPerLayer;
+    return run_norm(ctx, Ly, e->L[lvl], nwin, raw, out, pooled, pooled ? &e->L[lvl + 1] : nullptr, st);
+}
+
 // everything after the gather: 18 convs, 4 deconvs, norms, final blend
 static int forward_from_in0(Ctx* ctx, int nwin, const WindowDesc* wd_dev, int32_t* acc, int64_t slabY,
                             int64_t slabX, const float* wz, const float* wy, const float* wx, float* logits_out) {
@@ -540,10 +704,24 @@ static int forward_from_in0(Ctx* ctx, int nwin, const WindowDesc* wd_dev, int32_
     int rc;
     DLV_CUDA_OK(ctx, cudaMemsetAsync(e->stats, 0, sizeof(double) * 18 * e->batch * kStatsPerLayer, ctx->stream));
 #define CB(i, name, lvl, a, na, b, out, pool) if ((rc = conv_block(ctx, e, i, name, lvl, nwin, a, na, b, out, pool))) return rc;
+    IsPlan probe;
+    const bool fused = ctx->use_fused && plan_conv_is(ctx, ctx->net.conv.at("upcat_1.convs.conv_0"), e->L[0], nwin, probe) &&
+                       plan_conv_is(ctx, ctx->net.conv.at("upcat_2.convs.conv_0"), e->L[1], nwin, probe);
+    const bf16* last_raw = e->raw[0];
+    if (fused) {
+#define FB(i, name, lvl, a, na, b, prod, pi, out) if ((rc = fused_block(ctx, e, i, name, lvl, nwin, a, na, b, prod, pi, out))) return rc;
+        FB(0, "conv_0.conv_0", 0, e->in0, 2, nullptr, nullptr, 0, e->c0a)
+        FB(1, "conv_0.conv_1", 0, e->c0a, 4, nullptr, "conv_0.conv_0", 0, e->x0)
+        if ((rc = norm_block(ctx, e, 1, "conv_0.conv_1", 0, nwin, e->x0, nullptr, e->p1))) return rc;
+        FB(2, "down_1.convs.conv_0", 1, e->p1, 4, nullptr, nullptr, 0, e->d1a)
+        FB(3, "down_1.convs.conv_1", 1, e->d1a, 4, nullptr, "down_1.convs.conv_0", 2, e->x1)
+        if ((rc = norm_block(ctx, e, 3, "down_1.convs.conv_1", 1, nwin, e->x1, nullptr, e->p2))) return rc;
+    } else {
     CB(0, "conv_0.conv_0", 0, e->in0, 2, nullptr, e->c0a, nullptr)
     CB(1, "conv_0.conv_1", 0, e->c0a, 4, nullptr, e->x0, e->p1)
     CB(2, "down_1.convs.conv_0", 1, e->p1, 4, nullptr, e->d1a, nullptr)
     CB(3, "down_1.convs.conv_1", 1, e->d1a, 4, nullptr, e->x1, e->p2)
+    }
     CB(4, "down_2.convs.conv_0", 2, e->p2, 4, nullptr, e->d2a, nullptr)
     CB(5, "down_2.convs.conv_1", 2, e->d2a, 8, nullptr, e->x2, e->p3)
     CB(6, "down_3.convs.conv_0", 3, e->p3, 8, nullptr, e->d3a, nullptr)
@@ -557,17 +735,27 @@ static int forward_from_in0(Ctx* ctx, int nwin, const WindowDesc* wd_dev, int32_
     CB(12, "upcat_3.convs.conv_0", 2, e->x2, 8, e->up3, e->c3a, nullptr)
     CB(13, "upcat_3.convs.conv_1", 2, e->c3a, 8, nullptr, e->u3, nullptr)
     if ((rc = deconv_block(ctx, e, "upcat_2", 2, nwin, e->u3, e->up2))) return rc;
+    if (fused) {
+        FB(14, "upcat_2.convs.conv_0", 1, e->x1, 4, e->up2, "down_1.convs.conv_1", 3, e->c2a)
+        FB(15, "upcat_2.convs.conv_1", 1, e->c2a, 4, nullptr, "upcat_2.convs.conv_0", 14, e->raw[1])
+        if ((rc = norm_block(ctx, e, 15, "upcat_2.convs.conv_1", 1, nwin, e->raw[1], e->u2, nullptr))) return rc;
+        if ((rc = deconv_block(ctx, e, "upcat_1", 1, nwin, e->u2, e->up1))) return rc;
+        FB(16, "upcat_1.convs.conv_0", 0, e->x0, 4, e->up1, "conv_0.conv_1", 1, e->c1a)
+        FB(17, "upcat_1.convs.conv_1", 0, e->c1a, 4, nullptr, "upcat_1.convs.conv_0", 16, e->raw[0])
+#undef FB
+    } else {
     CB(14, "upcat_2.convs.conv_0", 1, e->x1, 4, e->up2, e->c2a, nullptr)
     CB(15, "upcat_2.convs.conv_1", 1, e->c2a, 4, nullptr, e->u2, nullptr)
     if ((rc = deconv_block(ctx, e, "upcat_1", 1, nwin, e->u2, e->up1))) return rc;
     CB(16, "upcat_1.convs.conv_0", 0, e->x0, 4, e->up1, e->c1a, nullptr)
     CB(17, "upcat_1.convs.conv_1", 0, e->c1a, 4, nullptr, nullptr, nullptr)
+    }
 #undef CB
     const ConvLayer& last = ctx->net.conv.at("upcat_1.convs.conv_1");
     const Level& L0 = e->L[0];
     const int n = L0.Z * L0.Y * L0.X;
     dim3 grid((n + 255) / 256, nwin);
-    final_blend_kernel<<<grid, 256, 0, ctx->stream>>>(e->raw[0], to_dev(L0), e->stats + static_cast<size_t>(17) * e->batch * kStatsPerLayer,
+    final_blend_kernel<<<grid, 256, 0, ctx->stream>>>(last_raw, to_dev(L0), e->stats + static_cast<size_t>(17) * e->batch * kStatsPerLayer,
                                                       last.gamma, last.beta, ctx->net.final_w, ctx->net.final_b, wd_dev, acc,
                                                       slabY, slabX, wz, wy, wx, logits_out);
     ctx->launches++;
@@ -620,14 +808,23 @@ int op_conv3d(Ctx* ctx, const char* name, const float* x, int n, int D, int H, i
     pack_act_kernel<<<dim3((nv + 255) / 256, n * (Ly.cin_pad / 8)), 256, 0, ctx->stream>>>(x, Ly.cin, to_dev(L), in, Ly.cin_pad / 8);
     ctx->launches++;
     cudaMemsetAsync(stats, 0, sizeof(double) * n * Ly.cout * 2, ctx->stream);
-    rc = run_conv(ctx, Ly, L, n, in, Ly.cin_pad / 8, nullptr, raw, L, stats);
+    IsPlan probe;
+    double* part = nullptr;
+    if (ctx->use_fused && plan_conv_is(ctx, Ly, L, n, probe)) {
+        // Cout = 32 layers: the input-stationary kernel (plain, already-normalised input)
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&part), sizeof(double) * n * kIsMaxParts * 64);
+        if (e != cudaSuccess) { set_error(ctx, "dlv_op_conv3d: %s", cudaGetErrorString(e)); cudaFree(in); cudaFree(raw); return DLV_ERR_CUDA; }
+        rc = run_conv_is(ctx, Ly, L, n, in, Ly.cin_pad / 8, nullptr, nullptr, nullptr, raw, part, stats);
+    } else {
+        rc = run_conv(ctx, Ly, L, n, in, Ly.cin_pad / 8, nullptr, raw, L, stats);
+    }
     if (rc == 0) {
         unpack_act_kernel<<<dim3((nv + 255) / 256, n * (Ly.cout / 8)), 256, 0, ctx->stream>>>(raw, Ly.cout, to_dev(L), y, Ly.cout / 8);
         ctx->launches++;
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { set_error(ctx, "dlv_op_conv3d: %s", cudaGetErrorString(e)); rc = DLV_ERR_CUDA; }
     }
-    cudaFree(in); cudaFree(raw);
+    cudaFree(in); cudaFree(raw); cudaFree(part);
     return rc;
 }
 
