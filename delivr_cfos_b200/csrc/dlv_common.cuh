@@ -50,6 +50,16 @@ __device__ __forceinline__ float mish_f(float x) {
     return x * __fdividef(t, t + 2.f);
 }
 
+// Same function in 8 issue slots and without a branch:  mish(x) = x - 2x / (w(w+2) + 2),  w = e^x.
+// w = inf (x > 88) gives 1/inf = 0 -> x; w -> 0 gives x - 2x/2 = 0.
+__device__ __forceinline__ float mish_fast(float x) {
+    float w, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(x * 1.4426950408889634f));
+    const float d = fmaf(w, w + 2.f, 2.f);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    return fmaf(-2.f * x, r, x);
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
@@ -68,6 +78,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile("{\n\t.reg .pred p;\n\t"
                  "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Non-blocking probe (no hardware suspend): used to look at the NEXT step's barriers from inside an MMA burst.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
                  "selp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
@@ -108,6 +127,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Same with the descriptors passed as 32-bit halves: the upper half of a K-major no-swizzle descriptor (SBO, version)
+// is a constant, so all per-instruction descriptor arithmetic is 32-bit (no carry chains on the uniform datapath).
+__device__ __forceinline__ void umma_bf16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+                 "setp.ne.b32 p, %5, 0;\n\t"
+                 "mov.b64 da, {%1, %3};\n\t"
+                 "mov.b64 db, {%2, %3};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate) : "memory");
+}
 // Arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
@@ -143,20 +172,30 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Zero 32 lanes x 32 consecutive fp32 columns of TMEM (the warp's own lane quadrant).
+__device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
+    const uint32_t z = 0u;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                 "{%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
+                 :: "r"(taddr), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // Sum v[c] over the 32 lanes of a warp; on return lane c holds the total of column c.
-// 31 shuffles instead of 160 (butterfly that halves the live columns each round).
-__device__ __forceinline__ float warp_transpose_sum32(const float (&v)[32]) {
-    const int lane = lane_id();
-    float a16[16], a8[8], a4[4], a2[2];
-    {
-        const bool up = lane & 16;
+// 31 shuffles instead of 160 (butterfly that halves the live columns each round).  Split in two so that partial
+// results of several tiles can be accumulated after the first round (16 live values instead of 32).
+__device__ __forceinline__ void warp_transpose_round1(const float (&v)[32], float (&a16)[16]) {
+    const bool up = lane_id() & 16;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            float send = up ? v[i] : v[i + 16];
-            float keep = up ? v[i + 16] : v[i];
-            a16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-        }
+    for (int i = 0; i < 16; ++i) {
+        float send = up ? v[i] : v[i + 16];
+        float keep = up ? v[i + 16] : v[i];
+        a16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
     }
+}
+__device__ __forceinline__ float warp_transpose_finish(const float (&a16)[16]) {
+    const int lane = lane_id();
+    float a8[8], a4[4], a2[2];
     {
         const bool up = lane & 8;
 #pragma unroll
@@ -188,6 +227,11 @@ __device__ __forceinline__ float warp_transpose_sum32(const float (&v)[32]) {
     float send = up ? a2[0] : a2[1];
     float keep = up ? a2[1] : a2[0];
     return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+__device__ __forceinline__ float warp_transpose_sum32(const float (&v)[32]) {
+    float a16[16];
+    warp_transpose_round1(v, a16);
+    return warp_transpose_finish(a16);
 }
 
 }  // namespace dlv

@@ -24,7 +24,8 @@
 
 namespace dlv {
 
-constexpr int kIsThreads = 320;          // warp 0 producer, 1 MMA, 2-5 epilogue, 6-9 transform
+constexpr int kIsXformWarps = 8;         // two warps per 8-channel input chunk
+constexpr int kIsThreads = (6 + kIsXformWarps) * 32;   // warp 0 producer, 1 MMA, 2-5 epilogue, 6.. transform
 constexpr int kIsMaxStages = 4;
 
 struct IsArgs {
@@ -48,6 +49,10 @@ struct IsArgs {
     int KB, NC, NZS, Zs, nitems, RL, H, nstages;
     uint32_t stage_bytes, w_bytes;
     double inv_count;           // 1 / (Z*Y*X)
+    long long* dbg;             // optional [grid][8] cycle counters (DLV_IS_DEBUG)
+    int dbg_mode;               // experiments: 1 = transform copies without math, 2 = math without smem stores
+    uint32_t tap_a[36];         // per (kb, ky, kx): A descriptor offset (16 B units) = kb*2*RL + H + (ky-1)*Xp + (kx-1)
+    uint32_t tap_b[36];         // per (kb, ky, kx): B descriptor offset (16 B units) = (kb*9 + ky*3 + kx) * 192
 };
 
 // deterministic reduction of the per-item partial sums: stats[win][c][0..1] = sum over parts (fixed order)
@@ -71,8 +76,8 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* wsm = smem;
     uint8_t* stages = smem + p.w_bytes;
-    uint32_t* masks = reinterpret_cast<uint32_t*>(stages + static_cast<size_t>(p.nstages) * p.stage_bytes);   // [4][32]
-    double* comb = reinterpret_cast<double*>(masks + 128);                                                   // [4][64]
+    uint32_t* masks = reinterpret_cast<uint32_t*>(stages + static_cast<size_t>(p.nstages) * p.stage_bytes);   // [kIsXformWarps][32]
+    double* comb = reinterpret_cast<double*>(masks + kIsXformWarps * 32);                                                   // [4][64]
     uint64_t* bars = reinterpret_cast<uint64_t*>(comb + 256);
     uint64_t* full = bars;                          // [stages]
     uint64_t* empty = bars + kIsMaxStages;          // [stages]
@@ -86,7 +91,7 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
     const int nplain = p.nchunks - p.xform_chunks;
 
     if (threadIdx.x == 0) {
-        const uint32_t full_count = (nplain > 0 ? 1u : 0u) + (p.xform_chunks > 0 ? 4u : 0u);
+        const uint32_t full_count = (nplain > 0 ? 1u : 0u) + (p.xform_chunks > 0 ? static_cast<uint32_t>(kIsXformWarps) : 0u);
         for (int s = 0; s < p.nstages; ++s) { mbar_init(&full[s], full_count); mbar_init(&empty[s], 1); }
         for (int s = 0; s < S; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
         mbar_init(wfull, 1);
@@ -139,97 +144,129 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer
-        int stage = 0; uint32_t phase = 0;
-        uint32_t slot_par = 0;       // per-slot use parity (bit s)
-        mbar_wait(wfull, 0);
-        const uint32_t w_addr = smem_u32(wsm);
-        for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
-            int win, c, za, zb;
-            item_geom(item, win, c, za, zb);
-            const int zi0 = max(za - 1, 1), zi1 = min(zb + 1, p.Z);
-            for (int zi = zi0; zi <= zi1; ++zi) {
-                const int lo = max(zi - 1, za), hi = min(zi + 1, zb);              // output planes fed by this input plane
-                const int new_lo = (zi == zi0) ? lo : ((zi + 1 <= zb) ? zi + 1 : hi + 1);   // planes >= new_lo start here
-                // the epilogue must have drained the slots that start a new plane
-                for (int zo = new_lo; zo <= hi; ++zo) {
-                    const int s = zo % S;
-                    mbar_wait(&tempty[s], ((slot_par >> s) & 1u) ^ 1u);
-                    slot_par ^= 1u << s;
+        // ------------------------------------------------------------ MMA issuer: ONE thread for the whole kernel.
+        // The tensor pipe runs only ~4 instructions behind the issuing thread (measured), so every cycle this
+        // thread spends outside the MMA stream is a bubble.  The loop is therefore software-pipelined: the next
+        // step's parameters are computed and its barriers probed (non-blocking) in the middle of the current burst.
+        if (elect_one_sync()) {
+            long long c_wait = 0, c_steps = 0;
+            const long long c_begin = clock64();
+            mbar_wait(wfull, 0);
+            const uint32_t dhi = (128u >> 4) | (1u << 14);      // constant upper descriptor word (SBO 128 B, version 1)
+            const uint32_t b_base = ((smem_u32(wsm) >> 4) & 0x3FFFu) | (96u << 16);
+            const uint32_t a_stage0 = ((smem_u32(stages) >> 4) & 0x3FFFu) | (static_cast<uint32_t>(p.RL) << 16);
+            const uint32_t a_stage_step = p.stage_bytes >> 4;
+            struct Step {
+                uint32_t a_lo0, b_lo0, b_lo1, c0, i0, i1;
+                int n1, stage, done0, done1;       // done*: slots whose plane completes with this step (-1: none)
+                int acq0, acq1;                    // slots that start a new plane (-1: none)
+                uint32_t par0, par1, full_par;
+            };
+            // iterator over (item, input plane)
+            int item = blockIdx.x, win = 0, c = 0, za = 0, zb = 0, zi0 = 0, zi1 = 0, zi = 0;
+            int stage = 0; uint32_t phase = 0, slot_par = 0;
+            bool have = item < p.nitems;
+            if (have) { item_geom(item, win, c, za, zb); zi0 = max(za - 1, 1); zi1 = min(zb + 1, p.Z); zi = zi0; }
+            auto make_step = [&](Step& st) {
+                const int lo = max(zi - 1, za), hi = min(zi + 1, zb);
+                const int new_lo = (zi == zi0) ? lo : ((zi + 1 <= zb) ? zi + 1 : hi + 1);
+                const int cnt = hi - lo + 1;
+                const int n0 = min(cnt, S - (lo & (S - 1)));
+                st.n1 = cnt - n0;
+                st.a_lo0 = a_stage0 + static_cast<uint32_t>(stage) * a_stage_step;
+                st.b_lo0 = b_base + static_cast<uint32_t>((lo - (zi - 1)) * 32);
+                st.b_lo1 = st.b_lo0 + static_cast<uint32_t>(n0 * 32);
+                st.c0 = tmem_base + (lo & (S - 1)) * 32;
+                st.i0 = umma_idesc_bf16_m128(32) + (static_cast<uint32_t>((n0 - 1) * 4) << 17);
+                st.i1 = umma_idesc_bf16_m128(32) + (static_cast<uint32_t>((st.n1 > 0 ? st.n1 - 1 : 0) * 4) << 17);
+                st.stage = stage;
+                st.full_par = phase;
+                st.acq0 = st.acq1 = -1; st.par0 = st.par1 = 0;
+                if (new_lo <= hi) { st.acq0 = new_lo & (S - 1); st.par0 = (slot_par >> st.acq0) & 1u; slot_par ^= 1u << st.acq0; }
+                if (new_lo + 1 <= hi) { st.acq1 = (new_lo + 1) & (S - 1); st.par1 = (slot_par >> st.acq1) & 1u; slot_par ^= 1u << st.acq1; }
+                // output planes whose last contributing input plane is this one
+                st.done0 = (zi - 1 >= lo) ? ((zi - 1) & (S - 1)) : -1;
+                st.done1 = (zi == zi1 && zi <= zb) ? (zi & (S - 1)) : -1;
+                // advance the iterator
+                if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+                if (zi < zi1) {
+                    ++zi;
+                } else {
+                    item += gridDim.x;
+                    have = item < p.nitems;
+                    if (have) { item_geom(item, win, c, za, zb); zi0 = max(za - 1, 1); zi1 = min(zb + 1, p.Z); zi = zi0; }
                 }
-                mbar_wait(&full[stage], phase);
+            };
+            auto wait_step = [&](const Step& st, bool ok_full, bool ok0, bool ok1) {
+                const long long w0 = p.dbg ? clock64() : 0;
+                if (!ok0 && st.acq0 >= 0) mbar_wait(&tempty[st.acq0], st.par0);
+                if (!ok1 && st.acq1 >= 0) mbar_wait(&tempty[st.acq1], st.par1);
+                if (!ok_full) mbar_wait(&full[st.stage], st.full_par);
                 tc_fence_after();
-                if (elect_one_sync()) {
-                    // pieces: contiguous runs of output planes in slot order, at most two per range (ring wrap)
-                    // {tmem column, B row offset (16 B units), instruction descriptor}; n == 0 -> absent
-                    auto piece = [&](int a, int n, uint32_t& col, uint64_t& boff, uint32_t& idesc) {
-                        col = tmem_base + (a % S) * 32;
-                        boff = static_cast<uint64_t>((a - (zi - 1)) * 32);
-                        idesc = umma_idesc_bf16_m128(32 * (n > 0 ? n : 1));
-                    };
-                    auto split = [&](int a, int b, int& n0, int& n1) {      // planes a..b -> n0 before the wrap, n1 after
-                        const int cnt = b - a + 1;
-                        n0 = cnt > 0 ? min(cnt, S - a % S) : 0;
-                        n1 = cnt > 0 ? cnt - n0 : 0;
-                    };
-                    // every MMA but the first of the step accumulates into all planes lo..hi
-                    int n0, n1;
-                    split(lo, hi, n0, n1);
-                    uint32_t c0, c1, i0, i1; uint64_t b0, b1;
-                    piece(lo, n0, c0, b0, i0);
-                    piece(lo + n0, n1, c1, b1, i1);
-                    // the first MMA overwrites the planes that start at this step (>= new_lo) and accumulates into the others
-                    int on0, on1, nn0, nn1;
-                    split(lo, new_lo - 1, on0, on1);
-                    split(new_lo, hi, nn0, nn1);
-                    uint32_t oc0, oc1, oi0, oi1, nc0, nc1, ni0, ni1; uint64_t ob0, ob1, nb0, nb1;
-                    piece(lo, on0, oc0, ob0, oi0);
-                    piece(lo + on0, on1, oc1, ob1, oi1);
-                    piece(new_lo, nn0, nc0, nb0, ni0);
-                    piece(new_lo + nn0, nn1, nc1, nb1, ni1);
-                    const uint32_t a_base = smem_u32(stages + static_cast<size_t>(stage) * p.stage_bytes);
-                    const uint64_t adesc0 = umma_desc_kmajor_noswz(a_base, p.RL * 16, 128);
-                    const uint64_t bdesc0 = umma_desc_kmajor_noswz(w_addr, 96 * 16, 128);
-                    {
-                        const uint64_t atap = adesc0 + static_cast<uint64_t>(p.H - p.Xp - 1);
-#pragma unroll
-                        for (int t = 0; t < T; ++t) {
-                            if (on0) umma_bf16(oc0 + t * (S * 32), atap + t * 128, bdesc0 + ob0, oi0, 1u);
-                            if (on1) umma_bf16(oc1 + t * (S * 32), atap + t * 128, bdesc0 + ob1, oi1, 1u);
-                            if (nn0) umma_bf16(nc0 + t * (S * 32), atap + t * 128, bdesc0 + nb0, ni0, 0u);
-                            if (nn1) umma_bf16(nc1 + t * (S * 32), atap + t * 128, bdesc0 + nb1, ni1, 0u);
-                        }
+                if (p.dbg) c_wait += clock64() - w0;
+            };
+            const int nrows = 3 * p.KB;                                  // (kb, ky) rows of 3 taps
+            const uint32_t xp = static_cast<uint32_t>(p.Xp);
+            const uint32_t a_kb_adj = static_cast<uint32_t>(2 * p.RL) - 3u * xp;   // row 2 of kb -> row 0 of kb + 1
+            const uint32_t a_tap0 = static_cast<uint32_t>(p.H - p.Xp - 1);
+            Step cur, nxt;
+            bool more = have;
+            if (more) { make_step(cur); wait_step(cur, false, false, false); }
+            while (more) {
+                bool more_next = false, ok_full = false, ok0 = true, ok1 = true;
+                auto lookahead = [&]() {
+                    more_next = have;
+                    if (more_next) {
+                        make_step(nxt);
+                        ok_full = mbar_test_wait(&full[nxt.stage], nxt.full_par);
+                        if (nxt.acq0 >= 0) ok0 = mbar_test_wait(&tempty[nxt.acq0], nxt.par0);
+                        if (nxt.acq1 >= 0) ok1 = mbar_test_wait(&tempty[nxt.acq1], nxt.par1);
                     }
+                };
+                // rows of 3 taps; the look-ahead sits before the last row (>= 6 MMAs still to issue hide it)
+                auto issue_rows = [&](const bool two) {
+                    uint32_t arow = cur.a_lo0 + a_tap0, brow = cur.b_lo0, brow1 = cur.b_lo1;
+                    int ky = 0;
 #pragma unroll 1
-                    for (int kb = 0; kb < p.KB; ++kb) {
-#pragma unroll 1
-                        for (int ky = 0; ky < 3; ++ky) {
+                    for (int r = 0; r < nrows; ++r) {
+                        if (r == nrows - 1) lookahead();
 #pragma unroll
-                            for (int kx = 0; kx < 3; ++kx) {
-                                if (kb == 0 && ky == 0 && kx == 0) continue;
-                                const uint64_t atap = adesc0 + static_cast<uint64_t>(kb * 2 * p.RL + p.H + (ky - 1) * p.Xp + (kx - 1));
-                                const uint64_t btap = bdesc0 + static_cast<uint64_t>(((kb * 9 + ky * 3 + kx) * 3072) >> 4);
+                        for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
-                                for (int t = 0; t < T; ++t) {
-                                    umma_bf16(c0 + t * (S * 32), atap + t * 128, btap + b0, i0, 1u);
-                                    if (n1) umma_bf16(c1 + t * (S * 32), atap + t * 128, btap + b1, i1, 1u);
-                                }
+                            for (int t = 0; t < T; ++t) {
+                                umma_bf16_lh(cur.c0 + t * (S * 32), arow + kx + t * 128, brow + kx * 192, dhi, cur.i0, 1u);
+                                if (two) umma_bf16_lh(tmem_base + t * (S * 32), arow + kx + t * 128, brow1 + kx * 192, dhi, cur.i1, 1u);
                             }
                         }
+                        brow += 576; brow1 += 576;
+                        if (++ky == 3) { ky = 0; arow += a_kb_adj + xp; } else { arow += xp; }
                     }
-                    umma_commit(&empty[stage]);
-                    // output planes whose last contributing input plane was this one are complete
-                    for (int zo = lo; zo <= hi; ++zo)
-                        if (min(zo + 1, zi1) == zi) umma_commit(&tfull[zo % S]);
-                }
-                __syncwarp();
-                if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+                };
+                if (cur.n1 == 0) issue_rows(false); else issue_rows(true);
+                umma_commit(&empty[cur.stage]);
+                if (cur.done0 >= 0) umma_commit(&tfull[cur.done0]);
+                if (cur.done1 >= 0) umma_commit(&tfull[cur.done1]);
+                ++c_steps;
+                if (more_next) { wait_step(nxt, ok_full, ok0, ok1); cur = nxt; }
+                more = more_next;
+            }
+            if (p.dbg) {
+                long long* d = p.dbg + blockIdx.x * 8;
+                d[0] = clock64() - c_begin; d[1] = c_wait; d[2] = 0; d[3] = 0; d[4] = c_steps;
             }
         }
+        __syncwarp();
     } else if (warp < 6) {
         // ------------------------------------------------------------ epilogue (4 warps = 4 TMEM lane quadrants)
         const int q = warp & 3;
         uint32_t slot_par = 0;
+        // all accumulators start at zero (every MMA accumulates); then hand every slot to the MMA warp
+        for (int col = 0; col < 512; col += 32) tmem_zero32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + col);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0)
+            for (int s = 0; s < S; ++s) mbar_arrive(&tempty[s]);
         for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
             int win, c, za, zb;
             item_geom(item, win, c, za, zb);
@@ -252,33 +289,51 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
                 mbar_wait(&tfull[s], (slot_par >> s) & 1u);
                 slot_par ^= 1u << s;
                 tc_fence_after();
-                if (anyw) {
-                    float acc_s[32], acc_q[32];
+                {
+                    float part_s[16], part_q[16];          // column sums after the first butterfly round, over the T tiles
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) { acc_s[i] = 0.f; acc_q[i] = 0.f; }
+                    for (int i = 0; i < 16; ++i) { part_s[i] = 0.f; part_q[i] = 0.f; }
 #pragma unroll
                     for (int t = 0; t < T; ++t) {
-                        if (__ballot_sync(0xffffffffu, valid[t]) == 0) continue;
-                        float v[32];
-                        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * (S * 32) + s * 32, v);
-                        if (valid[t]) {
-                            __nv_bfloat16* o = p.out + (poff[t] + static_cast<int64_t>(zo) * p.PL) * 8;
+                        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * (S * 32) + s * 32;
+                        if (anyw && __ballot_sync(0xffffffffu, valid[t]) != 0) {      // warp-uniform
+                            float v[32];
+                            tmem_ld32(taddr, v);
+                            tmem_zero32(taddr);          // the slot's next plane accumulates from zero
+                            if (valid[t]) {
+                                __nv_bfloat16* o = p.out + (poff[t] + static_cast<int64_t>(zo) * p.PL) * 8;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                uint4 u;
-                                u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-                                u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                                u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-                                u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-                                *reinterpret_cast<uint4*>(o + static_cast<int64_t>(j) * p.outS * 8) = u;
+                                for (int j = 0; j < 4; ++j) {
+                                    uint4 u;
+                                    u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                                    u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                                    u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                                    u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                                    *reinterpret_cast<uint4*>(o + static_cast<int64_t>(j) * p.outS * 8) = u;
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) v[i] = 0.f;
                             }
+                            float r16[16];
+                            warp_transpose_round1(v, r16);
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) { acc_s[i] += v[i]; acc_q[i] = fmaf(v[i], v[i], acc_q[i]); }
+                            for (int i = 0; i < 16; ++i) part_s[i] += r16[i];
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] *= v[i];
+                            warp_transpose_round1(v, r16);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) part_q[i] += r16[i];
+                        } else {
+                            tmem_zero32(taddr);          // rows outside the window: discard what the MMAs summed there
                         }
                     }
-                    run_s += static_cast<double>(warp_transpose_sum32(acc_s));
-                    run_q += static_cast<double>(warp_transpose_sum32(acc_q));
+                    if (anyw) {
+                        run_s += static_cast<double>(warp_transpose_finish(part_s));
+                        run_q += static_cast<double>(warp_transpose_finish(part_q));
+                    }
                 }
+                tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[s]);
@@ -298,17 +353,24 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
             asm volatile("bar.sync 1, 128;" ::: "memory");
         }
     } else if (p.xform_chunks > 0) {
-        // ------------------------------------------------------------ transform warps: warp w stages chunk w
-        const int chunk = warp - 6;
-        uint32_t* mymask = masks + chunk * 32;
+        // ------------------------------------------------------------ transform warps: NW warps per 8-channel chunk
+        // (the 32-position groups of the run are dealt round-robin to them).  The math is branch-free so that the
+        // compiler can interleave the MUFU -> FMA -> MUFU chains of all elements of a batch; the floor of this role
+        // is the MUFU pipe (ex2 + rcp per element, 16 lanes per SM and clock).
+        constexpr int NW = kIsXformWarps / 4;
+        const int tw = warp - 6;
+        const int chunk = tw & 3, sub = tw >> 2;
+        uint32_t* mymask = masks + tw * 32;
         const __nv_bfloat16* base = p.in0 + static_cast<int64_t>(chunk) * p.inS * 8;
         const int nit = (p.RL + 31) / 32;
+        constexpr int U = 8;                       // 32-position groups per register batch: covers RL <= 512 with NW = 2
         int stage = 0; uint32_t phase = 0;
+        long long x_empty = 0, x_work = 0;
         for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
             int win, c, za, zb;
             item_geom(item, win, c, za, zb);
             const int zi0 = max(za - 1, 1), zi1 = min(zb + 1, p.Z);
-            // halo mask of the column's run (same for every plane)
+            // halo mask of the column's run (same for every plane of the item)
             for (int it = 0; it < nit; ++it) {
                 const int i = it * 32 + lane;
                 const int qq = c * R - p.H + i;
@@ -335,41 +397,59 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
                 for (int i = 0; i < 8; ++i) { a[i] = __shfl_sync(0xffffffffu, ma, i); b[i] = __shfl_sync(0xffffffffu, mb, i); }
             }
             __syncwarp();
-            for (int zi = zi0; zi <= zi1; ++zi) {
-                mbar_wait(&empty[stage], phase ^ 1);
+            auto run_src = [&](int zz) {
                 const int64_t pos = static_cast<int64_t>(p.in_guard) + static_cast<int64_t>(win) * p.Vp +
-                                    static_cast<int64_t>(zi) * p.PL + c * R - p.H;
-                const uint4* src = reinterpret_cast<const uint4*>(base + pos * 8);
+                                    static_cast<int64_t>(zz) * p.PL + c * R - p.H;
+                return reinterpret_cast<const uint4*>(base + pos * 8);
+            };
+            auto load_batch = [&](const uint4* src, int k0, uint4 (&u)[U]) {
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                    const int i = (NW * (k0 + k) + sub) * 32 + lane;
+                    u[k] = (i < p.RL) ? ld_nc_u4(src + i) : make_uint4(0u, 0u, 0u, 0u);
+                }
+            };
+            auto xform_batch = [&](uint32_t dst, int k0, const uint4 (&u)[U]) {
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                    const int it = NW * (k0 + k) + sub;
+                    const int i = it * 32 + lane;
+                    uint4 o;
+                    o.x = pack_bf16x2(mish_fast(fmaf(bf16_lo(u[k].x), a[0], b[0])), mish_fast(fmaf(bf16_hi(u[k].x), a[1], b[1])));
+                    o.y = pack_bf16x2(mish_fast(fmaf(bf16_lo(u[k].y), a[2], b[2])), mish_fast(fmaf(bf16_hi(u[k].y), a[3], b[3])));
+                    o.z = pack_bf16x2(mish_fast(fmaf(bf16_lo(u[k].z), a[4], b[4])), mish_fast(fmaf(bf16_hi(u[k].z), a[5], b[5])));
+                    o.w = pack_bf16x2(mish_fast(fmaf(bf16_lo(u[k].w), a[6], b[6])), mish_fast(fmaf(bf16_hi(u[k].w), a[7], b[7])));
+                    if (p.dbg_mode == 1) o = u[k];
+                    const bool in = (it < 32) && ((mymask[it & 31] >> lane) & 1u);     // halo positions stay exactly zero
+                    o.x = in ? o.x : 0u; o.y = in ? o.y : 0u; o.z = in ? o.z : 0u; o.w = in ? o.w : 0u;
+                    if (i < p.RL) st_shared_u4(dst + static_cast<uint32_t>(i) * 16u, o);
+                }
+            };
+            // the loads of the NEXT input plane are issued before the current plane is transformed (register double buffer)
+            uint4 ucur[U], unext[U];
+            load_batch(run_src(zi0), 0, ucur);
+            for (int zi = zi0; zi <= zi1; ++zi) {
+                const uint4* src = run_src(zi);
+                if (zi < zi1) load_batch(run_src(zi + 1), 0, unext);
+                const long long x0 = p.dbg ? clock64() : 0;
+                mbar_wait(&empty[stage], phase ^ 1);
+                const long long x1 = p.dbg ? clock64() : 0;
                 const uint32_t dst = smem_u32(stages + static_cast<size_t>(stage) * p.stage_bytes + static_cast<size_t>(chunk) * p.RL * 16);
-                constexpr int U = 7;
-                for (int it0 = 0; it0 < nit; it0 += U) {
-                    uint4 u[U];
-#pragma unroll
-                    for (int k = 0; k < U; ++k) {
-                        const int i = (it0 + k) * 32 + lane;
-                        u[k] = (it0 + k < nit && i < p.RL) ? ld_nc_u4(src + i) : make_uint4(0u, 0u, 0u, 0u);
-                    }
-#pragma unroll
-                    for (int k = 0; k < U; ++k) {
-                        const int i = (it0 + k) * 32 + lane;
-                        if (it0 + k < nit && i < p.RL) {
-                            uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                            if ((mymask[it0 + k] >> lane) & 1u) {
-                                o.x = pack_bf16x2(mish_f(fmaf(bf16_lo(u[k].x), a[0], b[0])), mish_f(fmaf(bf16_hi(u[k].x), a[1], b[1])));
-                                o.y = pack_bf16x2(mish_f(fmaf(bf16_lo(u[k].y), a[2], b[2])), mish_f(fmaf(bf16_hi(u[k].y), a[3], b[3])));
-                                o.z = pack_bf16x2(mish_f(fmaf(bf16_lo(u[k].z), a[4], b[4])), mish_f(fmaf(bf16_hi(u[k].z), a[5], b[5])));
-                                o.w = pack_bf16x2(mish_f(fmaf(bf16_lo(u[k].w), a[6], b[6])), mish_f(fmaf(bf16_hi(u[k].w), a[7], b[7])));
-                            }
-                            st_shared_u4(dst + static_cast<uint32_t>(i) * 16u, o);
-                        }
-                    }
+                xform_batch(dst, 0, ucur);
+                for (int k0 = U; (NW * k0 + sub) * 32 < p.RL; k0 += U) {      // runs longer than one batch (large windows)
+                    load_batch(src, k0, ucur);
+                    xform_batch(dst, k0, ucur);
                 }
                 fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core's async proxy
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full[stage]);
+                if (p.dbg) { x_empty += x1 - x0; x_work += clock64() - x1; }
                 if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+#pragma unroll
+                for (int k = 0; k < U; ++k) ucur[k] = unext[k];
             }
         }
+        if (p.dbg && tw == 0 && lane == 0) { p.dbg[blockIdx.x * 8 + 5] = x_empty; p.dbg[blockIdx.x * 8 + 6] = x_work; }
     }
 
     tc_fence_before();

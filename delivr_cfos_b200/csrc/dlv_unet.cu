@@ -90,7 +90,7 @@ __global__ void norm_mish_kernel(const __nv_bfloat16* __restrict__ raw, LevelDev
         const uint4 u = *reinterpret_cast<const uint4*>(raw + cbase + P * 8);
         float f[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y), bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = mish_f(fmaf(f[i], a[i], b[i]));
+        for (int i = 0; i < 8; ++i) f[i] = mish_fast(fmaf(f[i], a[i], b[i]));
         uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
         if (out) *reinterpret_cast<uint4*>(out + cbase + P * 8) = o;
         // pooling compares the bf16-rounded activations (what the next layer would read)
@@ -154,7 +154,7 @@ __global__ void final_blend_kernel(const __nv_bfloat16* __restrict__ raw, LevelD
         const uint4 u = *reinterpret_cast<const uint4*>(raw + static_cast<int64_t>(ch) * L.S * 8 + P * 8);
         const float f[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y), bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) logit = fmaf(sw[ch * 8 + i], mish_f(fmaf(f[i], sa[ch * 8 + i], sb[ch * 8 + i])), logit);
+        for (int i = 0; i < 8; ++i) logit = fmaf(sw[ch * 8 + i], mish_fast(fmaf(f[i], sa[ch * 8 + i], sb[ch * 8 + i])), logit);
     }
     if (logits_out) {   // operator-level entry point: plain per-window logits, window order
         logits_out[static_cast<int64_t>(win) * L.Z * L.Y * L.X + idx] = logit;
@@ -480,11 +480,11 @@ static bool plan_conv_is(const Ctx* ctx, const ConvLayer& Ly, const Level& L, in
     auto fits = [&](int T, int& nst, int& RL, uint32_t& sb) {
         RL = ((128 * T + 2 * P.H + 7) / 8) * 8;
         sb = static_cast<uint32_t>(nchunks) * RL * 16;
-        const uint32_t fixed = P.w_bytes + 128 * 4 + 256 * 8 + 256;
+        const uint32_t fixed = P.w_bytes + kIsXformWarps * 32 * 4 + 256 * 8 + 256;
         nst = 0;
         for (int n = kIsMaxStages; n >= 2; --n)
             if (fixed + static_cast<uint64_t>(n) * sb <= kSmemLimit) { nst = n; break; }
-        return nst >= 2 && RL <= 16383;
+        return nst >= 2 && RL <= 1024;      // 32 mask words per transform warp
     };
     // cost model per tile and k-block: 9 taps x (56 clk for an N = 96 MMA, 88 where the slot ring wraps: 2 of S steps),
     // times the column quantisation of the plane
@@ -562,7 +562,17 @@ static int run_conv_is(Ctx* ctx, const ConvLayer& Ly, const Level& L, int nwin, 
     a.RL = P.RL; a.H = P.H; a.nstages = P.nstages;
     a.stage_bytes = P.stage_bytes; a.w_bytes = P.w_bytes;
     a.inv_count = 1.0 / (static_cast<double>(L.Z) * L.Y * L.X);
+    for (int kb = 0; kb < Ly.KB; ++kb)
+        for (int ky = 0; ky < 3; ++ky)
+            for (int kx = 0; kx < 3; ++kx) {
+                const int i = kb * 9 + ky * 3 + kx;
+                a.tap_a[i] = static_cast<uint32_t>(kb * 2 * P.RL + P.H + (ky - 1) * L.Xp + (kx - 1));
+                a.tap_b[i] = static_cast<uint32_t>(i * 192);
+            }
     const int grid = std::min(ctx->num_sms, a.nitems);
+    static const bool dbg = getenv("DLV_IS_DEBUG") != nullptr;
+    if (const char* e = getenv("DLV_IS_MODE")) a.dbg_mode = atoi(e);
+    if (dbg) { cudaMalloc(reinterpret_cast<void**>(&a.dbg), grid * 64); cudaMemset(a.dbg, 0, grid * 64); }
     if (ctx->time_convs) cudaEventRecord(ctx->ev0, ctx->stream);
     int rc = (P.T == 4) ? launch_conv_is_t<4, 4>(ctx, a, grid, P.smem) : launch_conv_is_t<2, 8>(ctx, a, grid, P.smem);
     if (ctx->time_convs && rc == 0) {
@@ -571,6 +581,17 @@ static int run_conv_is(Ctx* ctx, const ConvLayer& Ly, const Level& L, int nwin, 
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
         ctx->conv_ms += ms;
+    }
+    if (dbg && rc == 0) {
+        cudaStreamSynchronize(ctx->stream);
+        std::vector<long long> h(grid * 8);
+        cudaMemcpy(h.data(), a.dbg, grid * 64, cudaMemcpyDeviceToHost);
+        cudaFree(a.dbg);
+        double t[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (int b = 0; b < grid; ++b) for (int k = 0; k < 7; ++k) t[k] += h[b * 8 + k];
+        const double st = t[4] > 0 ? t[4] : 1;
+        fprintf(stderr, "[is] %-22s nwin %d T %d NZS %d nst %d KB %d xf %d: cycles/CTA %.0f | per step: total %.0f mma-thread waits %.0f (%.0f %.0f) | xform empty-wait %.0f work %.0f\n",
+                Ly.name.c_str(), nwin, P.T, P.NZS, P.nstages, Ly.KB, a.xform_chunks, t[0] / grid, t[0] / st, t[1] / st, t[2] / st, t[3] / st, t[5] / st, t[6] / st);
     }
     if (rc) return rc;
     is_reduce_stats_kernel<<<nwin, 64, 0, ctx->stream>>>(part, P.nparts, stats);

@@ -1,9 +1,8 @@
 #!/bin/bash
 # ncu evidence for the current build: launch list of our kernels + full captures of the dominant ones
+# usage: gpu_prof.sh [tag] [env assignments...]
 mkdir -p gpurun_out
-K='regex:conv_tc|norm_mish|final_blend|gather_windows|window_active|average_kernel|erode_|ccl_|scan_|bbox_init|relabel|boundary'
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c 400 --csv --log-file gpurun_out/launches_small.csv python bench.py --workload small --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_small.log 2>&1; echo "ncu list exit $?"
-# full capture: warm-up pass = 1 gather + 18 conv + 4 deconv ...; skip the first pass, take the L0 Cout=32 convs
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 22 -c 22 -o gpurun_out/prof_conv python bench.py --workload small --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_conv.log 2>&1; echo "ncu conv exit $?"
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'norm_mish|final_blend|gather_windows' -s 18 -c 19 -o gpurun_out/prof_elem python bench.py --workload small --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_elem.log 2>&1; echo "ncu elem exit $?"
-ls -la gpurun_out
+tag=${1:-cur}; shift
+K='regex:conv_tc|conv_is|is_reduce|norm_mish|final_blend|gather_windows|window_active|average_kernel|erode_|ccl_|scan_|bbox_init|relabel|boundary'
+env "$@" timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c 400 --csv --log-file gpurun_out/launches_${tag}.csv python bench.py --workload small --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_list_${tag}.log 2>&1; echo "ncu list exit $?"
+env "$@" timeout 1200 ncu --set full --clock-control none --import-source on -k regex:conv_is -c 8 -o gpurun_out/prof_is_${tag} python bench.py --workload small --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_is_${tag}.log 2>&1; echo "ncu is exit $?"
