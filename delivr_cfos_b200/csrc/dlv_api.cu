@@ -58,6 +58,12 @@ int dlv_init(int device, dlv_ctx** out) {
     if (const char* e = getenv("DLV_IS_T")) ctx->is_tiles = atoi(e);
     DLV_CUDA_OK(ctx, cudaSetDevice(device));
     DLV_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    {   // keep freed transient buffers in the pool (they are re-used by the next call instead of returned to the driver)
+        cudaMemPool_t pool;
+        DLV_CUDA_OK(ctx, cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = ~0ull;
+        DLV_CUDA_OK(ctx, cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     DLV_CUDA_OK(ctx, cudaEventCreate(&ctx->ev0));
     DLV_CUDA_OK(ctx, cudaEventCreate(&ctx->ev1));
     return DLV_OK;
@@ -120,24 +126,25 @@ int dlv_ccl(dlv_ctx* c, const void* mask_any, const int64_t shape[3], int connec
     const uint8_t* mask = static_cast<const uint8_t*>(mask_any);
     void *mask_own = nullptr, *lab_own = nullptr;
     if (!dlv::dev_ptr(mask_any)) {
-        DLV_CUDA_OK(ctx, cudaMalloc(&mask_own, n ? n : 1));
+        DLV_CUDA_OK(ctx, dlv::dmalloc(ctx, &mask_own, n));
         DLV_CUDA_OK(ctx, cudaMemcpyAsync(mask_own, mask_any, n, cudaMemcpyHostToDevice, ctx->stream));
         mask = static_cast<const uint8_t*>(mask_own);
     }
     uint32_t* labels = static_cast<uint32_t*>(labels_out_any);
     const bool lab_host = labels_out_any && !dlv::dev_ptr(labels_out_any);
     if (!labels_out_any || lab_host) {
-        cudaError_t e = cudaMalloc(&lab_own, (n ? n : 1) * 4);
-        if (e != cudaSuccess) { cudaFree(mask_own); dlv::set_error(ctx, "dlv_ccl: label buffer: %s", cudaGetErrorString(e)); return DLV_ERR_CUDA; }
+        cudaError_t e = dlv::dmalloc(ctx, &lab_own, n * 4);
+        if (e != cudaSuccess) { dlv::dfree(ctx, mask_own); dlv::set_error(ctx, "dlv_ccl: label buffer: %s", cudaGetErrorString(e)); return DLV_ERR_CUDA; }
         labels = static_cast<uint32_t*>(lab_own);
     }
     int rc = dlv::ccl_run(ctx, mask, shape, labels, table_out);
     if (rc == 0 && lab_host) {
-        cudaError_t e = cudaMemcpy(labels_out_any, labels, n * 4, cudaMemcpyDeviceToHost);
+        cudaError_t e = cudaMemcpyAsync(labels_out_any, labels, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { dlv::set_error(ctx, "dlv_ccl: label copy: %s", cudaGetErrorString(e)); rc = DLV_ERR_CUDA; }
     }
-    cudaFree(mask_own);
-    cudaFree(lab_own);
+    dlv::dfree(ctx, mask_own);
+    dlv::dfree(ctx, lab_own);
     return rc;
 }
 
@@ -169,7 +176,7 @@ int dlv_unet_forward(dlv_ctx* c, const uint16_t* windows_dev, int nwin, const in
     std::vector<dlv::WindowDesc> wd(nwin);
     for (int w = 0; w < nwin; ++w) wd[w] = dlv::WindowDesc{w * roi[0], 0, 0, 0};
     dlv::WindowDesc* wd_dev = nullptr;
-    DLV_CUDA_OK(ctx, cudaMalloc(reinterpret_cast<void**>(&wd_dev), sizeof(dlv::WindowDesc) * nwin));
+    DLV_CUDA_OK(ctx, dlv::dmalloc(ctx, &wd_dev, sizeof(dlv::WindowDesc) * nwin));
     cudaMemcpyAsync(wd_dev, wd.data(), sizeof(dlv::WindowDesc) * nwin, cudaMemcpyHostToDevice, ctx->stream);
     const int64_t wvox = static_cast<int64_t>(roi[0]) * roi[1] * roi[2];
     for (int off = 0; off < nwin && rc == 0; off += cap) {
@@ -178,7 +185,7 @@ int dlv_unet_forward(dlv_ctx* c, const uint16_t* windows_dev, int nwin, const in
                                    logits_dev + off * wvox);
     }
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(wd_dev);
+    dlv::dfree(ctx, wd_dev);
     if (rc == 0 && e != cudaSuccess) { dlv::set_error(ctx, "dlv_unet_forward: %s", cudaGetErrorString(e)); rc = DLV_ERR_CUDA; }
     return rc;
 }

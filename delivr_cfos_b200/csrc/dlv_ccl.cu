@@ -339,12 +339,12 @@ int ccl_run(Ctx* ctx, const uint8_t* mask, const int64_t shape[3], uint32_t* L, 
 #define CK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error(ctx, "dlv_ccl: %s: %s", #expr, cudaGetErrorString(_e)); rc = DLV_ERR_CUDA; goto done; } } while (0)
     if (n > 0) {
         const int64_t nb = (nwords + kScanBlock - 1) / kScanBlock;
-        CK(cudaMalloc(&bits, nwords * 4));
-        CK(cudaMalloc(&rootbits, nwords * 4));
-        CK(cudaMalloc(&wprefix, nwords * 4));
-        CK(cudaMalloc(&bsum, nb * 4));
-        CK(cudaMalloc(&n_dev, 4));
-        CK(cudaMalloc(&bg_dev, 6 * sizeof(int)));
+        CK(dmalloc(ctx, &bits, nwords * 4));
+        CK(dmalloc(ctx, &rootbits, nwords * 4));
+        CK(dmalloc(ctx, &wprefix, nwords * 4));
+        CK(dmalloc(ctx, &bsum, nb * 4));
+        CK(dmalloc(ctx, &n_dev, 4));
+        CK(dmalloc(ctx, &bg_dev, 6 * sizeof(int)));
         CK(cudaMemcpyAsync(bg_dev, bg, sizeof(bg), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2)); CK(cudaEventCreate(&e3));
         CK(cudaEventRecord(e0, ctx->stream));
@@ -374,9 +374,9 @@ int ccl_run(Ctx* ctx, const uint8_t* mask, const int64_t shape[3], uint32_t* L, 
         if (!T->voxel_counts || !T->sums || !T->bbox) { set_error(ctx, "dlv_ccl: host table allocation failed"); rc = DLV_ERR_ARG; goto done; }
         std::vector<int> hb(rows * 6);
         if (n > 0) {
-            CK(cudaMalloc(&cnt, rows * 8));
-            CK(cudaMalloc(&sums, rows * 24));
-            CK(cudaMalloc(&bbox, rows * 24));
+            CK(dmalloc(ctx, &cnt, rows * 8));
+            CK(dmalloc(ctx, &sums, rows * 24));
+            CK(dmalloc(ctx, &bbox, rows * 24));
             CK(cudaMemsetAsync(cnt, 0, rows * 8, ctx->stream));
             CK(cudaMemsetAsync(sums, 0, rows * 24, ctx->stream));
             CK(cudaEventRecord(e2, ctx->stream));
@@ -410,8 +410,8 @@ int ccl_run(Ctx* ctx, const uint8_t* mask, const int64_t shape[3], uint32_t* L, 
     ctx->launches += launches;
 done:
 #undef CK
-    cudaFree(bits); cudaFree(rootbits); cudaFree(wprefix); cudaFree(bsum); cudaFree(n_dev); cudaFree(bg_dev);
-    cudaFree(cnt); cudaFree(sums); cudaFree(bbox);
+    dfree(ctx, bits); dfree(ctx, rootbits); dfree(ctx, wprefix); dfree(ctx, bsum); dfree(ctx, n_dev); dfree(ctx, bg_dev);
+    dfree(ctx, cnt); dfree(ctx, sums); dfree(ctx, bbox);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     if (e2) cudaEventDestroy(e2);

@@ -60,6 +60,110 @@ __device__ __forceinline__ float mish_fast(float x) {
     return fmaf(-2.f * x, r, x);
 }
 
+// ---------------------------------------------------------------- packed fp32 pairs (FFMA2 / FADD2 / FMUL2, sm_100)
+// Two fp32 lanes in one 64-bit register: one issue slot does the work of two.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// InstanceNorm affine + Mish on 8 bf16 channels (one 16 B position-chunk), packed arithmetic:
+//   y = x*a + b;  w = e^y;  mish(y) = y - y / (0.5 w^2 + w + 1) = y + y * rneg,  rneg = -1 / (0.5 w^2 + w + 1).
+// Channel pairs i >= NRP take rneg from MUFU.RCP of the NEGATED denominator (w = +inf -> rcp(-inf) = -0 -> y;
+// w = 0 -> rcp(-1) = -1 -> 0): 5 packed FMA-pipe ops + 4 MUFU per pair.
+// Channel pairs i < NRP keep the MUFU pipe for ex2 only and take the reciprocal from two Newton steps on the FMA pipe
+// (seed = magic - bits(d), 5 % error -> 0.26 % -> 7e-6; the signs are arranged so that the second step lands on
+// -1/d): 9 packed ops + 4 ALU ops + 2 MUFU per pair.  The exponent is clamped to 2^63 so that d stays finite.
+// NRP trades MUFU cycles (16 lanes / clk / SM) against issue slots.
+template <int NRP>
+__device__ __forceinline__ void norm_mish8_f32(const uint4 u, const f32x2 (&a)[4], const f32x2 (&b)[4], f32x2 (&out)[4]) {
+    const f32x2 kLog2e = pk2(1.4426950408889634f, 1.4426950408889634f);
+    const f32x2 kNegHalf = pk2(-0.5f, -0.5f), kNegOne = pk2(-1.f, -1.f);
+    const f32x2 kHalf = pk2(0.5f, 0.5f), kOne = pk2(1.f, 1.f), kTwo = pk2(2.f, 2.f), kNegTwo = pk2(-2.f, -2.f);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    f32x2 y[4], t[4], d[4];
+    float e0[4], e1[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = fma2(pk2(bf16_lo(w[i]), bf16_hi(w[i])), a[i], b[i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t[i] = mul2(y[i], kLog2e);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        upk2(t[i], e0[i], e1[i]);
+        if (i < NRP) { e0[i] = fminf(e0[i], 63.f); e1[i] = fminf(e1[i], 63.f); }
+        e0[i] = ex2_approx(e0[i]); e1[i] = ex2_approx(e1[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const f32x2 e = pk2(e0[i], e1[i]);
+        d[i] = (i < NRP) ? fma2(e, fma2(e, kHalf, kOne), kOne)                // +(0.5 w^2 + w + 1)
+                         : fma2(e, fma2(e, kNegHalf, kNegOne), kNegOne);      // -(0.5 w^2 + w + 1)
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        upk2(d[i], e0[i], e1[i]);
+        if (i < NRP) {
+            const f32x2 r0 = pk2(__uint_as_float(0x7EF311C7u - __float_as_uint(e0[i])), __uint_as_float(0x7EF311C7u - __float_as_uint(e1[i])));
+            const f32x2 r1n = mul2(r0, fma2(d[i], r0, kNegTwo));              // -r1
+            const f32x2 r2n = mul2(r1n, fma2(d[i], r1n, kTwo));               // -r2
+            out[i] = fma2(y[i], r2n, y[i]);
+        } else {
+            out[i] = fma2(y[i], pk2(rcp_approx(e0[i]), rcp_approx(e1[i])), y[i]);
+        }
+    }
+}
+template <int NRP>
+__device__ __forceinline__ uint4 norm_mish8(const uint4 u, const f32x2 (&a)[4], const f32x2 (&b)[4]) {
+    f32x2 f[4];
+    norm_mish8_f32<NRP>(u, a, b, f);
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float lo, hi;
+        upk2(f[i], lo, hi);
+        o[i] = pack_bf16x2(lo, hi);
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t x, uint32_t y) {
+    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&x), *reinterpret_cast<__nv_bfloat162*>(&y));
+    return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t bf16x2_min(uint32_t x, uint32_t y) {
+    __nv_bfloat162 r = __hmin2(*reinterpret_cast<__nv_bfloat162*>(&x), *reinterpret_cast<__nv_bfloat162*>(&y));
+    return *reinterpret_cast<uint32_t*>(&r);
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");

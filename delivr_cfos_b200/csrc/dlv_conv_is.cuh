@@ -27,6 +27,10 @@ namespace dlv {
 constexpr int kIsXformWarps = 8;         // two warps per 8-channel input chunk
 constexpr int kIsThreads = (6 + kIsXformWarps) * 32;   // warp 0 producer, 1 MMA, 2-5 epilogue, 6.. transform
 constexpr int kIsMaxStages = 4;
+#ifndef DLV_IS_NEWTON_PAIRS
+#define DLV_IS_NEWTON_PAIRS 0
+#endif
+constexpr int kIsNewtonPairs = DLV_IS_NEWTON_PAIRS;   // channel pairs (of 4 per 16 B) whose reciprocal runs on the FMA pipe
 
 struct IsArgs {
     const __nv_bfloat16* in0;   // leading input chunks
@@ -50,7 +54,7 @@ struct IsArgs {
     uint32_t stage_bytes, w_bytes;
     double inv_count;           // 1 / (Z*Y*X)
     long long* dbg;             // optional [grid][8] cycle counters (DLV_IS_DEBUG)
-    int dbg_mode;               // experiments: 1 = transform copies without math, 2 = math without smem stores
+    int dbg_mode;               // timing experiments (results invalid): 1 skip TMEM loads, 2 skip TMEM zeroing, 4 skip the transform's smem traffic, 8 skip output stores
     uint32_t tap_a[36];         // per (kb, ky, kx): A descriptor offset (16 B units) = kb*2*RL + H + (ky-1)*Xp + (kx-1)
     uint32_t tap_b[36];         // per (kb, ky, kx): B descriptor offset (16 B units) = (kb*9 + ky*3 + kx) * 192
 };
@@ -65,6 +69,11 @@ __global__ void is_reduce_stats_kernel(const double* __restrict__ part, int npar
 }
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint4 ld_shared_u4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_shared_u4(uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -76,23 +85,23 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* wsm = smem;
     uint8_t* stages = smem + p.w_bytes;
-    uint32_t* masks = reinterpret_cast<uint32_t*>(stages + static_cast<size_t>(p.nstages) * p.stage_bytes);   // [kIsXformWarps][32]
-    double* comb = reinterpret_cast<double*>(masks + kIsXformWarps * 32);                                                   // [4][64]
+    double* comb = reinterpret_cast<double*>(stages + static_cast<size_t>(p.nstages) * p.stage_bytes);   // [4][64]
     uint64_t* bars = reinterpret_cast<uint64_t*>(comb + 256);
     uint64_t* full = bars;                          // [stages]
     uint64_t* empty = bars + kIsMaxStages;          // [stages]
     uint64_t* tfull = bars + 2 * kIsMaxStages;      // [S]
     uint64_t* tempty = tfull + S;                   // [S]
     uint64_t* wfull = tempty + S;                   // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+    uint64_t* rawfull = wfull + 1;                  // [stages] TMA -> transform warps (fused layers)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rawfull + kIsMaxStages);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int nplain = p.nchunks - p.xform_chunks;
 
     if (threadIdx.x == 0) {
-        const uint32_t full_count = (nplain > 0 ? 1u : 0u) + (p.xform_chunks > 0 ? static_cast<uint32_t>(kIsXformWarps) : 0u);
-        for (int s = 0; s < p.nstages; ++s) { mbar_init(&full[s], full_count); mbar_init(&empty[s], 1); }
+        // plain layers: the TMA completes `full` directly; fused layers: TMA -> rawfull -> transform warps -> full
+        const uint32_t full_count = p.xform_chunks > 0 ? static_cast<uint32_t>(kIsXformWarps) : 1u;
+        for (int s = 0; s < p.nstages; ++s) { mbar_init(&full[s], full_count); mbar_init(&empty[s], 1); mbar_init(&rawfull[s], 1); }
         for (int s = 0; s < S; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
         mbar_init(wfull, 1);
         fence_mbar_init();
@@ -120,7 +129,10 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
             for (uint32_t off = 0; off < p.w_bytes; off += 27648u)
                 tma_bulk_g2s(wsm + off, reinterpret_cast<const uint8_t*>(p.w) + off, min(27648u, p.w_bytes - off), wfull);
         }
-        if (nplain > 0) {
+        {
+            // every input chunk of the step arrives by TMA; chunks that hold RAW conv output are normalised in place
+            // by the transform warps before the MMA warp sees the stage
+            uint64_t* const bars_in = p.xform_chunks > 0 ? rawfull : full;
             int stage = 0; uint32_t phase = 0;
             for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
                 int win, c, za, zb;
@@ -128,16 +140,16 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
                 const int zi0 = max(za - 1, 1), zi1 = min(zb + 1, p.Z);
                 for (int zi = zi0; zi <= zi1; ++zi) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    if (lane == 0) mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(nplain) * p.RL * 16);
+                    if (lane == 0) mbar_arrive_expect_tx(&bars_in[stage], static_cast<uint32_t>(p.nchunks) * p.RL * 16);
                     __syncwarp();
                     const int64_t pos = static_cast<int64_t>(p.in_guard) + static_cast<int64_t>(win) * p.Vp +
                                         static_cast<int64_t>(zi) * p.PL + c * R - p.H;
-                    if (lane < nplain) {
-                        const int chunk = p.xform_chunks + lane;
+                    if (lane < p.nchunks) {
+                        const int chunk = lane;
                         const __nv_bfloat16* base = (chunk < p.nch0) ? p.in0 + static_cast<int64_t>(chunk) * p.inS * 8
                                                                      : p.in1 + static_cast<int64_t>(chunk - p.nch0) * p.inS * 8;
                         tma_bulk_g2s(stages + static_cast<size_t>(stage) * p.stage_bytes + static_cast<size_t>(chunk) * p.RL * 16,
-                                     base + pos * 8, p.RL * 16, &full[stage]);
+                                     base + pos * 8, p.RL * 16, &bars_in[stage]);
                     }
                     if (++stage == p.nstages) { stage = 0; phase ^= 1; }
                 }
@@ -283,60 +295,65 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
                 anyvalid |= valid[t];
             }
             const unsigned anyw = __ballot_sync(0xffffffffu, anyvalid);
-            double run_s = 0.0, run_q = 0.0;       // lane c: channel c
+            unsigned vw[T];
+#pragma unroll
+            for (int t = 0; t < T; ++t) vw[t] = __ballot_sync(0xffffffffu, valid[t]);
+            // InstanceNorm partial sums: every thread keeps fp32 running sums of ITS rows for the whole item (packed
+            // pairs of channels, one FADD2 + one FFMA2 per pair and plane); lanes are combined once per item.
+            f32x2 acc_s[16], acc_q[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { acc_s[i] = 0ull; acc_q[i] = 0ull; }
             for (int zo = za; zo <= zb; ++zo) {
                 const int s = zo % S;
                 mbar_wait(&tfull[s], (slot_par >> s) & 1u);
                 slot_par ^= 1u << s;
                 tc_fence_after();
-                {
-                    float part_s[16], part_q[16];          // column sums after the first butterfly round, over the T tiles
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) { part_s[i] = 0.f; part_q[i] = 0.f; }
+                for (int t = 0; t < T; ++t) {
+                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * (S * 32) + s * 32;
+                    if (anyw && vw[t] != 0) {      // warp-uniform
+                        float v[32];
+                        if (p.dbg_mode & 1) {
 #pragma unroll
-                    for (int t = 0; t < T; ++t) {
-                        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * (S * 32) + s * 32;
-                        if (anyw && __ballot_sync(0xffffffffu, valid[t]) != 0) {      // warp-uniform
-                            float v[32];
-                            tmem_ld32(taddr, v);
-                            tmem_zero32(taddr);          // the slot's next plane accumulates from zero
-                            if (valid[t]) {
-                                __nv_bfloat16* o = p.out + (poff[t] + static_cast<int64_t>(zo) * p.PL) * 8;
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    uint4 u;
-                                    u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-                                    u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                                    u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-                                    u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-                                    *reinterpret_cast<uint4*>(o + static_cast<int64_t>(j) * p.outS * 8) = u;
-                                }
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) v[i] = 0.f;
-                            }
-                            float r16[16];
-                            warp_transpose_round1(v, r16);
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) part_s[i] += r16[i];
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] *= v[i];
-                            warp_transpose_round1(v, r16);
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) part_q[i] += r16[i];
+                            for (int i = 0; i < 32; ++i) v[i] = 1.f;
                         } else {
-                            tmem_zero32(taddr);          // rows outside the window: discard what the MMAs summed there
+                            tmem_ld32(taddr, v);
                         }
-                    }
-                    if (anyw) {
-                        run_s += static_cast<double>(warp_transpose_finish(part_s));
-                        run_q += static_cast<double>(warp_transpose_finish(part_q));
+                        if (!(p.dbg_mode & 2)) tmem_zero32(taddr);          // the slot's next plane accumulates from zero
+                        if (valid[t] && !(p.dbg_mode & 8)) {
+                            __nv_bfloat16* o = p.out + (poff[t] + static_cast<int64_t>(zo) * p.PL) * 8;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                uint4 u;
+                                u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                                u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                                u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                                u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                                *reinterpret_cast<uint4*>(o + static_cast<int64_t>(j) * p.outS * 8) = u;
+                            }
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const f32x2 x2 = pk2(v[2 * i], v[2 * i + 1]);
+                                acc_s[i] = add2(acc_s[i], x2);
+                                acc_q[i] = fma2(x2, x2, acc_q[i]);
+                            }
+                        }
+                    } else if (!(p.dbg_mode & 2)) {
+                        tmem_zero32(taddr);          // rows outside the window: discard what the MMAs summed there
                     }
                 }
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[s]);
+            }
+            double run_s = 0.0, run_q = 0.0;       // lane c: channel c
+            if (anyw) {
+                float fs[32], fq[32];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { upk2(acc_s[i], fs[2 * i], fs[2 * i + 1]); upk2(acc_q[i], fq[2 * i], fq[2 * i + 1]); }
+                run_s = static_cast<double>(warp_transpose_sum32(fs));
+                run_q = static_cast<double>(warp_transpose_sum32(fq));
             }
             // combine the four quadrants in a fixed order and write this item's partial sums
             comb[q * 64 + lane * 2] = run_s;
@@ -353,34 +370,35 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
             asm volatile("bar.sync 1, 128;" ::: "memory");
         }
     } else if (p.xform_chunks > 0) {
-        // ------------------------------------------------------------ transform warps: NW warps per 8-channel chunk
-        // (the 32-position groups of the run are dealt round-robin to them).  The math is branch-free so that the
-        // compiler can interleave the MUFU -> FMA -> MUFU chains of all elements of a batch; the floor of this role
-        // is the MUFU pipe (ex2 + rcp per element, 16 lanes per SM and clock).
+        // ------------------------------------------------------------ transform warps: NW warps per 8-channel chunk.
+        // The raw chunk lands in the stage by TMA; each lane normalises "its" positions IN PLACE (ld.shared ->
+        // packed x*a+b -> mish -> st.shared, same address), so there is no global-load latency to hide and no
+        // register double buffer.  The floor of this role is the MUFU pipe (ex2 + rcp per element).
         constexpr int NW = kIsXformWarps / 4;
         const int tw = warp - 6;
         const int chunk = tw & 3, sub = tw >> 2;
-        uint32_t* mymask = masks + tw * 32;
-        const __nv_bfloat16* base = p.in0 + static_cast<int64_t>(chunk) * p.inS * 8;
-        const int nit = (p.RL + 31) / 32;
-        constexpr int U = 8;                       // 32-position groups per register batch: covers RL <= 512 with NW = 2
+        const int ngroups = (p.RL + 31) / 32;                    // 32-position groups of the run
+        const int nmine = (ngroups - sub + NW - 1) / NW;         // groups sub, sub + NW, ... handled by this warp
+        const uint32_t chunk_off = static_cast<uint32_t>(chunk) * p.RL * 16 + static_cast<uint32_t>(lane) * 16;
         int stage = 0; uint32_t phase = 0;
-        long long x_empty = 0, x_work = 0;
+        long long x_wait = 0, x_work = 0;
         for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
             int win, c, za, zb;
             item_geom(item, win, c, za, zb);
             const int zi0 = max(za - 1, 1), zi1 = min(zb + 1, p.Z);
-            // halo mask of the column's run (same for every plane of the item)
-            for (int it = 0; it < nit; ++it) {
-                const int i = it * 32 + lane;
+            // halo mask of this lane's positions (same for every plane of the item): bit k <-> group sub + NW*k
+            uint32_t inbits = 0, okbits = 0;
+            for (int k = 0; k < nmine; ++k) {
+                const int i = (sub + NW * k) * 32 + lane;
                 const int qq = c * R - p.H + i;
                 const int yp = qq / p.Xp, xp = qq - yp * p.Xp;
-                const bool in = i < p.RL && qq >= 0 && qq < p.PL && yp >= 1 && yp <= p.Y && xp >= 1;
-                const unsigned m = __ballot_sync(0xffffffffu, in);
-                if (lane == 0) mymask[it] = m;
+                const bool ok = i < p.RL;
+                const bool in = ok && qq >= 0 && qq < p.PL && yp >= 1 && yp <= p.Y && xp >= 1;
+                inbits |= (in ? 1u : 0u) << k;
+                okbits |= (ok ? 1u : 0u) << k;
             }
-            // InstanceNorm scale / shift of the producing layer for this window's 8 channels
-            float a[8], b[8];
+            // InstanceNorm scale / shift of the producing layer for this window's 8 channels, as packed pairs
+            f32x2 a[4], b[4];
             {
                 float ma = 0.f, mb = 0.f;
                 if (lane < 8) {
@@ -394,62 +412,46 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
                     mb = static_cast<float>(static_cast<double>(p.in_beta[ch]) - mean * sc);
                 }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { a[i] = __shfl_sync(0xffffffffu, ma, i); b[i] = __shfl_sync(0xffffffffu, mb, i); }
+                for (int i = 0; i < 4; ++i) {
+                    a[i] = pk2(__shfl_sync(0xffffffffu, ma, 2 * i), __shfl_sync(0xffffffffu, ma, 2 * i + 1));
+                    b[i] = pk2(__shfl_sync(0xffffffffu, mb, 2 * i), __shfl_sync(0xffffffffu, mb, 2 * i + 1));
+                }
             }
-            __syncwarp();
-            auto run_src = [&](int zz) {
-                const int64_t pos = static_cast<int64_t>(p.in_guard) + static_cast<int64_t>(win) * p.Vp +
-                                    static_cast<int64_t>(zz) * p.PL + c * R - p.H;
-                return reinterpret_cast<const uint4*>(base + pos * 8);
-            };
-            auto load_batch = [&](const uint4* src, int k0, uint4 (&u)[U]) {
-#pragma unroll
-                for (int k = 0; k < U; ++k) {
-                    const int i = (NW * (k0 + k) + sub) * 32 + lane;
-                    u[k] = (i < p.RL) ? ld_nc_u4(src + i) : make_uint4(0u, 0u, 0u, 0u);
-                }
-            };
-            auto xform_batch = [&](uint32_t dst, int k0, const uint4 (&u)[U]) {
-#pragma unroll
-                for (int k = 0; k < U; ++k) {
-                    const int it = NW * (k0 + k) + sub;
-                    const int i = it * 32 + lane;
-                    uint4 o;
-                    o.x = pack_bf16x2(mish_fast(fmaf(bf16_lo(u[k].x), a[0], b[0])), mish_fast(fmaf(bf16_hi(u[k].x), a[1], b[1])));
-                    o.y = pack_bf16x2(mish_fast(fmaf(bf16_lo(u[k].y), a[2], b[2])), mish_fast(fmaf(bf16_hi(u[k].y), a[3], b[3])));
-                    o.z = pack_bf16x2(mish_fast(fmaf(bf16_lo(u[k].z), a[4], b[4])), mish_fast(fmaf(bf16_hi(u[k].z), a[5], b[5])));
-                    o.w = pack_bf16x2(mish_fast(fmaf(bf16_lo(u[k].w), a[6], b[6])), mish_fast(fmaf(bf16_hi(u[k].w), a[7], b[7])));
-                    if (p.dbg_mode == 1) o = u[k];
-                    const bool in = (it < 32) && ((mymask[it & 31] >> lane) & 1u);     // halo positions stay exactly zero
-                    o.x = in ? o.x : 0u; o.y = in ? o.y : 0u; o.z = in ? o.z : 0u; o.w = in ? o.w : 0u;
-                    if (i < p.RL) st_shared_u4(dst + static_cast<uint32_t>(i) * 16u, o);
-                }
-            };
-            // the loads of the NEXT input plane are issued before the current plane is transformed (register double buffer)
-            uint4 ucur[U], unext[U];
-            load_batch(run_src(zi0), 0, ucur);
             for (int zi = zi0; zi <= zi1; ++zi) {
-                const uint4* src = run_src(zi);
-                if (zi < zi1) load_batch(run_src(zi + 1), 0, unext);
                 const long long x0 = p.dbg ? clock64() : 0;
-                mbar_wait(&empty[stage], phase ^ 1);
+                mbar_wait(&rawfull[stage], phase);
                 const long long x1 = p.dbg ? clock64() : 0;
-                const uint32_t dst = smem_u32(stages + static_cast<size_t>(stage) * p.stage_bytes + static_cast<size_t>(chunk) * p.RL * 16);
-                xform_batch(dst, 0, ucur);
-                for (int k0 = U; (NW * k0 + sub) * 32 < p.RL; k0 += U) {      // runs longer than one batch (large windows)
-                    load_batch(src, k0, ucur);
-                    xform_batch(dst, k0, ucur);
+                const uint32_t base = smem_u32(stages + static_cast<size_t>(stage) * p.stage_bytes) + chunk_off;
+                // two groups (16 elements per lane) per iteration: enough independent MUFU chains to keep the pipe busy
+                int k = (p.dbg_mode & 4) ? nmine : 0;
+#pragma unroll 1
+                for (; k + 1 < nmine; k += 2) {
+                    const uint32_t ad0 = base + static_cast<uint32_t>(sub + NW * k) * 512u;
+                    const uint32_t ad1 = ad0 + NW * 512u;
+                    const bool ok1 = (okbits >> (k + 1)) & 1u;        // only the last group can be partial
+                    uint4 u0 = ld_shared_u4(ad0), u1 = make_uint4(0u, 0u, 0u, 0u);
+                    if (ok1) u1 = ld_shared_u4(ad1);
+                    uint4 o0 = norm_mish8<kIsNewtonPairs>(u0, a, b), o1 = norm_mish8<kIsNewtonPairs>(u1, a, b);
+                    const bool in0 = (inbits >> k) & 1u, in1 = (inbits >> (k + 1)) & 1u;
+                    if (!in0) o0 = make_uint4(0u, 0u, 0u, 0u);          // halo positions stay exactly zero
+                    if (!in1) o1 = make_uint4(0u, 0u, 0u, 0u);
+                    st_shared_u4(ad0, o0);
+                    if (ok1) st_shared_u4(ad1, o1);
+                }
+                if (k < nmine && ((okbits >> k) & 1u)) {
+                    const uint32_t ad0 = base + static_cast<uint32_t>(sub + NW * k) * 512u;
+                    uint4 o0 = norm_mish8<kIsNewtonPairs>(ld_shared_u4(ad0), a, b);
+                    if (!((inbits >> k) & 1u)) o0 = make_uint4(0u, 0u, 0u, 0u);
+                    st_shared_u4(ad0, o0);
                 }
                 fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core's async proxy
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full[stage]);
-                if (p.dbg) { x_empty += x1 - x0; x_work += clock64() - x1; }
+                if (p.dbg) { x_wait += x1 - x0; x_work += clock64() - x1; }
                 if (++stage == p.nstages) { stage = 0; phase ^= 1; }
-#pragma unroll
-                for (int k = 0; k < U; ++k) ucur[k] = unext[k];
             }
         }
-        if (p.dbg && tw == 0 && lane == 0) { p.dbg[blockIdx.x * 8 + 5] = x_empty; p.dbg[blockIdx.x * 8 + 6] = x_work; }
+        if (p.dbg && tw == 0 && lane == 0) { p.dbg[blockIdx.x * 8 + 5] = x_wait; p.dbg[blockIdx.x * 8 + 6] = x_work; }
     }
 
     tc_fence_before();

@@ -171,10 +171,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvArgs
                 }
             }
         };
+        float bsr[MODE == kModeDeconvScatter ? 32 : 1];
+        int bias_nb = -1;
         for (int item = item0; item < item1; ++item, ++it) {
             const int g = item / p.NB, nb = item - g * p.NB;
             const int64_t s = static_cast<int64_t>(g) * p.T * 128;
             const int buf = it & 1;
+            if (MODE == kModeDeconvScatter && nb != bias_nb) {
+                bias_nb = nb;
+#pragma unroll
+                for (int i = 0; i < (MODE == kModeDeconvScatter ? 32 : 1); ++i) bsr[i] = __ldg(p.bias + nb * 32 + i);
+            }
             mbar_wait(&tfull[buf], (it >> 1) & 1);
             tc_fence_after();
             for (int t = 0; t < p.T; ++t) {
@@ -217,22 +224,22 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvArgs
                         run_s[h] += static_cast<double>(warp_transpose_sum32(v));
                         run_q[h] += static_cast<double>(warp_transpose_sum32(sq));
                     } else {
+                        // transposed conv k2 s2: the 8 sub-positions (a,b,c) of this input voxel are the 8 column
+                        // blocks of ONE N = 256 accumulator (h = a*4 + b*2 + c), 32 couts each
                         if (valid) {
-                            const int NBc = p.cout / NBLK;
-                            const int abc = nb / NBc, cob = nb - abc * NBc;
+                            const int abc = h;
                             const int oz = 2 * (zp - 1) + (abc >> 2) + 1;
                             const int oy = 2 * (yp - 1) + ((abc >> 1) & 1) + 1;
                             const int ox = 2 * (xp - 1) + (abc & 1) + 1;
                             const int64_t Po = static_cast<int64_t>(win) * p.oVp + (static_cast<int64_t>(oz) * p.oYp + oy) * p.oXp + ox;
-                            const float* bs = p.bias + cob * NBLK + h * 32;
-                            __nv_bfloat16* o = p.out + (static_cast<int64_t>(cob * (NBLK / 8) + h * 4) * p.outS + p.out_guard + Po) * 8;
+                            __nv_bfloat16* o = p.out + (static_cast<int64_t>(nb * 4) * p.outS + p.out_guard + Po) * 8;
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 uint4 u;
-                                u.x = pack_bf16x2(v[8 * j + 0] + __ldg(bs + 8 * j + 0), v[8 * j + 1] + __ldg(bs + 8 * j + 1));
-                                u.y = pack_bf16x2(v[8 * j + 2] + __ldg(bs + 8 * j + 2), v[8 * j + 3] + __ldg(bs + 8 * j + 3));
-                                u.z = pack_bf16x2(v[8 * j + 4] + __ldg(bs + 8 * j + 4), v[8 * j + 5] + __ldg(bs + 8 * j + 5));
-                                u.w = pack_bf16x2(v[8 * j + 6] + __ldg(bs + 8 * j + 6), v[8 * j + 7] + __ldg(bs + 8 * j + 7));
+                                u.x = pack_bf16x2(v[8 * j + 0] + bsr[8 * j + 0], v[8 * j + 1] + bsr[8 * j + 1]);
+                                u.y = pack_bf16x2(v[8 * j + 2] + bsr[8 * j + 2], v[8 * j + 3] + bsr[8 * j + 3]);
+                                u.z = pack_bf16x2(v[8 * j + 4] + bsr[8 * j + 4], v[8 * j + 5] + bsr[8 * j + 5]);
+                                u.w = pack_bf16x2(v[8 * j + 6] + bsr[8 * j + 6], v[8 * j + 7] + bsr[8 * j + 7]);
                                 *reinterpret_cast<uint4*>(o + static_cast<int64_t>(j) * p.outS * 8) = u;
                             }
                         }

@@ -76,6 +76,12 @@ struct Ctx {
 
 void set_error(Ctx* ctx, const char* fmt, ...);
 
+// Transient device buffers come from the device's stream-ordered pool (release threshold raised in dlv_init, so a
+// second call of the same size re-uses the memory instead of paying cudaMalloc / cudaFree for gigabytes).
+inline cudaError_t dmalloc(Ctx* ctx, void** p, size_t bytes) { return cudaMallocAsync(p, bytes ? bytes : 1, ctx->stream); }
+template <class T> inline cudaError_t dmalloc(Ctx* ctx, T** p, size_t bytes) { return dmalloc(ctx, reinterpret_cast<void**>(p), bytes); }
+inline void dfree(Ctx* ctx, void* p) { if (p) cudaFreeAsync(p, ctx->stream); }
+
 #define DLV_CUDA_OK(ctx, expr)                                                              \
     do {                                                                                    \
         cudaError_t _e = (expr);                                                            \

@@ -3,7 +3,11 @@
 //
 // Replaces the compute of run_inference (inference/inference.py:229-329) and sliding_window_inference
 // (inference/sliding_window_inferer.py:102-251) of the reference.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <vector>
 
@@ -87,11 +91,13 @@ __global__ void average_kernel(const int32_t* __restrict__ acc, float* __restric
 
 struct DevBuf {
     void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
+    cudaStream_t s = nullptr;
+    ~DevBuf() { if (p) cudaFreeAsync(p, s); }
     template <class T> T* as() { return static_cast<T*>(p); }
 };
 static int dev_alloc(Ctx* ctx, DevBuf& b, size_t bytes) {
-    DLV_CUDA_OK(ctx, cudaMalloc(&b.p, bytes ? bytes : 1));
+    b.s = ctx->stream;
+    DLV_CUDA_OK(ctx, dmalloc(ctx, &b.p, bytes));
     return 0;
 }
 template <class T>
@@ -220,8 +226,19 @@ int segment_run(Ctx* ctx, const void* volume_any, const dlv_seg_params* P, void*
     }
     if (P->overlap < 0.f || P->overlap >= 1.f) { set_error(ctx, "overlap must be >= 0 and < 1."); return DLV_ERR_ARG; }
     const int batch = P->window_batch > 0 ? P->window_batch : 32;
+    // DLV_TRACE=1: host wall clock per phase on stderr (adds a stream synchronisation at every mark)
+    static const bool trace = getenv("DLV_TRACE") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (!trace) return;
+        cudaStreamSynchronize(ctx->stream);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[dlv_segment] %-22s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
     int rc = engine_prepare(ctx, P->roi, batch);
     if (rc) return rc;
+    mark("engine_prepare");
 
     const size_t nvox_pad = static_cast<size_t>(PZ) * PY * PX;
     const size_t nvox = static_cast<size_t>(Z) * Y * X;
@@ -235,6 +252,7 @@ int segment_run(Ctx* ctx, const void* volume_any, const dlv_seg_params* P, void*
         slab = slab_own.as<uint16_t>();
     }
 
+    mark("volume on device");
     // ---- window grid, z-major / x fastest like dense_patch_slices
     const std::vector<int> sz = window_starts(PZ, P->roi[0], P->overlap), sy = window_starts(PY, P->roi[1], P->overlap),
                            sx = window_starts(PX, P->roi[2], P->overlap);
@@ -256,6 +274,7 @@ int segment_run(Ctx* ctx, const void* volume_any, const dlv_seg_params* P, void*
         DLV_CUDA_OK(ctx, cudaMemcpyAsync(d_active.p, active.data(), nwin * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     }
 
+    mark("skip-rule scan");
     // ---- schedule: passes x active windows
     const int passes = P->tta ? 13 : 1;
     int single_flip = 0;
@@ -276,6 +295,7 @@ int segment_run(Ctx* ctx, const void* volume_any, const dlv_seg_params* P, void*
     DevBuf d_acc;
     if ((rc = dev_alloc(ctx, d_acc, nvox_pad * 4))) return rc;
     DLV_CUDA_OK(ctx, cudaMemsetAsync(d_acc.p, 0, nvox_pad * 4, ctx->stream));
+    mark("schedule + acc memset");
     cudaEvent_t e0, e1, e2;
     cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
     const int64_t launches0 = ctx->launches;
@@ -283,10 +303,12 @@ int segment_run(Ctx* ctx, const void* volume_any, const dlv_seg_params* P, void*
     cudaEventRecord(e0, ctx->stream);
     rc = seg_accumulate(ctx, slab, PY, PX, sched, P->roi, batch, P->blend_mode, d_acc.as<int32_t>());
     cudaEventRecord(e1, ctx->stream);
+    mark("u-net passes");
 
     // ---- average (in place: int32 sums -> fp32 logits)
     if (rc == 0) rc = seg_average(ctx, d_acc.as<int32_t>(), PZ, 0, P->shape_pad, P->roi, P->overlap, active.data(), passes, P->blend_mode);
 
+    mark("average");
     // ---- binarise + eroded-mask gate
     DevBuf bin_own, sig_own;
     uint8_t* bin = static_cast<uint8_t*>(binaries_any);
@@ -299,6 +321,7 @@ int segment_run(Ctx* ctx, const void* volume_any, const dlv_seg_params* P, void*
         rc = post_finalise(ctx, d_acc.as<float>(), slab, P->shape_pad, P->shape_real, P->threshold, P->erosion_iters,
                            P->erosion_block_planes, bin, sig);
     cudaEventRecord(e2, ctx->stream);
+    mark("finalise");
     if (rc == 0) {
         if (bin_host) cudaMemcpyAsync(binaries_any, bin, nvox, cudaMemcpyDeviceToHost, ctx->stream);
         if (sig_host) cudaMemcpyAsync(sig_any, sig, nvox * 4, cudaMemcpyDeviceToHost, ctx->stream);
@@ -307,6 +330,7 @@ int segment_run(Ctx* ctx, const void* volume_any, const dlv_seg_params* P, void*
     }
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (rc == 0 && e != cudaSuccess) { set_error(ctx, "dlv_segment: %s", cudaGetErrorString(e)); rc = DLV_ERR_CUDA; }
+    mark("outputs");
     if (rc == 0 && st_out) {
         float ms = 0.f;
         st_out->windows_total = nwin;

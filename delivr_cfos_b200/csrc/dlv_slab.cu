@@ -81,13 +81,13 @@ int dlv_windows_active(dlv_ctx* c, const uint16_t* slab_dev, int64_t SY, int64_t
     if (n <= 0) return DLV_OK;
     cudaSetDevice(ctx->device);
     int32_t *d_o = nullptr, *d_a = nullptr;
-    DLV_CUDA_OK(ctx, cudaMalloc(reinterpret_cast<void**>(&d_o), sizeof(int32_t) * 3 * n));
-    DLV_CUDA_OK(ctx, cudaMalloc(reinterpret_cast<void**>(&d_a), sizeof(int32_t) * n));
+    DLV_CUDA_OK(ctx, dlv::dmalloc(ctx, &d_o, sizeof(int32_t) * 3 * n));
+    DLV_CUDA_OK(ctx, dlv::dmalloc(ctx, &d_a, sizeof(int32_t) * n));
     cudaMemcpyAsync(d_o, origins_host, sizeof(int32_t) * 3 * n, cudaMemcpyHostToDevice, ctx->stream);
     int rc = dlv::windows_active(ctx, slab_dev, SY, SX, d_o, n, roi, d_a);
     cudaMemcpyAsync(active_host, d_a, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_o); cudaFree(d_a);
+    dlv::dfree(ctx, d_o); dlv::dfree(ctx, d_a);
     if (rc == 0 && e != cudaSuccess) { dlv::set_error(ctx, "dlv_windows_active: %s", cudaGetErrorString(e)); rc = DLV_ERR_CUDA; }
     return rc;
 }
@@ -135,7 +135,7 @@ int dlv_ccl_boundary_pairs(dlv_ctx* c, const uint32_t* labels_lo_plane_dev, cons
     if (!labels_lo_plane_dev || !labels_hi_plane_dev || !pairs_dev || !count_host_out || cap < 0) { dlv::set_error(ctx, "dlv_ccl_boundary_pairs: bad argument"); return DLV_ERR_ARG; }
     cudaSetDevice(ctx->device);
     unsigned long long* cnt = nullptr;
-    DLV_CUDA_OK(ctx, cudaMalloc(reinterpret_cast<void**>(&cnt), 8));
+    DLV_CUDA_OK(ctx, dlv::dmalloc(ctx, &cnt, 8));
     cudaMemsetAsync(cnt, 0, 8, ctx->stream);
     if (Y > 0 && X > 0) {
         dim3 grid(static_cast<unsigned>((X + 127) / 128), static_cast<unsigned>(Y));
@@ -146,7 +146,7 @@ int dlv_ccl_boundary_pairs(dlv_ctx* c, const uint32_t* labels_lo_plane_dev, cons
     unsigned long long h = 0;
     cudaMemcpyAsync(&h, cnt, 8, cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(cnt);
+    dlv::dfree(ctx, cnt);
     if (e != cudaSuccess) { dlv::set_error(ctx, "dlv_ccl_boundary_pairs: %s", cudaGetErrorString(e)); return DLV_ERR_CUDA; }
     *count_host_out = static_cast<int64_t>(h);
     return DLV_OK;

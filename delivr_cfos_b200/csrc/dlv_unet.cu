@@ -53,12 +53,30 @@ __global__ void window_active_kernel(const uint16_t* __restrict__ slab, int64_t 
     const int win = blockIdx.x;
     const int oz = origins[3 * win], oy = origins[3 * win + 1], ox = origins[3 * win + 2];
     int any = 0;
-    const int n = rz * ry * rx;
-    for (int idx = threadIdx.x; idx < n && !any; idx += blockDim.x) {
-        const int x = idx % rx, y = (idx / rx) % ry, z = idx / (rx * ry);
-        any |= slab[(static_cast<int64_t>(oz + z) * slabY + (oy + y)) * slabX + (ox + x)] > 0;
+    if (((ox | rx) & 7) == 0 && (slabX & 7) == 0) {
+        // 16 B loads (8 voxels), 8 independent loads per thread in flight; block-wide early exit every round
+        const int rx8 = rx >> 3, n8 = rz * ry * rx8;
+        for (int base = 0; base < n8; base += 8 * blockDim.x) {
+            uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int idx = base + k * blockDim.x + threadIdx.x;
+                if (idx < n8) {
+                    const int x8 = idx % rx8, y = (idx / rx8) % ry, z = idx / (rx8 * ry);
+                    const uint4 u = ld_nc_u4(slab + (static_cast<int64_t>(oz + z) * slabY + (oy + y)) * slabX + ox + 8 * x8);
+                    acc.x |= u.x; acc.y |= u.y; acc.z |= u.z; acc.w |= u.w;
+                }
+            }
+            if (__syncthreads_or((acc.x | acc.y | acc.z | acc.w) != 0u)) { any = 1; break; }
+        }
+    } else {
+        const int n = rz * ry * rx;
+        for (int idx = threadIdx.x; idx < n && !any; idx += blockDim.x) {
+            const int x = idx % rx, y = (idx / rx) % ry, z = idx / (rx * ry);
+            any |= slab[(static_cast<int64_t>(oz + z) * slabY + (oy + y)) * slabX + (ox + x)] > 0;
+        }
+        any = __syncthreads_or(any);
     }
-    any = __syncthreads_or(any);
     if (threadIdx.x == 0) active[win] = any;
 }
 
@@ -106,6 +124,29 @@ __global__ void norm_mish_kernel(const __nv_bfloat16* __restrict__ raw, LevelDev
         if (idx >= L.Z * L.Y * L.X) return;
         const int x = idx % L.X, y = (idx / L.X) % L.Y, z = idx / (L.X * L.Y);
         apply(pos_of(L, win, z, y, x), m);
+    } else if (!out) {
+        // Pool only (the full-resolution activation is re-derived by the consuming fused conv): mish is decreasing
+        // left of its minimum and increasing right of it, so max over the 2x2x2 block of mish(a*x+b) is
+        // max(mish(a*max x + b), mish(a*min x + b)) - two activations per channel instead of eight.
+        const int X2 = L.X / 2, Y2 = L.Y / 2, Z2 = L.Z / 2;
+        if (idx >= X2 * Y2 * Z2) return;
+        const int x = idx % X2, y = (idx / X2) % Y2, z = idx / (X2 * Y2);
+        uint4 mx, mn;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint4 u = ld_nc_u4(raw + cbase + pos_of(L, win, 2 * z + (k >> 2), 2 * y + ((k >> 1) & 1), 2 * x + (k & 1)) * 8);
+            if (k == 0) { mx = u; mn = u; }
+            else {
+                mx.x = bf16x2_max(mx.x, u.x); mx.y = bf16x2_max(mx.y, u.y); mx.z = bf16x2_max(mx.z, u.z); mx.w = bf16x2_max(mx.w, u.w);
+                mn.x = bf16x2_min(mn.x, u.x); mn.y = bf16x2_min(mn.y, u.y); mn.z = bf16x2_min(mn.z, u.z); mn.w = bf16x2_min(mn.w, u.w);
+            }
+        }
+        f32x2 a2[4], b2[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { a2[i] = pk2(a[2 * i], a[2 * i + 1]); b2[i] = pk2(b[2 * i], b[2 * i + 1]); }
+        const uint4 hi = norm_mish8<0>(mx, a2, b2), lo = norm_mish8<0>(mn, a2, b2);
+        const uint4 o = make_uint4(bf16x2_max(hi.x, lo.x), bf16x2_max(hi.y, lo.y), bf16x2_max(hi.z, lo.z), bf16x2_max(hi.w, lo.w));
+        *reinterpret_cast<uint4*>(pooled + static_cast<int64_t>(chunk) * Lp.S * 8 + pos_of(Lp, win, z, y, x) * 8) = o;
     } else {
         const int X2 = L.X / 2, Y2 = L.Y / 2, Z2 = L.Z / 2;
         if (idx >= X2 * Y2 * Z2) return;
@@ -130,7 +171,7 @@ __global__ void final_blend_kernel(const __nv_bfloat16* __restrict__ raw, LevelD
                                    int32_t* __restrict__ acc, int64_t slabY, int64_t slabX,
                                    const float* __restrict__ wz, const float* __restrict__ wy, const float* __restrict__ wx,
                                    float* __restrict__ logits_out) {
-    __shared__ float sa[32], sb[32], sw[32];
+    __shared__ f32x2 sa[16], sb[16], sw[16];
     const int win = blockIdx.y;
     if (threadIdx.x < 32) {
         const int c = threadIdx.x;
@@ -139,23 +180,31 @@ __global__ void final_blend_kernel(const __nv_bfloat16* __restrict__ raw, LevelD
         double var = stats[(static_cast<int64_t>(win) * 32 + c) * 2 + 1] * inv - mean * mean;
         var = var > 0.0 ? var : 0.0;
         const double a = static_cast<double>(gamma[c]) / sqrt(var + 1e-5);
-        sa[c] = static_cast<float>(a);
-        sb[c] = static_cast<float>(static_cast<double>(beta[c]) - mean * a);
-        sw[c] = fw[c];
+        reinterpret_cast<float*>(sa)[c] = static_cast<float>(a);
+        reinterpret_cast<float*>(sb)[c] = static_cast<float>(static_cast<double>(beta[c]) - mean * a);
+        reinterpret_cast<float*>(sw)[c] = fw[c];
     }
     __syncthreads();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= L.Z * L.Y * L.X) return;
     const int x = idx % L.X, y = (idx / L.X) % L.Y, z = idx / (L.X * L.Y);
     const int64_t P = pos_of(L, win, z, y, x);
-    float logit = fb;
+    uint4 u[4];
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) u[ch] = ld_nc_u4(raw + static_cast<int64_t>(ch) * L.S * 8 + P * 8);
+    f32x2 dot = 0ull;
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
-        const uint4 u = *reinterpret_cast<const uint4*>(raw + static_cast<int64_t>(ch) * L.S * 8 + P * 8);
-        const float f[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y), bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+        f32x2 a2[4], b2[4], m[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) logit = fmaf(sw[ch * 8 + i], mish_fast(fmaf(f[i], sa[ch * 8 + i], sb[ch * 8 + i])), logit);
+        for (int i = 0; i < 4; ++i) { a2[i] = sa[ch * 4 + i]; b2[i] = sb[ch * 4 + i]; }
+        norm_mish8_f32<4>(u[ch], a2, b2, m);      // reciprocals on the FMA pipe: one MUFU per element
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dot = fma2(sw[ch * 4 + i], m[i], dot);
     }
+    float d0, d1;
+    upk2(dot, d0, d1);
+    const float logit = fb + d0 + d1;
     if (logits_out) {   // operator-level entry point: plain per-window logits, window order
         logits_out[static_cast<int64_t>(win) * L.Z * L.Y * L.X + idx] = logit;
         return;
@@ -284,13 +333,13 @@ static int pack_conv_is(Ctx* ctx, ConvLayer& L, const float* W, bool first) {
 }
 
 static int pack_deconv(Ctx* ctx, ConvLayer& L, const float* W) {
-    // W[cin][cout][2][2][2] (torch ConvTranspose3d) -> [KB][NB = 8*cout/nblk][1][2][nblk][8]
+    // W[cin][cout][2][2][2] (torch ConvTranspose3d) -> [KB][NB = cout/32][1][2][256 = (abc, 32 couts)][8]:
+    // one N = 256 MMA produces all 8 sub-positions of 32 output channels for 128 input voxels
     L.ntaps = 1;
     L.cin_pad = L.cin;
     L.KB = L.cin / 16;
-    L.nblk = (L.cout >= 64) ? 64 : 32;
-    const int NBc = L.cout / L.nblk;
-    L.NB = 8 * NBc;
+    L.nblk = 256;
+    L.NB = L.cout / 32;
     std::vector<bf16> pk(static_cast<size_t>(L.KB) * L.NB * 2 * L.nblk * 8);
     for (int kb = 0; kb < L.KB; ++kb)
         for (int nb = 0; nb < L.NB; ++nb)
@@ -298,7 +347,7 @@ static int pack_deconv(Ctx* ctx, ConvLayer& L, const float* W) {
                 for (int n = 0; n < L.nblk; ++n)
                     for (int e = 0; e < 8; ++e) {
                         const int ci = kb * 16 + kc * 8 + e;
-                        const int abc = nb / NBc, co = (nb % NBc) * L.nblk + n;
+                        const int abc = n / 32, co = nb * 32 + (n % 32);
                         const float v = W[(static_cast<size_t>(ci) * L.cout + co) * 8 + abc];
                         pk[(((static_cast<size_t>(kb) * L.NB + nb) * 2 + kc) * L.nblk + n) * 8 + e] = to_bf16(v);
                     }
@@ -451,8 +500,7 @@ static int run_conv(Ctx* ctx, const ConvLayer& Ly, const Level& L, int nwin, con
         rc = (Ly.nblk == 32) ? launch_conv_t<32, 27, kModeConvStats>(ctx, a, grid2, smem)
                              : launch_conv_t<64, 27, kModeConvStats>(ctx, a, grid2, smem);
     } else {
-        rc = (Ly.nblk == 32) ? launch_conv_t<32, 1, kModeDeconvScatter>(ctx, a, grid2, smem)
-                             : launch_conv_t<64, 1, kModeDeconvScatter>(ctx, a, grid2, smem);
+        rc = launch_conv_t<256, 1, kModeDeconvScatter>(ctx, a, grid2, smem);
     }
     if (ctx->time_convs && rc == 0) {
         cudaEventRecord(ctx->ev1, ctx->stream);
@@ -590,7 +638,7 @@ static int run_conv_is(Ctx* ctx, const ConvLayer& Ly, const Level& L, int nwin, 
         double t[7] = {0, 0, 0, 0, 0, 0, 0};
         for (int b = 0; b < grid; ++b) for (int k = 0; k < 7; ++k) t[k] += h[b * 8 + k];
         const double st = t[4] > 0 ? t[4] : 1;
-        fprintf(stderr, "[is] %-22s nwin %d T %d NZS %d nst %d KB %d xf %d: cycles/CTA %.0f | per step: total %.0f mma-thread waits %.0f (%.0f %.0f) | xform empty-wait %.0f work %.0f\n",
+        fprintf(stderr, "[is] %-22s nwin %d T %d NZS %d nst %d KB %d xf %d: cycles/CTA %.0f | per step: total %.0f mma-thread waits %.0f (%.0f %.0f) | xform raw-wait %.0f work %.0f\n",
                 Ly.name.c_str(), nwin, P.T, P.NZS, P.nstages, Ly.KB, a.xform_chunks, t[0] / grid, t[0] / st, t[1] / st, t[2] / st, t[3] / st, t[5] / st, t[6] / st);
     }
     if (rc) return rc;
