@@ -43,20 +43,19 @@ struct IsArgs {
     const float* in_beta;       // [32]
     int64_t inS;                // positions per chunk of the inputs
     int in_guard;
-    const __nv_bfloat16* w;     // [KB][9][2][96][8]
+    const __nv_bfloat16* w;     // [KB][9 (ky,kx)][2][96][8]; FOLD: [1][3 (ky)][2][96][8]
     __nv_bfloat16* out;         // raw conv output, 4 chunks
     int64_t outS;
     int out_guard;
-    double* part;               // [nwin][nparts][32][2] partial sums of this layer's output
+    double* part;               // [nwin][nparts][32][2] partial sums of this layer's output, nparts = (Z / G) * NC
     int nparts;
     int Z, Y, X, Xp, PL, Vp;
     int KB, NC, NZS, Zs, nitems, RL, H, nstages;
+    int G;                      // planes per statistics group (Zs is a multiple of G)
     uint32_t stage_bytes, w_bytes;
     double inv_count;           // 1 / (Z*Y*X)
     long long* dbg;             // optional [grid][8] cycle counters (DLV_IS_DEBUG)
     int dbg_mode;               // timing experiments (results invalid): 1 skip TMEM loads, 2 skip TMEM zeroing, 4 skip the transform's smem traffic, 8 skip output stores
-    uint32_t tap_a[36];         // per (kb, ky, kx): A descriptor offset (16 B units) = kb*2*RL + H + (ky-1)*Xp + (kx-1)
-    uint32_t tap_b[36];         // per (kb, ky, kx): B descriptor offset (16 B units) = (kb*9 + ky*3 + kx) * 192
 };
 
 // deterministic reduction of the per-item partial sums: stats[win][c][0..1] = sum over parts (fixed order)
@@ -78,15 +77,18 @@ __device__ __forceinline__ void st_shared_u4(uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-template <int T, int S>
+// FOLD: the uint16 first layer.  Its K = 16 slot holds the 3 kx neighbours x 4 split terms of the single input channel
+// (gather_windows_kernel), so only the centre kx tap exists: 3 MMAs per plane and tile instead of 9.
+template <int T, int S, bool FOLD>
 __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) {
+    constexpr int KXN = FOLD ? 1 : 3;
     static_assert(T * S * 32 <= 512, "accumulator ring exceeds TMEM");
     constexpr int R = 128 * T;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* wsm = smem;
     uint8_t* stages = smem + p.w_bytes;
-    double* comb = reinterpret_cast<double*>(stages + static_cast<size_t>(p.nstages) * p.stage_bytes);   // [4][64]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(comb + 256);
+    double* comb = reinterpret_cast<double*>(stages + static_cast<size_t>(p.nstages) * p.stage_bytes);   // [2][4][64]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(comb + 512);
     uint64_t* full = bars;                          // [stages]
     uint64_t* empty = bars + kIsMaxStages;          // [stages]
     uint64_t* tfull = bars + 2 * kIsMaxStages;      // [S]
@@ -220,7 +222,7 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
             const int nrows = 3 * p.KB;                                  // (kb, ky) rows of 3 taps
             const uint32_t xp = static_cast<uint32_t>(p.Xp);
             const uint32_t a_kb_adj = static_cast<uint32_t>(2 * p.RL) - 3u * xp;   // row 2 of kb -> row 0 of kb + 1
-            const uint32_t a_tap0 = static_cast<uint32_t>(p.H - p.Xp - 1);
+            const uint32_t a_tap0 = static_cast<uint32_t>(p.H - p.Xp - (FOLD ? 0 : 1));
             Step cur, nxt;
             bool more = have;
             if (more) { make_step(cur); wait_step(cur, false, false, false); }
@@ -243,14 +245,14 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
                     for (int r = 0; r < nrows; ++r) {
                         if (r == nrows - 1) lookahead();
 #pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) {
+                        for (int kx = 0; kx < KXN; ++kx) {
 #pragma unroll
                             for (int t = 0; t < T; ++t) {
                                 umma_bf16_lh(cur.c0 + t * (S * 32), arow + kx + t * 128, brow + kx * 192, dhi, cur.i0, 1u);
                                 if (two) umma_bf16_lh(tmem_base + t * (S * 32), arow + kx + t * 128, brow1 + kx * 192, dhi, cur.i1, 1u);
                             }
                         }
-                        brow += 576; brow1 += 576;
+                        brow += 192 * KXN; brow1 += 192 * KXN;
                         if (++ky == 3) { ky = 0; arow += a_kb_adj + xp; } else { arow += xp; }
                     }
                 };
@@ -271,7 +273,7 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
     } else if (warp < 6) {
         // ------------------------------------------------------------ epilogue (4 warps = 4 TMEM lane quadrants)
         const int q = warp & 3;
-        uint32_t slot_par = 0;
+        uint32_t slot_par = 0, flush = 0;
         // all accumulators start at zero (every MMA accumulates); then hand every slot to the MMA warp
         for (int col = 0; col < 512; col += 32) tmem_zero32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + col);
         tmem_wait_st();
@@ -298,8 +300,11 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
             unsigned vw[T];
 #pragma unroll
             for (int t = 0; t < T; ++t) vw[t] = __ballot_sync(0xffffffffu, valid[t]);
-            // InstanceNorm partial sums: every thread keeps fp32 running sums of ITS rows for the whole item (packed
-            // pairs of channels, one FADD2 + one FFMA2 per pair and plane); lanes are combined once per item.
+            // InstanceNorm partial sums: every thread keeps fp32 running sums of ITS rows over one GROUP of kIsStatGroup
+            // output planes (packed pairs of channels, one FADD2 + one FFMA2 per pair and plane); at the end of a
+            // group the lanes and quadrants are combined in a fixed order and written as that (group, column)'s
+            // partial record.  Groups are aligned to absolute z and z segments are whole groups, so the records -
+            // and therefore the statistics - do not depend on how the planes were split into work items.
             f32x2 acc_s[16], acc_q[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) { acc_s[i] = 0ull; acc_q[i] = 0ull; }
@@ -346,28 +351,33 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[s]);
-            }
-            double run_s = 0.0, run_q = 0.0;       // lane c: channel c
-            if (anyw) {
-                float fs[32], fq[32];
+                if (zo % p.G == 0 || zo == zb) {
+                    // end of a statistics group: lane c <- channel c, quadrants combined by warp q == 2.  `comb` is
+                    // double-buffered: the barrier of flush k + 1 orders warp 2's reads of flush k before the writes
+                    // of flush k + 2, so one barrier per flush suffices.
+                    double run_s = 0.0, run_q = 0.0;
+                    if (anyw) {
+                        float fs[32], fq[32];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) { upk2(acc_s[i], fs[2 * i], fs[2 * i + 1]); upk2(acc_q[i], fq[2 * i], fq[2 * i + 1]); }
-                run_s = static_cast<double>(warp_transpose_sum32(fs));
-                run_q = static_cast<double>(warp_transpose_sum32(fq));
+                        for (int i = 0; i < 16; ++i) { upk2(acc_s[i], fs[2 * i], fs[2 * i + 1]); upk2(acc_q[i], fq[2 * i], fq[2 * i + 1]); }
+                        run_s = static_cast<double>(warp_transpose_sum32(fs));
+                        run_q = static_cast<double>(warp_transpose_sum32(fq));
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { acc_s[i] = 0ull; acc_q[i] = 0ull; }
+                    }
+                    double* cb = comb + (flush & 1u) * 256;
+                    ++flush;
+                    cb[q * 64 + lane * 2] = run_s;
+                    cb[q * 64 + lane * 2 + 1] = run_q;
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (q == 2) {     // warp 2 -> q = 2
+                        const int grp = (zo - 1) / p.G;
+                        double* dst = p.part + (static_cast<int64_t>(win) * p.nparts + grp * p.NC + c) * 64;
+                        dst[lane * 2] = cb[lane * 2] + cb[64 + lane * 2] + cb[128 + lane * 2] + cb[192 + lane * 2];
+                        dst[lane * 2 + 1] = cb[lane * 2 + 1] + cb[64 + lane * 2 + 1] + cb[128 + lane * 2 + 1] + cb[192 + lane * 2 + 1];
+                    }
+                }
             }
-            // combine the four quadrants in a fixed order and write this item's partial sums
-            comb[q * 64 + lane * 2] = run_s;
-            comb[q * 64 + lane * 2 + 1] = run_q;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (q == 2) {     // warp 2 -> q = 2
-                const int zseg = (item / p.NC) % p.NZS;
-                double* dst = p.part + (static_cast<int64_t>(win) * p.nparts + zseg * p.NC + c) * 64;
-                const double a = comb[lane * 2] + comb[64 + lane * 2] + comb[128 + lane * 2] + comb[192 + lane * 2];
-                const double b = comb[lane * 2 + 1] + comb[64 + lane * 2 + 1] + comb[128 + lane * 2 + 1] + comb[192 + lane * 2 + 1];
-                dst[lane * 2] = a;
-                dst[lane * 2 + 1] = b;
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
         }
     } else if (p.xform_chunks > 0) {
         // ------------------------------------------------------------ transform warps: NW warps per 8-channel chunk.
@@ -422,15 +432,21 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
                 mbar_wait(&rawfull[stage], phase);
                 const long long x1 = p.dbg ? clock64() : 0;
                 const uint32_t base = smem_u32(stages + static_cast<size_t>(stage) * p.stage_bytes) + chunk_off;
-                // two groups (16 elements per lane) per iteration: enough independent MUFU chains to keep the pipe busy
+                // two groups (16 elements per lane) per iteration: enough independent MUFU chains to keep the pipe busy;
+                // the NEXT iteration's raw values are loaded before this iteration's arithmetic (the shared-memory
+                // load latency was the largest single stall of this role)
                 int k = (p.dbg_mode & 4) ? nmine : 0;
+                uint4 n0 = make_uint4(0u, 0u, 0u, 0u), n1 = n0;
+                if (k < nmine && ((okbits >> k) & 1u)) n0 = ld_shared_u4(base + static_cast<uint32_t>(sub + NW * k) * 512u);
+                if (k + 1 < nmine && ((okbits >> (k + 1)) & 1u)) n1 = ld_shared_u4(base + static_cast<uint32_t>(sub + NW * (k + 1)) * 512u);
 #pragma unroll 1
                 for (; k + 1 < nmine; k += 2) {
                     const uint32_t ad0 = base + static_cast<uint32_t>(sub + NW * k) * 512u;
                     const uint32_t ad1 = ad0 + NW * 512u;
                     const bool ok1 = (okbits >> (k + 1)) & 1u;        // only the last group can be partial
-                    uint4 u0 = ld_shared_u4(ad0), u1 = make_uint4(0u, 0u, 0u, 0u);
-                    if (ok1) u1 = ld_shared_u4(ad1);
+                    const uint4 u0 = n0, u1 = n1;
+                    if ((okbits >> (k + 2)) & 1u) n0 = ld_shared_u4(ad0 + 2 * NW * 512u);      // okbits is 0 beyond nmine
+                    if ((okbits >> (k + 3)) & 1u) n1 = ld_shared_u4(ad1 + 2 * NW * 512u);
                     uint4 o0 = norm_mish8<kIsNewtonPairs>(u0, a, b), o1 = norm_mish8<kIsNewtonPairs>(u1, a, b);
                     const bool in0 = (inbits >> k) & 1u, in1 = (inbits >> (k + 1)) & 1u;
                     if (!in0) o0 = make_uint4(0u, 0u, 0u, 0u);          // halo positions stay exactly zero
@@ -440,7 +456,7 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
                 }
                 if (k < nmine && ((okbits >> k) & 1u)) {
                     const uint32_t ad0 = base + static_cast<uint32_t>(sub + NW * k) * 512u;
-                    uint4 o0 = norm_mish8<kIsNewtonPairs>(ld_shared_u4(ad0), a, b);
+                    uint4 o0 = norm_mish8<kIsNewtonPairs>(n0, a, b);
                     if (!((inbits >> k) & 1u)) o0 = make_uint4(0u, 0u, 0u, 0u);
                     st_shared_u4(ad0, o0);
                 }

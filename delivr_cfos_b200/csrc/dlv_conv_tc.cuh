@@ -224,23 +224,30 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvArgs
                         run_s[h] += static_cast<double>(warp_transpose_sum32(v));
                         run_q[h] += static_cast<double>(warp_transpose_sum32(sq));
                     } else {
-                        // transposed conv k2 s2: the 8 sub-positions (a,b,c) of this input voxel are the 8 column
-                        // blocks of ONE N = 256 accumulator (h = a*4 + b*2 + c), 32 couts each
+                        // transposed conv k2 s2: the N = 256 accumulator of this input voxel holds all 8 output
+                        // sub-positions; block h = (a, b, jp) carries chunks j = 2 jp, 2 jp + 1, each as the x-even
+                        // and x-odd output voxel side by side (pack_deconv) -> 2 x 16 B contiguous stores per chunk
                         if (valid) {
-                            const int abc = h;
-                            const int oz = 2 * (zp - 1) + (abc >> 2) + 1;
-                            const int oy = 2 * (yp - 1) + ((abc >> 1) & 1) + 1;
-                            const int ox = 2 * (xp - 1) + (abc & 1) + 1;
+                            const int a = h >> 2, b = (h >> 1) & 1, jp = h & 1;
+                            const int oz = 2 * (zp - 1) + a + 1;
+                            const int oy = 2 * (yp - 1) + b + 1;
+                            const int ox = 2 * (xp - 1) + 1;
                             const int64_t Po = static_cast<int64_t>(win) * p.oVp + (static_cast<int64_t>(oz) * p.oYp + oy) * p.oXp + ox;
-                            __nv_bfloat16* o = p.out + (static_cast<int64_t>(nb * 4) * p.outS + p.out_guard + Po) * 8;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                uint4 u;
-                                u.x = pack_bf16x2(v[8 * j + 0] + bsr[8 * j + 0], v[8 * j + 1] + bsr[8 * j + 1]);
-                                u.y = pack_bf16x2(v[8 * j + 2] + bsr[8 * j + 2], v[8 * j + 3] + bsr[8 * j + 3]);
-                                u.z = pack_bf16x2(v[8 * j + 4] + bsr[8 * j + 4], v[8 * j + 5] + bsr[8 * j + 5]);
-                                u.w = pack_bf16x2(v[8 * j + 6] + bsr[8 * j + 6], v[8 * j + 7] + bsr[8 * j + 7]);
-                                *reinterpret_cast<uint4*>(o + static_cast<int64_t>(j) * p.outS * 8) = u;
+                            for (int jl = 0; jl < 2; ++jl) {
+                                const int j = jp * 2 + jl;
+                                __nv_bfloat16* o = p.out + (static_cast<int64_t>(nb * 4 + j) * p.outS + p.out_guard + Po) * 8;
+#pragma unroll
+                                for (int c = 0; c < 2; ++c) {
+                                    const float* vv = v + (jl * 2 + c) * 8;
+                                    const float* bb = bsr + j * 8;
+                                    uint4 u;
+                                    u.x = pack_bf16x2(vv[0] + bb[0], vv[1] + bb[1]);
+                                    u.y = pack_bf16x2(vv[2] + bb[2], vv[3] + bb[3]);
+                                    u.z = pack_bf16x2(vv[4] + bb[4], vv[5] + bb[5]);
+                                    u.w = pack_bf16x2(vv[6] + bb[6], vv[7] + bb[7]);
+                                    *reinterpret_cast<uint4*>(o + c * 8) = u;
+                                }
                             }
                         }
                     }

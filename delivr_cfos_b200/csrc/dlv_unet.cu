@@ -29,8 +29,10 @@ __device__ __forceinline__ int64_t pos_of(const LevelDev& L, int win, int z, int
 
 // uint16 window gather (sliding_window_inferer.py:181-195,207, flips :218-219) fused with the operand format of
 // the first convolution.  A uint16 v is split as v = hi + lo, hi = v & 0xFF00, lo = v & 0xFF - both exact in
-// bf16 - and the first-layer weights as W = Wh + Wl (two bf16), channels = {hi, lo, hi, lo} against
-// {Wh, Wh, Wl, Wl}: the tensor-core product reproduces the fp32 product v*W to ~2^-16 relative.
+// bf16 - and the first-layer weights as W = Wh + Wl (two bf16): {hi, lo, hi, lo} against {Wh, Wh, Wl, Wl}
+// reproduces the fp32 product v*W to ~2^-16 relative on the tensor cores.  The three kx neighbours of a voxel are
+// folded into the K = 16 slot as well (channel = kx*4 + term; zero outside the window = the conv's zero padding),
+// so the first layer needs only its centre-kx taps.
 __global__ void gather_windows_kernel(const uint16_t* __restrict__ slab, int64_t slabY, int64_t slabX,
                                       const WindowDesc* __restrict__ wd, LevelDev L, __nv_bfloat16* __restrict__ in0) {
     const int win = blockIdx.y;
@@ -40,11 +42,18 @@ __global__ void gather_windows_kernel(const uint16_t* __restrict__ slab, int64_t
     const WindowDesc w = wd[win];
     const int zs = (w.flip == 1) ? L.Z - 1 - z : z;
     const int ys = (w.flip == 2) ? L.Y - 1 - y : y;
-    const int xs = (w.flip == 3) ? L.X - 1 - x : x;
-    const uint32_t v = slab[(static_cast<int64_t>(w.oz + zs) * slabY + (w.oy + ys)) * slabX + (w.ox + xs)];
-    const uint32_t hi = pack_bf16x2(static_cast<float>(v & 0xFF00u), static_cast<float>(v & 0xFFu));
-    uint4 u = make_uint4(hi, hi, 0u, 0u);
-    *reinterpret_cast<uint4*>(in0 + pos_of(L, win, z, y, x) * 8) = u;
+    const uint16_t* row = slab + (static_cast<int64_t>(w.oz + zs) * slabY + (w.oy + ys)) * slabX + w.ox;
+    uint32_t t[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int xw = x + k - 1;
+        uint32_t v = 0u;
+        if (xw >= 0 && xw < L.X) v = row[(w.flip == 3) ? L.X - 1 - xw : xw];
+        t[k] = pack_bf16x2(static_cast<float>(v & 0xFF00u), static_cast<float>(v & 0xFFu));
+    }
+    const int64_t P = pos_of(L, win, z, y, x);
+    *reinterpret_cast<uint4*>(in0 + P * 8) = make_uint4(t[0], t[0], t[1], t[1]);
+    *reinterpret_cast<uint4*>(in0 + (L.S + P) * 8) = make_uint4(t[2], t[2], 0u, 0u);
 }
 
 // per-window input maximum > 0 test (skip rule, sliding_window_inferer.py:198; applied per window)
@@ -293,10 +302,11 @@ static int pack_conv(Ctx* ctx, ConvLayer& L, const float* W, bool first) {
                             const int ci = kb * 16 + kc * 8 + e, co = nb * L.nblk + n;
                             float v = 0.f;
                             if (first) {
-                                if (ci < 4) {
-                                    const float w = W[static_cast<size_t>(co) * 27 + tap];
+                                // kx folded into K (gather_windows_kernel): only the centre-kx taps carry weights
+                                if (ci < 12 && tap % 3 == 1) {
+                                    const float w = W[static_cast<size_t>(co) * 27 + (tap - 1) + ci / 4];
                                     const float wh = __bfloat162float(to_bf16(w));
-                                    v = (ci < 2) ? wh : (w - wh);
+                                    v = (ci % 4 < 2) ? wh : (w - wh);
                                 }
                             } else if (ci < L.cin) {
                                 v = W[(static_cast<size_t>(co) * L.cin + ci) * 27 + tap];
@@ -309,32 +319,35 @@ static int pack_conv(Ctx* ctx, ConvLayer& L, const float* W, bool first) {
 // Cout = 32 layers, input-stationary kernel: W[32][cin][3][3][3] -> [KB][9 (ky,kx)][2][96][8]; the 96 B rows are the
 // three kz blocks in the order of the output planes they feed (z-1: kz = 2, z: kz = 1, z+1: kz = 0).
 static int pack_conv_is(Ctx* ctx, ConvLayer& L, const float* W, bool first) {
-    std::vector<bf16> pk(static_cast<size_t>(L.KB) * 9 * 2 * 96 * 8, to_bf16(0.f));
+    const int ntap = first ? 3 : 9;        // first layer: kx folded into K, taps = ky only
+    std::vector<bf16> pk(static_cast<size_t>(L.KB) * ntap * 2 * 96 * 8, to_bf16(0.f));
     for (int kb = 0; kb < L.KB; ++kb)
-        for (int tap = 0; tap < 9; ++tap)
+        for (int tap = 0; tap < ntap; ++tap)
             for (int kc = 0; kc < 2; ++kc)
                 for (int row = 0; row < 96; ++row)
                     for (int e = 0; e < 8; ++e) {
                         const int kz = 2 - row / 32, co = row % 32, ci = kb * 16 + kc * 8 + e;
-                        const int t27 = kz * 9 + tap;
                         float v = 0.f;
                         if (first) {
-                            if (ci < 4) {
-                                const float w = W[static_cast<size_t>(co) * 27 + t27];
+                            if (ci < 12) {
+                                const float w = W[static_cast<size_t>(co) * 27 + kz * 9 + tap * 3 + ci / 4];
                                 const float wh = __bfloat162float(to_bf16(w));
-                                v = (ci < 2) ? wh : (w - wh);
+                                v = (ci % 4 < 2) ? wh : (w - wh);
                             }
                         } else if (ci < L.cin) {
-                            v = W[(static_cast<size_t>(co) * L.cin + ci) * 27 + t27];
+                            v = W[(static_cast<size_t>(co) * L.cin + ci) * 27 + kz * 9 + tap];
                         }
-                        pk[((((static_cast<size_t>(kb) * 9 + tap) * 2 + kc) * 96 + row) * 8) + e] = to_bf16(v);
+                        pk[((((static_cast<size_t>(kb) * ntap + tap) * 2 + kc) * 96 + row) * 8) + e] = to_bf16(v);
                     }
     return upload(ctx, pk.data(), pk.size() * sizeof(bf16), reinterpret_cast<void**>(&L.w_is));
 }
 
 static int pack_deconv(Ctx* ctx, ConvLayer& L, const float* W) {
-    // W[cin][cout][2][2][2] (torch ConvTranspose3d) -> [KB][NB = cout/32][1][2][256 = (abc, 32 couts)][8]:
-    // one N = 256 MMA produces all 8 sub-positions of 32 output channels for 128 input voxels
+    // W[cin][cout][2][2][2] (torch ConvTranspose3d) -> [KB][NB = cout/32][1][2][256][8]: one N = 256 MMA produces
+    // all 8 sub-positions of 32 output channels for 128 input voxels.  Column order inside the 256:
+    // n = ((a*2 + b)*2 + jp)*32 + (jl*2 + c)*8 + e  with output sub-position (a, b, c), output channel
+    // co = nb*32 + (jp*2 + jl)*8 + e: a 32-column accumulator block holds, for two 8-channel chunks, the x-even and
+    // the x-odd output voxel side by side, so the epilogue stores 32 contiguous bytes per chunk (full sectors).
     L.ntaps = 1;
     L.cin_pad = L.cin;
     L.KB = L.cin / 16;
@@ -347,7 +360,10 @@ static int pack_deconv(Ctx* ctx, ConvLayer& L, const float* W) {
                 for (int n = 0; n < L.nblk; ++n)
                     for (int e = 0; e < 8; ++e) {
                         const int ci = kb * 16 + kc * 8 + e;
-                        const int abc = n / 32, co = nb * 32 + (n % 32);
+                        const int blk = n / 32, r = n % 32;
+                        const int a = blk >> 2, b = (blk >> 1) & 1, jp = blk & 1;
+                        const int jl = r >> 4, c = (r >> 3) & 1, ce = r & 7;
+                        const int abc = a * 4 + b * 2 + c, co = nb * 32 + (jp * 2 + jl) * 8 + ce;
                         const float v = W[(static_cast<size_t>(ci) * L.cout + co) * 8 + abc];
                         pk[(((static_cast<size_t>(kb) * L.NB + nb) * 2 + kc) * L.nblk + n) * 8 + e] = to_bf16(v);
                     }
@@ -514,8 +530,15 @@ static int run_conv(Ctx* ctx, const ConvLayer& Ly, const Level& L, int nwin, con
 
 
 // ------------------------------------------------------------------- input-stationary fused conv launcher (Cout = 32)
+static const int kIsStatGroup = 8;      // output planes per InstanceNorm partial record of the fused conv
+// partial records per window of a level: (Z / G) groups x at most ceil(PL / 256) columns (T = 2)
+static int is_max_parts(const Level& L) {
+    const int G = (L.Z % kIsStatGroup == 0) ? kIsStatGroup : L.Z;
+    return (L.Z / G) * ((L.YpXp + 255) / 256);
+}
+
 struct IsPlan {
-    int T, S, RL, H, NC, NZS, Zs, nstages, nparts;
+    int T, S, RL, H, NC, NZS, Zs, nstages, nparts, G;
     uint32_t stage_bytes, w_bytes, smem;
 };
 
@@ -523,12 +546,12 @@ static bool plan_conv_is(const Ctx* ctx, const ConvLayer& Ly, const Level& L, in
     if (Ly.cout != 32 || Ly.ntaps != 27 || !Ly.w_is) return false;
     const int PL = L.YpXp;
     P.H = L.Xp + 1;
-    P.w_bytes = static_cast<uint32_t>(Ly.KB) * 9 * 3072;
+    P.w_bytes = static_cast<uint32_t>(Ly.KB) * (Ly.cin == 1 ? 3 : 9) * 3072;
     const int nchunks = 2 * Ly.KB;
     auto fits = [&](int T, int& nst, int& RL, uint32_t& sb) {
         RL = ((128 * T + 2 * P.H + 7) / 8) * 8;
         sb = static_cast<uint32_t>(nchunks) * RL * 16;
-        const uint32_t fixed = P.w_bytes + kIsXformWarps * 32 * 4 + 256 * 8 + 256;
+        const uint32_t fixed = P.w_bytes + kIsXformWarps * 32 * 4 + 512 * 8 + 256;
         nst = 0;
         for (int n = kIsMaxStages; n >= 2; --n)
             if (fixed + static_cast<uint64_t>(n) * sb <= kSmemLimit) { nst = n; break; }
@@ -551,12 +574,14 @@ static bool plan_conv_is(const Ctx* ctx, const ConvLayer& Ly, const Level& L, in
     P.T = bestT; P.S = 16 / bestT;
     fits(P.T, P.nstages, P.RL, P.stage_bytes);
     P.NC = (PL + 128 * P.T - 1) / (128 * P.T);
-    // z segmentation: balance the persistent grid (each extra segment re-stages ~2 input planes)
+    // z segmentation: balance the persistent grid (each extra segment re-stages ~2 input planes).  Segments are
+    // whole statistics groups of G planes, so the InstanceNorm partial records are the same for every choice.
+    P.G = (L.Z % kIsStatGroup == 0) ? kIsStatGroup : L.Z;
     int bestN = 1; double bestc = 1e30;
     for (int n = 1; n <= 6 && n <= L.Z; ++n) {
         const int Zs = (L.Z + n - 1) / n;
         const int nseg = (L.Z + Zs - 1) / Zs;
-        if (nseg != n) continue;
+        if (nseg != n || Zs % P.G != 0) continue;
         const int64_t items = static_cast<int64_t>(nwin) * P.NC * n;
         const int64_t waves = (items + ctx->num_sms - 1) / ctx->num_sms;
         const double c = static_cast<double>(waves) * (Zs + (n > 1 ? 1.5 : 0.0));
@@ -564,16 +589,15 @@ static bool plan_conv_is(const Ctx* ctx, const ConvLayer& Ly, const Level& L, in
     }
     P.NZS = bestN;
     P.Zs = (L.Z + bestN - 1) / bestN;
-    P.nparts = P.NZS * P.NC;
+    P.nparts = (L.Z / P.G) * P.NC;
     P.smem = kSmemLimit;        // always the full opt-in size: one CTA per SM owns all 512 TMEM columns
     return true;
 }
 
-static const int kIsMaxParts = 6 * 64;     // upper bound on NZS * NC the partial-sum scratch is sized for
 
-template <int T, int S>
+template <int T, int S, bool FOLD>
 static int launch_conv_is_t(Ctx* ctx, const IsArgs& a, int grid, uint32_t smem) {
-    auto k = conv_is_kernel<T, S>;
+    auto k = conv_is_kernel<T, S, FOLD>;
     static bool attr_set = false;
     if (!attr_set) {
         DLV_CUDA_OK(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
@@ -590,7 +614,7 @@ static int launch_conv_is_t(Ctx* ctx, const IsArgs& a, int grid, uint32_t smem) 
 static int run_conv_is(Ctx* ctx, const ConvLayer& Ly, const Level& L, int nwin, const bf16* in0, int nch0, const bf16* in1,
                        const ConvLayer* prod, const double* prod_stats, bf16* out, double* part, double* stats) {
     IsPlan P;
-    if (!plan_conv_is(ctx, Ly, L, nwin, P) || P.nparts > kIsMaxParts) {
+    if (!plan_conv_is(ctx, Ly, L, nwin, P) || P.nparts > is_max_parts(L)) {
         set_error(ctx, "conv %s: level %dx%dx%d does not fit the input-stationary kernel", Ly.name.c_str(), L.Z, L.Y, L.X);
         return DLV_ERR_UNSUPPORTED;
     }
@@ -605,24 +629,19 @@ static int run_conv_is(Ctx* ctx, const ConvLayer& Ly, const Level& L, int nwin, 
     a.w = Ly.w_is; a.out = out; a.outS = L.S; a.out_guard = L.guard;
     a.part = part; a.nparts = P.nparts;
     a.Z = L.Z; a.Y = L.Y; a.X = L.X; a.Xp = L.Xp; a.PL = L.YpXp; a.Vp = L.Vp;
-    a.KB = Ly.KB; a.NC = P.NC; a.NZS = P.NZS; a.Zs = P.Zs;
+    a.KB = Ly.KB; a.NC = P.NC; a.NZS = P.NZS; a.Zs = P.Zs; a.G = P.G;
     a.nitems = nwin * P.NC * P.NZS;
     a.RL = P.RL; a.H = P.H; a.nstages = P.nstages;
     a.stage_bytes = P.stage_bytes; a.w_bytes = P.w_bytes;
     a.inv_count = 1.0 / (static_cast<double>(L.Z) * L.Y * L.X);
-    for (int kb = 0; kb < Ly.KB; ++kb)
-        for (int ky = 0; ky < 3; ++ky)
-            for (int kx = 0; kx < 3; ++kx) {
-                const int i = kb * 9 + ky * 3 + kx;
-                a.tap_a[i] = static_cast<uint32_t>(kb * 2 * P.RL + P.H + (ky - 1) * L.Xp + (kx - 1));
-                a.tap_b[i] = static_cast<uint32_t>(i * 192);
-            }
     const int grid = std::min(ctx->num_sms, a.nitems);
     static const bool dbg = getenv("DLV_IS_DEBUG") != nullptr;
     if (const char* e = getenv("DLV_IS_MODE")) a.dbg_mode = atoi(e);
     if (dbg) { cudaMalloc(reinterpret_cast<void**>(&a.dbg), grid * 64); cudaMemset(a.dbg, 0, grid * 64); }
     if (ctx->time_convs) cudaEventRecord(ctx->ev0, ctx->stream);
-    int rc = (P.T == 4) ? launch_conv_is_t<4, 4>(ctx, a, grid, P.smem) : launch_conv_is_t<2, 8>(ctx, a, grid, P.smem);
+    int rc;
+    if (Ly.cin == 1) rc = (P.T == 4) ? launch_conv_is_t<4, 4, true>(ctx, a, grid, P.smem) : launch_conv_is_t<2, 8, true>(ctx, a, grid, P.smem);
+    else rc = (P.T == 4) ? launch_conv_is_t<4, 4, false>(ctx, a, grid, P.smem) : launch_conv_is_t<2, 8, false>(ctx, a, grid, P.smem);
     if (ctx->time_convs && rc == 0) {
         cudaEventRecord(ctx->ev1, ctx->stream);
         cudaEventSynchronize(ctx->ev1);
@@ -661,7 +680,7 @@ struct Engine {
     bf16 *p4 = nullptr, *d4a = nullptr, *x4 = nullptr;
     bf16* raw[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // pre-norm conv outputs, one per level
     double* stats = nullptr;     // [18 layers][batch][256][2]
-    double* part = nullptr;      // [batch][kIsMaxParts][64] partial sums of the layer in flight (fused path)
+    double* part = nullptr;      // [batch][is_max_parts][64] partial sums of the layer in flight (fused path)
     std::vector<void*> allocs;
 };
 static const int kStatsPerLayer = 256 * 2;
@@ -708,7 +727,7 @@ int engine_prepare(Ctx* ctx, const int32_t roi[3], int batch) {
     DLV_CUDA_OK(ctx, cudaMalloc(&p, sizeof(double) * 18 * batch * kStatsPerLayer));
     e->allocs.push_back(p);
     e->stats = static_cast<double*>(p);
-    DLV_CUDA_OK(ctx, cudaMalloc(&p, sizeof(double) * batch * kIsMaxParts * 64));
+    DLV_CUDA_OK(ctx, cudaMalloc(&p, sizeof(double) * batch * std::max(is_max_parts(e->L[0]), is_max_parts(e->L[1])) * 64));
     e->allocs.push_back(p);
     e->part = static_cast<double*>(p);
     DLV_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -881,7 +900,7 @@ int op_conv3d(Ctx* ctx, const char* name, const float* x, int n, int D, int H, i
     double* part = nullptr;
     if (ctx->use_fused && plan_conv_is(ctx, Ly, L, n, probe)) {
         // Cout = 32 layers: the input-stationary kernel (plain, already-normalised input)
-        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&part), sizeof(double) * n * kIsMaxParts * 64);
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&part), sizeof(double) * n * is_max_parts(L) * 64);
         if (e != cudaSuccess) { set_error(ctx, "dlv_op_conv3d: %s", cudaGetErrorString(e)); cudaFree(in); cudaFree(raw); return DLV_ERR_CUDA; }
         rc = run_conv_is(ctx, Ly, L, n, in, Ly.cin_pad / 8, nullptr, nullptr, nullptr, raw, part, stats);
     } else {
