@@ -31,6 +31,7 @@ import torch  # noqa: E402
 MAC_PER_PATCH_VOXEL = 142552          # SURVEY.md section 2.2 (all conv / deconv / 1x1 layers)
 ROI = (96, 96, 64)
 OVERLAP = 0.5
+CFG3 = dict(shape=(1000, 2048, 2048), seed=1003, name="cfg3 synthetic 1000x2048x2048 binary mask (blob field, 26-connected CC + table)")
 WORKLOADS = {
     "cfg2": dict(shape=(256, 2048, 2048), seed=1002, name="cfg2 synthetic 256x2048x2048 uint16 slab"),
     "cfg1": dict(shape=(64, 512, 512), seed=1001, name="cfg1 synthetic 64x512x512 uint16 volume"),
@@ -45,6 +46,19 @@ def peaks():
         d = json.load(open(p))
         return float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1424.2))), float(d.get("hbm_gbs", 6550.4)), "measured"
     return 1400.0, 6650.0, "fallback"
+
+
+def conv_traffic(workload, windows_active):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of all convolution launches of one step, from the
+    committed ncu capture of one full 32-window batch of this workload (profiles/conv_traffic.json), scaled by the
+    step's active-window count.  None when no capture exists for the workload."""
+    p = os.path.join(ROOT, "profiles", "conv_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p)).get(workload)
+    if not d:
+        return None, None
+    return d["dram_bytes_per_window"] * windows_active, d["source"]
 
 
 def state_dict():
@@ -141,12 +155,16 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + ["cfg3"])
+    ap.add_argument("--window-batch", type=int, default=int(os.environ.get("DLV_WINDOW_BATCH", 0)),
+                    help="windows per U-Net launch sequence (0: library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.workload == "cfg3":
+        return run_cfg3(args, rank, local_rank, world)
     if args.impl == "reference":
         return run_reference(args, rank, world)
     if world > 1 or args.gpus > 1:
@@ -170,9 +188,10 @@ def main():
     stream = torch.cuda.ExternalStream(ctx._L.dlv_stream(ctx._h), device=dev)
     from delivr_cfos_b200.inference.inference import erosion_block_planes
     ebp = erosion_block_planes(shape)
+    wb = args.window_batch
 
     def step():
-        st = ctx.segment(vol, shape_pad, shape, ROI, binaries, overlap=OVERLAP, erosion_block_planes=ebp)
+        st = ctx.segment(vol, shape_pad, shape, ROI, binaries, overlap=OVERLAP, erosion_block_planes=ebp, window_batch=wb)
         tb = ctx.ccl(binaries, shape, labels_out=labels)
         return st, tb
 
@@ -199,7 +218,7 @@ def main():
     torch.cuda.synchronize()
 
     def step_e2e():
-        ctx.segment(hvol, shape_pad, shape, ROI, hbin, overlap=OVERLAP, erosion_block_planes=ebp)
+        ctx.segment(hvol, shape_pad, shape, ROI, hbin, overlap=OVERLAP, erosion_block_planes=ebp, window_batch=wb)
         return ctx.ccl(hbin, shape)
 
     step_e2e()
@@ -215,7 +234,7 @@ def main():
 
     # ---- roofline of the dominant kernel (tcgen05 convolutions): one extra step with per-launch event timing
     ctx.set_conv_timing(True)
-    st_t = ctx.segment(vol, shape_pad, shape, ROI, binaries, overlap=OVERLAP, erosion_block_planes=ebp)
+    st_t = ctx.segment(vol, shape_pad, shape, ROI, binaries, overlap=OVERLAP, erosion_block_planes=ebp, window_batch=wb)
     ctx.set_conv_timing(False)
     conv_ms = st_t["ms_conv"]
     patch_vox = st_t["windows_active"] * ROI[0] * ROI[1] * ROI[2] * st_t["passes"]
@@ -223,6 +242,7 @@ def main():
     tf_peak, hbm_peak, peak_kind = peaks()
     achieved = flop / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     ccl_ms, _ = ctx.ccl_last_timing()
+    traffic, traffic_src = conv_traffic(args.workload, st_t["windows_active"])
 
     out = {
         "metric": "Gvoxels/s seg+CC", "value": value, "unit": "Gvoxels/s", "n_gpus": 1, "steps": args.steps,
@@ -230,13 +250,13 @@ def main():
         "dtype": "bf16", "data": f"synthetic; {wdesc}",
         "config": {"workload": wl["name"], "window": list(ROI), "overlap": OVERLAP, "tta": False, "blend": "constant",
                    "windows_total": st["windows_total"], "windows_active": st["windows_active"],
-                   "components": tb["n"], "l2": "inputs larger than L2 (volume + accumulator >> 126 MB)"},
+                   "components": tb["n"], "window_batch": wb or 32, "l2": "inputs larger than L2 (volume + accumulator >> 126 MB)"},
         "gpu_launches": launches,
         "clocks": clocks,
         "e2e": {"value": nvox / (ms_e2e * 1e-3) / 1e9, "unit": "Gvoxels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (all conv/deconv launches of one step)",
                      "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-                     "traffic": None, "peak_kind": f"bf16_tflops_sustained, {peak_kind}",
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_kind": f"bf16_tflops_sustained, {peak_kind}",
                      "conv_ms_per_step": conv_ms, "unet_ms_per_step": st["ms_unet"], "finalise_ms_per_step": st["ms_finalise"],
                      "ccl_ms_per_step": ccl_ms, "ccl_gbs_algorithmic": 9.0 * nvox / (ccl_ms * 1e-3) / 1e9 if ccl_ms else None,
                      "ccl_frac_of_hbm": (9.0 * nvox / (ccl_ms * 1e-3) / 1e9 / hbm_peak) if ccl_ms else None},
@@ -253,6 +273,74 @@ def main():
         out["cpu_baseline"] = {"value": sv.size / t / 1e9, "unit": "Gvoxels/s", "cores": threads, "kind": "port",
                                "sample": f"{CPU_SAMPLE[0]}x{CPU_SAMPLE[1]}x{CPU_SAMPLE[2]} volume (6 windows, all active), 1 pass + binarise + CC, {t:.1f} s"}
     print(json.dumps(out))
+
+
+def run_cfg3(args, rank, local_rank, world):
+    """--workload cfg3: connected components + table alone on the 1000x2048x2048 synthetic mask (BASELINE.json configs[2]).
+    HBM-bound; algorithmic bytes = 9 B/voxel (1 mask read + 4 label write + 4 label read)."""
+    if rank != 0:
+        return
+    shape = CFG3["shape"]
+    nvox = int(np.prod(shape))
+    if args.impl == "reference":
+        from oracle import pipeline_ref as P
+        sub = (64, 1024, 1024)
+        m = P.synth_mask(sub, CFG3["seed"])
+        ts = []
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            P.blob_table(m)
+            ts.append(time.perf_counter() - t0)
+        t = sum(ts[args.warmup:]) / args.steps
+        v = m.size / t / 1e9
+        print(json.dumps({"impl": "reference", "metric": "Gvoxels/s CC+table", "value": v, "unit": "Gvoxels/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                          "config": {"workload": CFG3["name"]},
+                          "cpu_baseline": {"value": v, "unit": "Gvoxels/s", "cores": 1, "kind": "port",
+                                           "sample": f"{sub[0]}x{sub[1]}x{sub[2]} crop of the mask, C oracle (cc3d stand-in), 1 thread"},
+                          "e2e": {"value": v, "unit": "Gvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    from delivr_cfos_b200 import Context
+    from delivr_cfos_b200.synth import synth_mask_cuda
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = Context(local_rank)
+    mask = synth_mask_cuda(shape, CFG3["seed"], device=dev)
+    labels = torch.empty(shape, dtype=torch.int32, device=dev)
+    stream = torch.cuda.ExternalStream(ctx._L.dlv_stream(ctx._h), device=dev)
+    torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        tb = ctx.ccl(mask, shape, labels_out=labels)
+    sampler = ClockSampler(local_rank)
+    l0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    kms = 0.0
+    for _ in range(args.steps):
+        tb = ctx.ccl(mask, shape, labels_out=labels)
+        kms += ctx.ccl_last_timing()[0]
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    kms /= args.steps
+    launches = ctx.launches - l0
+    clocks = sampler.stop()
+    _, hbm_peak, peak_kind = peaks()
+    gbs = 9.0 * nvox / (kms * 1e-3) / 1e9
+    fg = int(tb["voxel_counts"][1:].sum())
+    print(json.dumps({
+        "metric": "Gvoxels/s CC+table", "value": nvox / (ms * 1e-3) / 1e9, "unit": "Gvoxels/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": CFG3["name"], "components": tb["n"], "foreground_fraction": fg / nvox,
+                   "l2": "inputs larger than L2 (4.2 GB mask, 16.8 GB labels)"},
+        "gpu_launches": launches, "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "ccl_init/merge/compress/scan/relabel_stats (all CC kernels of one step)",
+                     "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
+                     "peak_kind": f"hbm_gbs copy bandwidth, {peak_kind}", "kernels_ms_per_step": kms,
+                     "algorithmic_bytes_per_voxel": 9},
+    }))
 
 
 if __name__ == "__main__":

@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdelivr_b200.so")
+# DLV_LIB selects an experiment build of the same sources (csrc/Makefile VARIANT=...); default: the product library
+LIB_PATH = os.environ.get("DLV_LIB") or os.path.join(_HERE, "libdelivr_b200.so")
 
 c_i32, c_i64, c_f32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
 

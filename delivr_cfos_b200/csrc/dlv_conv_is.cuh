@@ -24,7 +24,10 @@
 
 namespace dlv {
 
-constexpr int kIsXformWarps = 8;         // two warps per 8-channel input chunk
+#ifndef DLV_IS_XFORM_WARPS
+#define DLV_IS_XFORM_WARPS 8
+#endif
+constexpr int kIsXformWarps = DLV_IS_XFORM_WARPS;   // warps per step of the transform role (a multiple of 4: NW per 8-channel chunk)
 constexpr int kIsThreads = (6 + kIsXformWarps) * 32;   // warp 0 producer, 1 MMA, 2-5 epilogue, 6.. transform
 constexpr int kIsMaxStages = 4;
 #ifndef DLV_IS_NEWTON_PAIRS
@@ -58,13 +61,23 @@ struct IsArgs {
     int dbg_mode;               // timing experiments (results invalid): 1 skip TMEM loads, 2 skip TMEM zeroing, 4 skip the transform's smem traffic, 8 skip output stores
 };
 
-// deterministic reduction of the per-item partial sums: stats[win][c][0..1] = sum over parts (fixed order)
-__global__ void is_reduce_stats_kernel(const double* __restrict__ part, int nparts, double* __restrict__ stats) {
-    const int win = blockIdx.x, t = threadIdx.x;       // 64 threads: (c, k)
+// deterministic reduction of the per-item partial sums: stats[win][c][0..1] = sum over parts.  kIsReduceLanes strided
+// sub-sums per value (independent load chains), combined in a fixed order: the result depends on nparts only.
+constexpr int kIsReduceLanes = 8;
+__global__ void __launch_bounds__(64 * kIsReduceLanes) is_reduce_stats_kernel(const double* __restrict__ part, int nparts,
+                                                                              double* __restrict__ stats) {
+    __shared__ double sub[kIsReduceLanes][64];
+    const int win = blockIdx.x, t = threadIdx.x & 63, g = threadIdx.x >> 6;       // t = (c, k)
     const double* p = part + static_cast<int64_t>(win) * nparts * 64 + t;
     double s = 0.0;
-    for (int i = 0; i < nparts; ++i) s += p[static_cast<int64_t>(i) * 64];
-    stats[static_cast<int64_t>(win) * 64 + t] = s;
+    for (int i = g; i < nparts; i += kIsReduceLanes) s += p[static_cast<int64_t>(i) * 64];
+    sub[g][t] = s;
+    __syncthreads();
+    if (g == 0) {
+#pragma unroll
+        for (int k = 1; k < kIsReduceLanes; ++k) s += sub[k][t];
+        stats[static_cast<int64_t>(win) * 64 + t] = s;
+    }
 }
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

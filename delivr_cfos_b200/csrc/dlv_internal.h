@@ -95,7 +95,8 @@ inline void dfree(Ctx* ctx, void* p) { if (p) cudaFreeAsync(p, ctx->stream); }
 // dlv_unet.cu
 struct WindowDesc {
     int32_t oz, oy, ox;   // window origin inside the device-resident slab
-    int32_t flip;         // 0 none, 1 flip z, 2 flip y, 3 flip x (reference flip_dim 2 / 3 / 4)
+    int32_t flip;         // bits 0-7: 0 none, 1 flip z, 2 flip y, 3 flip x (reference flip_dim 2 / 3 / 4);
+                          // bits 8-15: repeat - 1 (the window's logits are blended `repeat` times)
 };
 int net_load(Ctx* ctx, int n, const char* const* names, const float* const* data, const int64_t* numel);
 void net_free(Ctx* ctx);

@@ -209,8 +209,11 @@ int seg_average(Ctx* ctx, int32_t* acc, int64_t nplanes, int64_t gz0, const int6
 
 // The 13-pass test-time-augmentation plan of inference.py:265-279: one plain pass, then 4 x {plain, flip z, flip y}
 // (the reference adds unseeded N(0, U(0,1e-3)) noise to raw intensities >= 1 in the 12 extra passes; that is below
-// the resolution of the arithmetic and not reproducible, so the passes are evaluated noise-free).
-static const int kTtaFlips[13] = {0, 0, 1, 2, 0, 1, 2, 0, 1, 2, 0, 1, 2};
+// the resolution of the arithmetic and not reproducible, so the passes are evaluated noise-free).  Noise-free, the 13
+// passes are 5 x plain + 4 x flip z + 4 x flip y; every pass is deterministic and the blend is an integer sum, so
+// each distinct pass is evaluated once and added `repeat` times - bit-identical to running all 13 (tested).
+static const int kTtaFlips[3] = {0, 1, 2};
+static const int kTtaRepeat[3] = {5, 4, 4};
 
 int segment_run(Ctx* ctx, const void* volume_any, const dlv_seg_params* P, void* binaries_any, void* avg_any, void* sig_any,
                 dlv_seg_stats* st_out) {
@@ -285,11 +288,13 @@ int segment_run(Ctx* ctx, const void* volume_any, const dlv_seg_params* P, void*
     std::vector<WindowDesc> sched;
     int64_t nactive = 0;
     for (int64_t w = 0; w < nwin; ++w) nactive += active[w] != 0;
-    sched.reserve(nactive * passes);
-    for (int ps = 0; ps < passes; ++ps)
+    const int distinct = P->tta ? 3 : 1;
+    sched.reserve(nactive * distinct);
+    for (int ps = 0; ps < distinct; ++ps)
         for (int64_t w = 0; w < nwin; ++w)
             if (active[w])
-                sched.push_back(WindowDesc{origins[3 * w], origins[3 * w + 1], origins[3 * w + 2], P->tta ? kTtaFlips[ps] : single_flip});
+                sched.push_back(WindowDesc{origins[3 * w], origins[3 * w + 1], origins[3 * w + 2],
+                                           P->tta ? (kTtaFlips[ps] | ((kTtaRepeat[ps] - 1) << 8)) : single_flip});
 
     // ---- accumulate
     DevBuf d_acc;

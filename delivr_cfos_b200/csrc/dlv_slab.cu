@@ -100,9 +100,12 @@ int dlv_seg_accumulate(dlv_ctx* c, const uint16_t* slab_dev, int64_t SY, int64_t
     cudaSetDevice(ctx->device);
     std::vector<dlv::WindowDesc> sched(n > 0 ? n : 0);
     for (int i = 0; i < n; ++i) {
-        const int32_t f = windows_host[4 * i + 3];
-        if (f != 0 && (f < 2 || f > 4)) { dlv::set_error(ctx, "dlv_seg_accumulate: flip_dim must be 0, 2, 3 or 4"); return DLV_ERR_ARG; }
-        sched[i] = dlv::WindowDesc{windows_host[4 * i], windows_host[4 * i + 1], windows_host[4 * i + 2], f ? f - 1 : 0};
+        const int32_t f = windows_host[4 * i + 3] & 0xFF, rep1 = windows_host[4 * i + 3] >> 8;
+        if ((f != 0 && (f < 2 || f > 4)) || rep1 < 0 || rep1 > 255) {
+            dlv::set_error(ctx, "dlv_seg_accumulate: flip_dim must be 0, 2, 3 or 4 and repeat 1..256");
+            return DLV_ERR_ARG;
+        }
+        sched[i] = dlv::WindowDesc{windows_host[4 * i], windows_host[4 * i + 1], windows_host[4 * i + 2], (f ? f - 1 : 0) | (rep1 << 8)};
     }
     return dlv::seg_accumulate(ctx, slab_dev, SY, SX, sched, roi, window_batch, blend_mode, acc_dev);
 }

@@ -40,15 +40,16 @@ __global__ void gather_windows_kernel(const uint16_t* __restrict__ slab, int64_t
     if (idx >= L.Z * L.Y * L.X) return;
     const int x = idx % L.X, y = (idx / L.X) % L.Y, z = idx / (L.X * L.Y);
     const WindowDesc w = wd[win];
-    const int zs = (w.flip == 1) ? L.Z - 1 - z : z;
-    const int ys = (w.flip == 2) ? L.Y - 1 - y : y;
+    const int flip = w.flip & 0xFF;
+    const int zs = (flip == 1) ? L.Z - 1 - z : z;
+    const int ys = (flip == 2) ? L.Y - 1 - y : y;
     const uint16_t* row = slab + (static_cast<int64_t>(w.oz + zs) * slabY + (w.oy + ys)) * slabX + w.ox;
     uint32_t t[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const int xw = x + k - 1;
         uint32_t v = 0u;
-        if (xw >= 0 && xw < L.X) v = row[(w.flip == 3) ? L.X - 1 - xw : xw];
+        if (xw >= 0 && xw < L.X) v = row[(flip == 3) ? L.X - 1 - xw : xw];
         t[k] = pack_bf16x2(static_cast<float>(v & 0xFF00u), static_cast<float>(v & 0xFFu));
     }
     const int64_t P = pos_of(L, win, z, y, x);
@@ -219,14 +220,17 @@ __global__ void final_blend_kernel(const __nv_bfloat16* __restrict__ raw, LevelD
         return;
     }
     const WindowDesc w = wd[win];
-    const int zo = (w.flip == 1) ? L.Z - 1 - z : z;
-    const int yo = (w.flip == 2) ? L.Y - 1 - y : y;
-    const int xo = (w.flip == 3) ? L.X - 1 - x : x;
+    const int flip = w.flip & 0xFF, repeat = (w.flip >> 8) + 1;
+    const int zo = (flip == 1) ? L.Z - 1 - z : z;
+    const int yo = (flip == 2) ? L.Y - 1 - y : y;
+    const int xo = (flip == 3) ? L.X - 1 - x : x;
     const float wgt = wz ? wz[zo] * wy[yo] * wx[xo] : 1.f;
     // fixed-point accumulation (2^-12 logit units): integer adds are associative, so the blended sum is
-    // bit-identical for any window order, batch composition or slab partition across GPUs.
+    // bit-identical for any window order, batch composition or slab partition across GPUs.  `repeat` identical
+    // passes (test-time augmentation evaluates the same flip several times) are one pass added `repeat` times.
     const float v = fminf(fmaxf(wgt * logit, -kAccClamp), kAccClamp);
-    atomicAdd(acc + (static_cast<int64_t>(w.oz + zo) * slabY + (w.oy + yo)) * slabX + (w.ox + xo), __float2int_rn(v * kAccScale));
+    atomicAdd(acc + (static_cast<int64_t>(w.oz + zo) * slabY + (w.oy + yo)) * slabX + (w.ox + xo),
+              __float2int_rn(v * kAccScale) * repeat);
     (void)xo;
 }
 
@@ -661,7 +665,7 @@ static int run_conv_is(Ctx* ctx, const ConvLayer& Ly, const Level& L, int nwin, 
                 Ly.name.c_str(), nwin, P.T, P.NZS, P.nstages, Ly.KB, a.xform_chunks, t[0] / grid, t[0] / st, t[1] / st, t[2] / st, t[3] / st, t[5] / st, t[6] / st);
     }
     if (rc) return rc;
-    is_reduce_stats_kernel<<<nwin, 64, 0, ctx->stream>>>(part, P.nparts, stats);
+    is_reduce_stats_kernel<<<nwin, 64 * kIsReduceLanes, 0, ctx->stream>>>(part, P.nparts, stats);
     ctx->launches++;
     DLV_CUDA_OK(ctx, cudaGetLastError());
     return 0;

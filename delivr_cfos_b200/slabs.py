@@ -43,15 +43,24 @@ class SlabPlan:
         self.sz, self.sy, self.sx = ([int(v) for v in s] for s in starts)
         nz = len(self.sz)
         w = np.ones(nz) if layer_weights is None else np.maximum(np.asarray(layer_weights, dtype=np.float64), 1e-9)
-        # contiguous partition balanced by (active-)window count per layer
+        # contiguous partition of the layers minimising the largest per-rank weight (active-window count); exact DP,
+        # nz and world are tiny.  Ranks beyond the layer count get empty ranges at the end.
         cum = np.concatenate([[0.0], np.cumsum(w)])
-        bounds = [0]
-        for r in range(1, self.world):
-            target = cum[-1] * r / self.world
-            k = int(np.searchsorted(cum, target, side="left"))
-            k = min(max(k, bounds[-1] + (1 if nz - bounds[-1] > self.world - r else 0)), nz - (self.world - r))
-            bounds.append(max(k, bounds[-1]))
-        bounds.append(nz)
+        k = min(self.world, nz)
+        INF = float("inf")
+        best = [[INF] * (nz + 1) for _ in range(k + 1)]
+        cut = [[0] * (nz + 1) for _ in range(k + 1)]
+        best[0][0] = 0.0
+        for r in range(1, k + 1):
+            for j in range(r, nz - (k - r) + 1):
+                for i in range(r - 1, j):
+                    c = max(best[r - 1][i], cum[j] - cum[i])
+                    if c < best[r][j]:
+                        best[r][j], cut[r][j] = c, i
+        bounds = [nz]
+        for r in range(k, 0, -1):
+            bounds.append(cut[r][bounds[-1]])
+        bounds = bounds[::-1] + [nz] * (self.world - k)
         self.layers = [(bounds[r], bounds[r + 1]) for r in range(self.world)]
 
     def rank(self, r):
@@ -200,9 +209,13 @@ class CudaSlabWorker:
         self.ctx, self.plan, self.r = ctx, plan, rank
         self.info = plan.rank(rank)
         self.dev = torch.device("cuda", ctx.device)
+        # every torch-side operation of the worker (allocation fills, adds, NCCL sends) is enqueued on the library's
+        # own (non-blocking) stream, so it is ordered with the kernels without any cross-stream event
+        self.stream = torch.cuda.ExternalStream(ctx._L.dlv_stream(ctx._h), device=self.dev)
         self.window_batch, self.threshold, self.tta, self.ebp = window_batch, threshold, tta, erosion_block_planes
         z0, z1 = self.info["slab"]
-        self.slab = planes_fn(z0, z1) if z1 > z0 else None            # uint16 (z1-z0, PY, PX) on the device
+        with torch.cuda.stream(self.stream):
+            self.slab = planes_fn(z0, z1) if z1 > z0 else None        # uint16 (z1-z0, PY, PX) on the device
         self.acc = None
 
     def accumulate(self):
@@ -215,10 +228,13 @@ class CudaSlabWorker:
         local[:, 0] -= z0
         active = self.ctx.windows_active(self.slab, local, self.plan.roi)
         sel = local[active != 0]
-        flips = [0, 0, 2, 3, 0, 2, 3, 0, 2, 3, 0, 2, 3] if self.tta else [0]      # inference.py:265-279
+        # inference.py:265-279: 13 passes = 5 x plain, 4 x flip z (dim 2), 4 x flip y (dim 3); identical passes are
+        # evaluated once and blended `repeat` times (flip_dim | (repeat - 1) << 8, see dlv_seg_accumulate)
+        flips = [0 | (4 << 8), 2 | (3 << 8), 3 | (3 << 8)] if self.tta else [0]
         sched = np.concatenate([np.concatenate([sel, np.full((len(sel), 1), f, dtype=np.int32)], axis=1) for f in flips]) \
             if len(sel) else np.zeros((0, 4), dtype=np.int32)
-        self.acc = torch.zeros(self.slab.shape, dtype=torch.int32, device=self.dev)
+        with torch.cuda.stream(self.stream):
+            self.acc = torch.zeros(self.slab.shape, dtype=torch.int32, device=self.dev)
         self.ctx.seg_accumulate(self.slab, sched, self.plan.roi, self.acc, window_batch=self.window_batch)
         return active
 
@@ -228,14 +244,16 @@ class CudaSlabWorker:
 
     def add_planes(self, g0, g1, t):
         z0 = self.info["slab"][0]
-        self.acc[g0 - z0: g1 - z0] += t
+        with self.torch.cuda.stream(self.stream):
+            self.acc[g0 - z0: g1 - z0] += t
 
     def finalise(self, active_global):
         torch = self.torch
         o0, o1 = self.info["own_real"]
         Z, Y, X = self.plan.shape_real
         if self.slab is None or o1 <= o0:
-            self.binaries = torch.zeros((0, Y, X), dtype=torch.uint8, device=self.dev)
+            with torch.cuda.stream(self.stream):
+                self.binaries = torch.zeros((0, Y, X), dtype=torch.uint8, device=self.dev)
             return self.binaries
         z0, z1 = self.info["slab"]
         self.ctx.seg_average(self.acc, z1 - z0, z0, self.plan.shape_pad, self.plan.roi, self.plan.overlap, active_global,
@@ -271,12 +289,20 @@ class CudaSlabWorker:
 
     def relabel(self, lut):
         if self.labels.numel():
-            self.ctx.relabel(self.labels, self.torch.from_numpy(lut.view(np.int32)).to(self.dev))
+            with self.torch.cuda.stream(self.stream):
+                lut_dev = self.torch.from_numpy(lut.view(np.int32)).to(self.dev)
+            self.ctx.relabel(self.labels, lut_dev)
 
 
 # ------------------------------------------------------------------------------------------- drivers
 def run_virtual(workers, plan):
     """All ranks in this process (LocalComm).  Returns the merged table; workers keep binaries / labels."""
+    world = plan.world
+    with _stream_ctx(workers[0]):
+        return _run_virtual(workers, plan)
+
+
+def _run_virtual(workers, plan):
     world = plan.world
     active = [w.accumulate() for w in workers]
     for r in range(world):                                    # exchange 1: logit halo, r -> next non-empty rank
@@ -327,8 +353,23 @@ def _merge(workers, plan, counts, pairs_with_src):
     return merge_tables(tables, luts, zoff, n_global, plan.shape_real)
 
 
+def _stream_ctx(worker):
+    """CUDA workers: make the library stream torch's current stream (NCCL ops and tensor math are then ordered with
+    the library's kernels).  CPU workers (tests): nothing to do."""
+    import contextlib
+    st = getattr(worker, "stream", None)
+    if st is None:
+        return contextlib.nullcontext()
+    return worker.torch.cuda.stream(st)
+
+
 def run_distributed(worker, plan, comm):
     """One rank per process.  Collectives: send/recv of the logit halo and of one label plane, two object all-gathers."""
+    with _stream_ctx(worker):
+        return _run_distributed(worker, plan, comm)
+
+
+def _run_distributed(worker, plan, comm):
     r, world = comm.rank, comm.world
     info = plan.rank(r)
     active = worker.accumulate()
@@ -388,8 +429,28 @@ def run_distributed(worker, plan, comm):
 
 
 # ------------------------------------------------------------------------------------------- bench entry (N > 1)
+def balanced_plan(ctx, comm, shape, roi, overlap, planes_fn):
+    """Load-balanced partition: every rank scans the windows of an equal-thickness share
+    with the skip rule's max pre-pass (dlv_windows_active), the per-layer active-window counts are all-gathered and the
+    layers are re-partitioned by active count.  -> (SlabPlan, active counts per window layer)"""
+    plan0 = SlabPlan(shape, roi, overlap, comm.world)
+    info = plan0.rank(comm.rank)
+    act = np.zeros(0, dtype=np.int32)
+    if info["layers"][1] > info["layers"][0]:
+        z0, z1 = info["win"]
+        slab0 = planes_fn(z0, z1)
+        local = plan0.windows_of(comm.rank).copy()
+        local[:, 0] -= z0
+        act = ctx.windows_active(slab0, local, roi)
+        del slab0
+    all_act = np.concatenate([np.asarray(a, dtype=np.int32) for a in comm.allgather(act)])
+    per_layer = all_act.reshape(len(plan0.sz), -1).sum(axis=1)
+    return SlabPlan(shape, roi, overlap, comm.world, layer_weights=per_layer), per_layer
+
+
 def bench_main(args, rank, local_rank, world):
-    """bench.py --gpus N: weak scaling - every rank holds a cfg2-sized share of an N-times taller volume."""
+    """bench.py --gpus N: weak scaling - an N-times taller volume (N cfg2-sized shares stacked along z), window
+    z-layers partitioned over the ranks by active-window count."""
     import json
     import torch
     import torch.distributed as dist
@@ -407,9 +468,9 @@ def bench_main(args, rank, local_rank, world):
     sd, wdesc = B.state_dict()
     ctx = Context(local_rank)
     ctx.load_weights(sd)
-    plan = SlabPlan(shape, B.ROI, B.OVERLAP, world)
-    info = plan.rank(rank)
-    PY, PX = plan.shape_pad[1], plan.shape_pad[2]
+    stream = torch.cuda.ExternalStream(ctx._L.dlv_stream(ctx._h), device=dev)
+    comm = TorchComm()
+    PZ, PY, PX = SlabPlan(shape, B.ROI, B.OVERLAP, world).shape_pad
 
     def planes(z0, z1_):
         full = torch.zeros((z1_ - z0, PY, PX), dtype=torch.uint16, device=dev)
@@ -420,45 +481,75 @@ def bench_main(args, rank, local_rank, world):
 
     from .inference.inference import erosion_block_planes
     ebp = erosion_block_planes(shape)
-    slab = planes(*info["slab"])
-    comm = TorchComm()
+    with torch.cuda.stream(stream):
+        plan, per_layer = balanced_plan(ctx, comm, shape, B.ROI, B.OVERLAP, planes)
+        info = plan.rank(rank)
+        slab = planes(*info["slab"])
+        # end-to-end leg: the rank's slab starts in pinned host memory, binaries end in pinned host memory
+        hslab = torch.empty(slab.shape, dtype=torch.uint16).pin_memory()
+        hslab.copy_(slab)
+        o0, o1 = info["own_real"]
+        hbin = torch.empty((max(o1 - o0, 0), Y, X), dtype=torch.uint8).pin_memory()
+    torch.cuda.synchronize()
 
-    def step():
-        w = CudaSlabWorker(ctx, plan, rank, lambda a, b: slab, erosion_block_planes=ebp)
-        return run_distributed(w, plan, comm), w
+    def step(host):
+        def load(a, b):
+            if not host:
+                return slab
+            d = torch.empty(slab.shape, dtype=torch.uint16, device=dev)
+            d.copy_(hslab, non_blocking=True)
+            return d
+        w = CudaSlabWorker(ctx, plan, rank, load, erosion_block_planes=ebp)
+        table = run_distributed(w, plan, comm)
+        if host:
+            with torch.cuda.stream(stream):
+                hbin.copy_(w.binaries, non_blocking=True)
+            stream.synchronize()
+        return table, w
+
+    def timed(host, steps):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            table, w = step(host)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        dist.barrier()
+        dt = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)      # device time, max over ranks
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return float(dt.item()) * 1e3 / steps, table
 
     for _ in range(args.warmup):
-        table, w = step()
-    stream = torch.cuda.ExternalStream(ctx._L.dlv_stream(ctx._h), device=dev)
-    dist.barrier()
-    torch.cuda.synchronize()
+        step(False)
     sampler = B.ClockSampler(local_rank) if rank == 0 else None
     l0 = ctx.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        table, w = step()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    dist.barrier()
-    dt = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)      # device time, max over ranks
-    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    ms = float(dt.item()) * 1e3 / args.steps
+    ms, table = timed(False, args.steps)
     launches = torch.tensor([ctx.launches - l0], device=dev, dtype=torch.int64)
     dist.all_reduce(launches)
+    clocks = sampler.stop() if sampler else None
+    step(True)
+    ms_e2e, table_e2e = timed(True, args.steps)
+    io = torch.tensor([hslab.numel() * 2, hbin.numel()], device=dev, dtype=torch.int64)
+    dist.all_reduce(io)
     if rank == 0:
         nvox = int(np.prod(shape))
         v = nvox / (ms * 1e-3) / 1e9
+        nrow = table_e2e["n"] + 1
         print(json.dumps({
             "metric": "Gvoxels/s seg+CC", "value": v, "unit": "Gvoxels/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": f"synthetic; {wdesc}",
             "config": {"workload": f"{wl['name']} x {world} stacked along z ({shape[0]}x{Y}x{X}), z-slab sharded",
-                       "window": list(B.ROI), "overlap": B.OVERLAP, "tta": False, "components": table["n"],
-                       "layers_per_rank": plan.layers, "timing": "CUDA events on the library stream between barriers, max over ranks",
-                       "l2": "inputs larger than L2"},
-            "gpu_launches": int(launches.item()), "clocks": sampler.stop(),
-            "e2e": {"value": v, "unit": "Gvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                    "note": "device-resident slabs; host-buffer e2e is measured at N=1"},
+                       "window": list(B.ROI), "overlap": B.OVERLAP, "tta": False, "blend": "constant", "components": table["n"],
+                       "layers_per_rank": plan.layers, "active_windows_per_layer": [int(c) for c in per_layer],
+                       "windows_active": int(per_layer.sum()),
+                       "timing": "CUDA events on the library stream between barriers, max over ranks",
+                       "l2": "inputs larger than L2 (slab + accumulator >> 126 MB)"},
+            "gpu_launches": int(launches.item()), "clocks": clocks,
+            "e2e": {"value": nvox / (ms_e2e * 1e-3) / 1e9, "unit": "Gvoxels/s", "h2d_bytes_per_step": int(io[0].item()),
+                    "d2h_bytes_per_step": int(io[1].item()) + nrow * (8 + 24 + 48),
+                    "note": "per-rank pinned host slab in, pinned host binaries + merged table out"},
         }))
     dist.destroy_process_group()

@@ -62,3 +62,30 @@ def synth_volume_cuda(shape, seed, roi=None, device="cuda", slab=32, blobs_per_m
         vol = torch.where(inside, vol, torch.zeros_like(vol))
         out[z0 - zr0: z1 - zr0, :Y, :X] = vol.to(torch.int32).to(torch.uint16)
     return out
+
+
+def synth_mask_cuda(shape, seed, device="cuda", kind="blobs", p=0.08, blobs_per_mvox=370.0, chunk=50):
+    """Seeded uint8 binary mask for config 3, generated on the GPU in z-chunks.
+
+    ``blobs``: ball-shaped blobs (offsets with dz^2+dy^2+dx^2 <= 5) around ~370 uniformly drawn centres per 10^6
+    voxels (foreground ~2 %); ``bernoulli``: independent voxels with probability ``p`` (stress case).
+    Every chunk draws from its own generator keyed by (seed, chunk), so the mask is a pure function of the arguments."""
+    Z, Y, X = (int(s) for s in shape)
+    out = torch.zeros((Z, Y, X), dtype=torch.uint8, device=device)
+    offs = [(a, b, c) for a in range(-2, 3) for b in range(-2, 3) for c in range(-2, 3) if a * a + b * b + c * c <= 5]
+    for ci, z0 in enumerate(range(0, Z, chunk)):
+        z1 = min(Z, z0 + chunk)
+        g = torch.Generator(device=device).manual_seed(int(seed) * 7919 + ci)
+        if kind == "bernoulli":
+            out[z0:z1] = (torch.rand((z1 - z0, Y, X), generator=g, device=device) < p).to(torch.uint8)
+            continue
+        n = max(1, int(blobs_per_mvox * (z1 - z0) * Y * X / 1e6))
+        cz = torch.randint(z0, z1, (n,), generator=g, device=device)
+        cy = torch.randint(0, Y, (n,), generator=g, device=device)
+        cx = torch.randint(0, X, (n,), generator=g, device=device)
+        for a, b, c in offs:
+            z = (cz + a).clamp_(0, Z - 1)
+            y = (cy + b).clamp_(0, Y - 1)
+            x = (cx + c).clamp_(0, X - 1)
+            out[z, y, x] = 1
+    return out

@@ -73,7 +73,8 @@ typedef struct dlv_seg_params {
     int32_t roi[3];         /* window (inference.py:164-168); each a multiple of 16             */
     float overlap;          /* 0.5 in the reference (inference.py:125)                          */
     int32_t tta;            /* 0: one pass; 1: the reference's 13-pass plan (inference.py:265-279),
-                               noise-free (sigma <= 1e-3 on intensities >= 1 is below bf16 resolution) */
+                               noise-free (sigma <= 1e-3 on intensities >= 1 is below bf16 resolution); the
+                               13 passes are 5 plain + 4 flip-z + 4 flip-y, evaluated as 3 weighted passes */
     float threshold;        /* sigmoid threshold, 0.5 (inference.py:120)                        */
     int32_t erosion_iters;  /* 30 (inference.py:82)                                             */
     int64_t erosion_block_planes; /* z-extent of the Arrayterator blocks (inference.py:53); <=0: whole volume */
@@ -159,8 +160,10 @@ int dlv_window_grid(const int64_t shape_pad[3], const int32_t roi[3], float over
 /* Skip rule (sliding_window_inferer.py:198): active_host[i] = max over window i > 0.  origins are local to the slab. */
 int dlv_windows_active(dlv_ctx* ctx, const uint16_t* slab_dev, int64_t SY, int64_t SX, const int32_t* origins_host, int n,
                        const int32_t roi[3], int32_t* active_host);
-/* Gather + U-Net + blend for n scheduled windows.  windows_host[i] = {oz, oy, ox, flip_dim (0|2|3|4)}, origins local
- * to the slab; acc_dev: int32, same extent as the slab, fixed point 2^-12 logit units (+=, order independent). */
+/* Gather + U-Net + blend for n scheduled windows.  windows_host[i] = {oz, oy, ox, flip_dim (0|2|3|4) | (repeat-1) << 8},
+ * origins local to the slab; the window's logits are added `repeat` times (identical noise-free TTA passes,
+ * inference.py:269-279, are evaluated once); acc_dev: int32, same extent as the slab, fixed point 2^-12 logit units
+ * (+=, order independent). */
 int dlv_seg_accumulate(dlv_ctx* ctx, const uint16_t* slab_dev, int64_t SY, int64_t SX, const int32_t* windows_host, int n,
                        const int32_t roi[3], int window_batch, int blend_mode, int32_t* acc_dev);
 /* In-place int32 sums -> float32 averaged logits for planes [gz0, gz0+nplanes) of the padded volume

@@ -74,3 +74,39 @@ def test_ccl_csv_drop_last_component():
     t = ctx.ccl(m, m.shape)
     assert csv_text(t, t["n"]) == P.csv_text(st, n)
     assert csv_text(t, t["n"]).count("\n") - 1 == n - 1
+
+
+def test_ccl_full_size_cfg3_properties():
+    """BASELINE.json configs[2] at full size (1000x2048x2048 mask, 4.2e9 voxels - the oracle would take minutes):
+    size-independent properties.  labels > 0 == mask; sum of counts == foreground; every label 1..N used; the labelling
+    is idempotent (labelling `labels > 0` again reproduces labels and table); first voxels appear in raster order."""
+    from delivr_cfos_b200 import Context
+    from delivr_cfos_b200.synth import synth_mask_cuda
+    ctx = Context(0)
+    shape = (1000, 2048, 2048)
+    mask = synth_mask_cuda(shape, 1003)
+    labels = torch.empty(shape, dtype=torch.int32, device="cuda")
+    t = ctx.ccl(mask, shape, labels_out=labels)
+    n = t["n"]
+    fg = int(mask.sum(dtype=torch.int64))
+    assert n > 1_000_000 and 0.01 < fg / mask.numel() < 0.04
+    assert int(t["voxel_counts"][1:].sum()) == fg and int(t["voxel_counts"][0]) == mask.numel() - fg
+    assert int(t["voxel_counts"][1:].min()) >= 1
+    for z0 in range(0, shape[0], 100):                 # labels > 0 exactly where the mask is set, all within 1..N
+        l = labels[z0:z0 + 100]
+        assert torch.equal(l > 0, mask[z0:z0 + 100] > 0)
+        assert int(l.max()) <= n
+    # first voxel of label k precedes the first voxel of label k+1 in raster order: bbox zmin is non-decreasing
+    zmin = t["bounding_boxes"][1:, 0]
+    assert (np.diff(zmin) >= 0).all()
+    # coordinate sums against a direct reduction of one axis
+    zs = sum(int((mask[z].sum(dtype=torch.int64)) * z) for z in range(0, shape[0]))
+    assert int(t["sums"][1:, 0].sum()) == zs
+    # idempotence
+    mask2 = (labels > 0).to(torch.uint8)
+    del mask
+    labels2 = torch.empty(shape, dtype=torch.int32, device="cuda")
+    t2 = ctx.ccl(mask2, shape, labels_out=labels2)
+    assert t2["n"] == n and torch.equal(labels, labels2)
+    for k in ("voxel_counts", "sums", "bounding_boxes"):
+        assert np.array_equal(t[k], t2[k]), k

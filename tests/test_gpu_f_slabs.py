@@ -44,3 +44,24 @@ def test_virtual_slabs_equal_single_gpu(shape, roi, world, tta):
     for k in ("voxel_counts", "sums", "bounding_boxes"):
         assert np.array_equal(table[k], t1[k]), k
     assert np.array_equal(table["centroids"], t1["centroids"], equal_nan=True)
+
+
+def test_tta_weighted_passes_equal_13_explicit_passes():
+    """inference.py:265-279 runs 13 passes (5 plain, 4 flip z, 4 flip y once the sub-resolution noise is dropped); the
+    library evaluates 3 and blends them 5/4/4 times.  The int32 blend sums must be bit-identical to 13 explicit passes."""
+    from delivr_cfos_b200 import Context
+    from delivr_cfos_b200.synth import synth_volume_cuda
+    ctx = Context(0)
+    ctx.load_weights(unet_ref.random_state_dict(5))
+    shape, roi = (64, 64, 64), (32, 32, 32)
+    vol = synth_volume_cuda(shape, 78, roi=roi, blobs_per_mvox=2500.0)
+    plan_windows = np.array([(z, y, x) for z in (0, 16, 32) for y in (0, 16, 32) for x in (0, 16, 32)], dtype=np.int32)
+    def sched(flips):
+        return np.concatenate([np.concatenate([plan_windows, np.full((len(plan_windows), 1), f, np.int32)], axis=1) for f in flips])
+    acc13 = torch.zeros(tuple(vol.shape), dtype=torch.int32, device="cuda")
+    acc3 = torch.zeros_like(acc13)
+    torch.cuda.synchronize()
+    ctx.seg_accumulate(vol, sched([0, 0, 2, 3, 0, 2, 3, 0, 2, 3, 0, 2, 3]), roi, acc13)
+    ctx.seg_accumulate(vol, sched([0 | (4 << 8), 2 | (3 << 8), 3 | (3 << 8)]), roi, acc3)
+    assert int(acc13.abs().sum()) > 0
+    assert torch.equal(acc13, acc3)
