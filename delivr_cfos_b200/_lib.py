@@ -50,7 +50,8 @@ EXPORTS = [
     "dlv_synchronize", "dlv_set_conv_timing", "dlv_load_weights", "dlv_segment", "dlv_ccl", "dlv_table_free",
     "dlv_ccl_last_timing", "dlv_unet_forward", "dlv_op_conv3d", "dlv_op_deconv", "dlv_op_finalise",
     "dlv_window_grid", "dlv_windows_active", "dlv_seg_accumulate", "dlv_seg_average", "dlv_op_finalise_slab",
-    "dlv_ccl_boundary_pairs", "dlv_relabel",
+    "dlv_ccl_boundary_pairs", "dlv_relabel", "dlv_tiff_info", "dlv_tiff_read_u16", "dlv_tiff_last_error",
+    "dlv_load_tiff_planes",
 ]
 
 _lib = None
@@ -114,6 +115,15 @@ def load_library():
     L.dlv_ccl_boundary_pairs.argtypes = [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, P(c_i64)]
     L.dlv_relabel.restype = ctypes.c_int
     L.dlv_relabel.argtypes = [c_vp, c_vp, c_i64, c_vp, c_i64]
+    L.dlv_tiff_info.restype = ctypes.c_int
+    L.dlv_tiff_info.argtypes = [ctypes.c_char_p, P(c_i64), P(c_i64), P(c_i32), P(c_i32)]
+    L.dlv_tiff_read_u16.restype = ctypes.c_int
+    L.dlv_tiff_read_u16.argtypes = [ctypes.c_char_p, c_vp, c_i64, c_i64]
+    L.dlv_tiff_last_error.restype = ctypes.c_char_p
+    L.dlv_tiff_last_error.argtypes = []
+    L.dlv_load_tiff_planes.restype = ctypes.c_int
+    L.dlv_load_tiff_planes.argtypes = [c_vp, P(ctypes.c_char_p), ctypes.c_int, c_i64, c_i64, c_i32, c_vp, c_vp, c_i64, c_i64,
+                                       ctypes.c_int]
     if L.dlv_abi_version() != 1:
         raise DlvError("libdelivr_b200.so ABI version mismatch")
     _lib = L
@@ -303,8 +313,34 @@ class Context:
                 return np.unique(p, axis=0) if len(p) else p.reshape(0, 2)
             cap = int(cnt.value)
 
+    def load_tiff_planes(self, paths, Y, X, slab, threshold=-1, mask=None, nthreads=0):
+        """slab: device uint16 (n, SY, SX) <- the n TIFF planes (downsample_and_mask.py:398-414 without the .npy)."""
+        n = len(paths)
+        arr = (ctypes.c_char_p * n)(*[os.fsencode(p) for p in paths])
+        self._check(self._L.dlv_load_tiff_planes(self._h, arr, n, int(Y), int(X), int(threshold), _ptr(mask), _ptr(slab),
+                                                 int(slab.shape[1]), int(slab.shape[2]), int(nthreads)), "dlv_load_tiff_planes")
+
     def relabel(self, labels, lut):
         self._check(self._L.dlv_relabel(self._h, _ptr(labels), int(labels.numel()), _ptr(lut), int(lut.numel())), "dlv_relabel")
+
+
+def tiff_info(path):
+    """-> (height, width, bits, compression) of IFD 0 (host only; no GPU needed)."""
+    L = load_library()
+    h, w, b, c = c_i64(), c_i64(), c_i32(), c_i32()
+    if L.dlv_tiff_info(os.fsencode(path), ctypes.byref(h), ctypes.byref(w), ctypes.byref(b), ctypes.byref(c)) != 0:
+        raise DlvError(f"dlv_tiff_info: {L.dlv_tiff_last_error().decode()}")
+    return h.value, w.value, b.value, c.value
+
+
+def tiff_read_u16(path):
+    """One TIFF plane as a uint16 numpy array (what cv2.imread(path, -1).astype(np.uint16) returns; host only)."""
+    L = load_library()
+    h, w, _, _ = tiff_info(path)
+    out = np.empty((h, w), dtype=np.uint16)
+    if L.dlv_tiff_read_u16(os.fsencode(path), out.ctypes.data, h, w) != 0:
+        raise DlvError(f"dlv_tiff_read_u16: {L.dlv_tiff_last_error().decode()}")
+    return out
 
 
 def window_grid(shape_pad, roi, overlap):

@@ -77,8 +77,12 @@ def create_nifti_seg(threshold, model_output, output_file, network_output_file, 
 
 def run_inference(niftis, output_folder, stack_shape, comment="none", model_weights="weights/inference_weights.tar",
                   tta=False, threshold=0.5, cuda_devices="0,1", crop_size=(64, 64, 32), workers=0, sw_batch_size=100,
-                  overlap=0.5, verbosity=True, load_all_ram=False, settings=None, blend="constant", device=0, _net=None):
+                  overlap=0.5, verbosity=True, load_all_ram=False, settings=None, blend="constant", device=0, _net=None,
+                  volume=None):
     """Sliding-window U-Net inference + binarisation; same contract as the reference (inference.py:113-332).
+
+    ``volume`` (extension): a device-resident uint16 ``(Zp, Yp, Xp)`` tensor from
+    ``tiff_planes.load_masked_volume`` - then ``niftis`` is not read (no masked_nifti.npy round trip).
 
     ``cuda_devices``, ``workers`` and ``sw_batch_size`` are accepted for signature compatibility; the window batch is
     chosen by the library (the reference derives it from free VRAM, inference.py:171-187).
@@ -96,7 +100,10 @@ def run_inference(niftis, output_folder, stack_shape, comment="none", model_weig
     stack_shape_pad = list(stack_shape)
     for idx, dim in enumerate(stack_shape_pad[2:]):
         stack_shape_pad[idx + 2] = int(np.ceil(dim / crop_size[idx]) * crop_size[idx])
-    dataset = np.memmap(str(niftis[0]), dtype=np.uint16, mode="r", shape=tuple(stack_shape_pad), offset=128)
+    if volume is None:
+        dataset = np.memmap(str(niftis[0]), dtype=np.uint16, mode="r", shape=tuple(stack_shape_pad), offset=128)
+    elif tuple(volume.shape) != tuple(stack_shape_pad[2:]):
+        raise ValueError(f"volume has shape {tuple(volume.shape)}, expected the padded stack shape {tuple(stack_shape_pad[2:])}")
     shape_pad = tuple(stack_shape_pad[2:])
     shape_real = tuple(int(s) for s in stack_shape[2:])
 
@@ -116,7 +123,8 @@ def run_inference(niftis, output_folder, stack_shape, comment="none", model_weig
     activated = (np.lib.format.open_memmap(network_output_file, mode="w+", dtype=np.float32, shape=shape_real)
                  if network_output_file else None)
     avg = None if load_all_ram else np.empty(shape_pad, dtype=np.float32)
-    volume = np.ascontiguousarray(dataset[0, 0])
+    if volume is None:
+        volume = np.ascontiguousarray(dataset[0, 0])
     st = net.ctx.segment(volume, shape_pad, shape_real, crop_size, binarized, overlap=overlap, tta=bool(tta),
                          threshold=threshold, erosion_iters=30, erosion_block_planes=erosion_block_planes(shape_real),
                          blend_mode={"constant": 0, "gaussian": 1}[blend], avg_logits_out=avg, sigmoid_out=activated)

@@ -183,6 +183,24 @@ int dlv_ccl_boundary_pairs(dlv_ctx* ctx, const uint32_t* labels_lo_plane_dev, co
 /* labels[i] = map[labels[i]] for non-zero labels (local -> global component numbers). */
 int dlv_relabel(dlv_ctx* ctx, uint32_t* labels_dev, int64_t n, const uint32_t* map_dev, int64_t nmap);
 
+/* ---- raw TIFF planes -> device-resident masked volume ----
+ * Replaces the masked_nifti.npy producer loop (downsample/downsample_and_mask.py:398-414: cv2.imread(plane, -1),
+ * mask rule, copy into the zero-padded array) and get_real_size (downsample_and_mask.py:25-30), so that the
+ * 2 B/voxel intermediate file is never written or re-read.  Reader: classic TIFF, II/MM, strips, one channel,
+ * 8/16-bit unsigned, compression none(1) / LZW(5) / Deflate(8, 32946) / PackBits(32773), predictor 1 or 2; anything
+ * else fails.  dlv_tiff_info / dlv_tiff_read_u16 are host-only (no ctx, no GPU); their message is
+ * dlv_tiff_last_error() (thread-local). */
+int dlv_tiff_info(const char* path, int64_t* height, int64_t* width, int32_t* bits, int32_t* compression);
+/* out_host[height][width]: IFD 0 decoded, 8-bit samples widened (like numpy .astype(uint16)). */
+int dlv_tiff_read_u16(const char* path, uint16_t* out_host, int64_t height, int64_t width);
+const char* dlv_tiff_last_error(void);
+/* Plane i of the slab <- paths[i] (each Y x X): decoded on `nthreads` host threads (<=0: all cores) into pinned memory,
+ * read by the GPU over PCIe, masked and written to slab_dev[i][SY][SX] (SY >= Y, SX >= X; the pad is zero-filled,
+ * downsample_and_mask.py:391-396).  Mask rule (:405-411): mask_dev_or_null (uint8 [n][Y][X]) != NULL: v *= mask
+ * (uint16 wrap-around); else threshold >= 0: v < threshold -> 0; else: unmasked. */
+int dlv_load_tiff_planes(dlv_ctx* ctx, const char* const* paths, int n, int64_t Y, int64_t X, int32_t threshold,
+                         const uint8_t* mask_dev_or_null, uint16_t* slab_dev, int64_t SY, int64_t SX, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif
