@@ -41,7 +41,8 @@ class SegStats(ctypes.Structure):
 
 class Table(ctypes.Structure):
     _fields_ = [("n", c_i64), ("voxel_counts", ctypes.POINTER(ctypes.c_uint64)),
-                ("sums", ctypes.POINTER(ctypes.c_uint64)), ("bbox", ctypes.POINTER(c_i64))]
+                ("sums", ctypes.POINTER(ctypes.c_uint64)), ("bbox", ctypes.POINTER(c_i64)),
+                ("centroids", ctypes.POINTER(ctypes.c_double))]
 
 
 # every symbol include/delivr_b200.h declares (tests check the .so exports exactly these)
@@ -51,7 +52,7 @@ EXPORTS = [
     "dlv_ccl_last_timing", "dlv_unet_forward", "dlv_op_conv3d", "dlv_op_deconv", "dlv_op_finalise",
     "dlv_window_grid", "dlv_windows_active", "dlv_seg_accumulate", "dlv_seg_average", "dlv_op_finalise_slab",
     "dlv_ccl_boundary_pairs", "dlv_relabel", "dlv_tiff_info", "dlv_tiff_read_u16", "dlv_tiff_last_error",
-    "dlv_load_tiff_planes",
+    "dlv_load_tiff_planes", "dlv_paint_boxes", "dlv_edt",
 ]
 
 _lib = None
@@ -124,7 +125,11 @@ def load_library():
     L.dlv_load_tiff_planes.restype = ctypes.c_int
     L.dlv_load_tiff_planes.argtypes = [c_vp, P(ctypes.c_char_p), ctypes.c_int, c_i64, c_i64, c_i32, c_vp, c_vp, c_i64, c_i64,
                                        ctypes.c_int]
-    if L.dlv_abi_version() != 1:
+    L.dlv_paint_boxes.restype = ctypes.c_int
+    L.dlv_paint_boxes.argtypes = [c_vp, c_vp, P(c_i64), c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, P(c_vp), c_i64]
+    L.dlv_edt.restype = ctypes.c_int
+    L.dlv_edt.argtypes = [c_vp, c_vp, P(c_i64), P(ctypes.c_double), c_vp]
+    if L.dlv_abi_version() != 2:
         raise DlvError("libdelivr_b200.so ABI version mismatch")
     _lib = L
     return L
@@ -143,6 +148,18 @@ def _ptr(x):
             raise ValueError("tensor must be contiguous")
         return x.data_ptr()
     return int(x)
+
+
+class _TableOwner:
+    """Keeps a dlv_table alive while numpy views of its arrays exist."""
+
+    def __init__(self, lib, tp):
+        self._lib, self._tp = lib, tp
+
+    def __del__(self):
+        if self._tp is not None:
+            self._lib.dlv_table_free(self._tp)
+            self._tp = None
 
 
 class Context:
@@ -171,6 +188,18 @@ class Context:
     def _check(self, rc, what):
         if rc != 0:
             raise DlvError(f"{what} failed ({rc}): {self._L.dlv_last_error(self._h).decode()}")
+
+    def _after_torch(self, *xs):
+        """Order the library's stream after torch's current stream when device tensors are passed in: a tensor that
+        torch is still writing (e.g. ``(labels > 0).to(uint8)`` just enqueued) must be complete before the library
+        reads it.  Results flow the other way through the entry points' own end-of-call synchronisation."""
+        if not any(getattr(x, "is_cuda", False) for x in xs):
+            return
+        import torch
+        cur = torch.cuda.current_stream(self.device)
+        lib = self._L.dlv_stream(self._h)
+        if cur.cuda_stream != lib:
+            torch.cuda.ExternalStream(lib, device=self.device).wait_stream(cur)
 
     @property
     def launches(self):
@@ -206,6 +235,7 @@ class Context:
                 erosion_iters=30, erosion_block_planes=0, blend_mode=0, window_batch=0, skip_empty=True,
                 flip_dim=None, avg_logits_out=None, sigmoid_out=None):
         p = SegParams()
+        self._after_torch(volume, binaries_out, avg_logits_out, sigmoid_out)
         p.shape_pad[:] = [int(s) for s in shape_pad]
         p.shape_real[:] = [int(s) for s in shape_real]
         p.roi[:] = [int(s) for s in roi]
@@ -224,19 +254,25 @@ class Context:
         """-> dict(n, voxel_counts uint64[N+1], sums uint64[N+1,3], bounding_boxes int64[N+1,6], centroids f64[N+1,3])."""
         shp = (c_i64 * 3)(*[int(s) for s in shape])
         tp = ctypes.POINTER(Table)()
+        self._after_torch(mask, labels_out)
         self._check(self._L.dlv_ccl(self._h, _ptr(mask), shp, 26, _ptr(labels_out), ctypes.byref(tp)), "dlv_ccl")
-        try:
-            t = tp.contents
-            n = int(t.n)
-            counts = np.ctypeslib.as_array(t.voxel_counts, shape=(n + 1,)).copy()
-            sums = np.ctypeslib.as_array(t.sums, shape=(n + 1, 3)).copy()
-            bbox = np.ctypeslib.as_array(t.bbox, shape=(n + 1, 6)).copy()
-        finally:
-            self._L.dlv_table_free(tp)
-        with np.errstate(invalid="ignore", divide="ignore"):
-            # cc3d's centroid definition: sum(coord) / count, one fp64 divide (count_blobs.py:85)
-            cent = sums.astype(np.float64) / counts.astype(np.float64)[:, None]
-        return {"n": n, "voxel_counts": counts, "sums": sums, "bounding_boxes": bbox, "centroids": cent}
+        # zero-copy views of the library's pinned table block; it goes back to the library's pool when the last
+        # array that refers to it is garbage-collected (dlv_table_free)
+        owner = _TableOwner(self._L, tp)
+        t = tp.contents
+        n = int(t.n)
+
+        def view(ptr, ctype, dtype, shape):
+            buf = (ctype * int(np.prod(shape))).from_address(ctypes.addressof(ptr.contents))
+            buf._owner = owner
+            return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+        return {"n": n,
+                "voxel_counts": view(t.voxel_counts, ctypes.c_uint64, np.uint64, (n + 1,)),
+                "sums": view(t.sums, ctypes.c_uint64, np.uint64, (n + 1, 3)),
+                "bounding_boxes": view(t.bbox, c_i64, np.int64, (n + 1, 6)),
+                # cc3d's centroid definition: sum(coord) / count, one fp64 divide (count_blobs.py:85)
+                "centroids": view(t.centroids, ctypes.c_double, np.float64, (n + 1, 3))}
 
     def ccl_last_timing(self):
         ms, ln = ctypes.c_double(), c_i64()
@@ -246,22 +282,26 @@ class Context:
     # ---- operator-level entry points (device pointers)
     def unet_forward(self, windows_u16, roi, logits_out):
         nwin = int(windows_u16.shape[0])
+        self._after_torch(windows_u16, logits_out)
         r = (c_i32 * 3)(*[int(s) for s in roi])
         self._check(self._L.dlv_unet_forward(self._h, _ptr(windows_u16), nwin, r, _ptr(logits_out)), "dlv_unet_forward")
 
     def op_conv3d(self, layer, x, y_out, stats_out):
         n, _, D, H, W = [int(s) for s in x.shape]
+        self._after_torch(x, y_out, stats_out)
         self._check(self._L.dlv_op_conv3d(self._h, layer.encode(), _ptr(x), n, D, H, W, _ptr(y_out), _ptr(stats_out)),
                     "dlv_op_conv3d")
 
     def op_deconv(self, upcat, x, y_out):
         n, _, D, H, W = [int(s) for s in x.shape]
+        self._after_torch(x, y_out)
         self._check(self._L.dlv_op_deconv(self._h, upcat.encode(), _ptr(x), n, D, H, W, _ptr(y_out)), "dlv_op_deconv")
 
     def op_finalise(self, avg_logits, volume, shape_pad, shape_real, binaries_out, threshold=0.5, erosion_iters=30,
                     erosion_block_planes=0, sigmoid_out=None):
         sp = (c_i64 * 3)(*[int(s) for s in shape_pad])
         sr = (c_i64 * 3)(*[int(s) for s in shape_real])
+        self._after_torch(avg_logits, volume, binaries_out, sigmoid_out)
         self._check(self._L.dlv_op_finalise(self._h, _ptr(avg_logits), _ptr(volume), sp, sr, float(threshold),
                                             int(erosion_iters), int(erosion_block_planes), _ptr(binaries_out),
                                             _ptr(sigmoid_out)), "dlv_op_finalise")
@@ -271,6 +311,7 @@ class Context:
         """origins int32 [n,3] local to the slab (device uint16 (SZ,SY,SX)) -> int32 [n] activity flags."""
         o = np.ascontiguousarray(origins, dtype=np.int32)
         out = np.zeros(len(o), dtype=np.int32)
+        self._after_torch(slab)
         r = (c_i32 * 3)(*[int(v) for v in roi])
         self._check(self._L.dlv_windows_active(self._h, _ptr(slab), int(slab.shape[1]), int(slab.shape[2]), o.ctypes.data,
                                                len(o), r, out.ctypes.data), "dlv_windows_active")
@@ -279,6 +320,7 @@ class Context:
     def seg_accumulate(self, slab, windows, roi, acc, window_batch=0, blend_mode=0):
         """windows int32 [n,4] = (oz,oy,ox,flip_dim) local to the slab; acc int32 device tensor shaped like slab."""
         w = np.ascontiguousarray(windows, dtype=np.int32).reshape(-1, 4)
+        self._after_torch(slab, acc)
         r = (c_i32 * 3)(*[int(v) for v in roi])
         self._check(self._L.dlv_seg_accumulate(self._h, _ptr(slab), int(slab.shape[1]), int(slab.shape[2]), w.ctypes.data,
                                                len(w), r, int(window_batch), int(blend_mode), _ptr(acc)), "dlv_seg_accumulate")
@@ -287,12 +329,14 @@ class Context:
         sp = (c_i64 * 3)(*[int(v) for v in shape_pad])
         r = (c_i32 * 3)(*[int(v) for v in roi])
         a = np.ascontiguousarray(active, dtype=np.int32)
+        self._after_torch(acc)
         self._check(self._L.dlv_seg_average(self._h, _ptr(acc), int(nplanes), int(gz0), sp, r, float(overlap), a.ctypes.data,
                                             int(passes), int(blend_mode)), "dlv_seg_average")
 
     def op_finalise_slab(self, avg, volume, nplanes, gz0, shape_real, oz0, oz1, binaries_out, threshold=0.5,
                          erosion_iters=30, erosion_block_planes=0, sigmoid_out=None):
         sr = (c_i64 * 3)(*[int(v) for v in shape_real])
+        self._after_torch(avg, volume, binaries_out, sigmoid_out)
         self._check(self._L.dlv_op_finalise_slab(self._h, _ptr(avg), _ptr(volume), int(volume.shape[1]), int(volume.shape[2]),
                                                  int(nplanes), int(gz0), sr, float(threshold), int(erosion_iters),
                                                  int(erosion_block_planes), int(oz0), int(oz1), _ptr(binaries_out),
@@ -303,6 +347,7 @@ class Context:
         import torch
         Y, X = int(labels_hi_plane.shape[-2]), int(labels_hi_plane.shape[-1])
         cap = max(1024, Y * X // 8)
+        self._after_torch(labels_lo_plane, labels_hi_plane)
         while True:
             buf = torch.empty((cap, 2), dtype=torch.int32, device=labels_hi_plane.device)
             cnt = c_i64()
@@ -317,10 +362,39 @@ class Context:
         """slab: device uint16 (n, SY, SX) <- the n TIFF planes (downsample_and_mask.py:398-414 without the .npy)."""
         n = len(paths)
         arr = (ctypes.c_char_p * n)(*[os.fsencode(p) for p in paths])
+        self._after_torch(mask, slab)
         self._check(self._L.dlv_load_tiff_planes(self._h, arr, n, int(Y), int(X), int(threshold), _ptr(mask), _ptr(slab),
                                                  int(slab.shape[1]), int(slab.shape[2]), int(nthreads)), "dlv_load_tiff_planes")
 
+    def paint_boxes(self, mask, shape, boxes, values, outs, chunk_voxels=0):
+        """outs[c][box_k] = mask[box_k] * values[k][c] for k in order (blob_highlighter.py:107-124,143-151;
+        blob_depthmap.py:198-207).  boxes int64 [n,6] numpy slice bounds, values int [n,nch], outs: list of nch
+        (Z,Y,X) uint8 or uint16 arrays / device tensors (all the same dtype), fully overwritten."""
+        b = np.ascontiguousarray(boxes, dtype=np.int64).reshape(-1, 6)
+        nch = len(outs)
+        v = np.ascontiguousarray(values, dtype=np.int64).reshape(len(b), nch)
+        eb = {1, 2} & {int(o.element_size()) if hasattr(o, "element_size") else int(o.dtype.itemsize) for o in outs}
+        if len(eb) != 1:
+            raise ValueError("outputs must all be uint8 or all be uint16")
+        shp = (c_i64 * 3)(*[int(s) for s in shape])
+        arr = (c_vp * nch)(*[_ptr(o) for o in outs])
+        self._after_torch(mask, *outs)
+        self._check(self._L.dlv_paint_boxes(self._h, _ptr(mask), shp, b.ctypes.data, v.ctypes.data, len(b), nch, eb.pop(), arr,
+                                            int(chunk_voxels)), "dlv_paint_boxes")
+
+    def edt(self, nonzero, sampling, out=None):
+        """Exact EDT of a zero-surrounded volume (blob_depthmap.py:174-181): uint8 (Z,Y,X) -> float64 distances."""
+        shape = tuple(int(v) for v in nonzero.shape)
+        if out is None:
+            out = np.empty(shape, dtype=np.float64)
+        shp = (c_i64 * 3)(*shape)
+        smp = (ctypes.c_double * 3)(*[float(v) for v in sampling])
+        self._after_torch(nonzero, out)
+        self._check(self._L.dlv_edt(self._h, _ptr(nonzero), shp, smp, _ptr(out)), "dlv_edt")
+        return out
+
     def relabel(self, labels, lut):
+        self._after_torch(labels, lut)
         self._check(self._L.dlv_relabel(self._h, _ptr(labels), int(labels.numel()), _ptr(lut), int(lut.numel())), "dlv_relabel")
 
 

@@ -148,13 +148,7 @@ int dlv_ccl(dlv_ctx* c, const void* mask_any, const int64_t shape[3], int connec
     return rc;
 }
 
-void dlv_table_free(dlv_table* t) {
-    if (!t) return;
-    free(t->voxel_counts);
-    free(t->sums);
-    free(t->bbox);
-    free(t);
-}
+void dlv_table_free(dlv_table* t) { dlv::table_free(t); }
 
 int dlv_ccl_last_timing(const dlv_ctx* c, double* ms_kernels, int64_t* launches) {
     if (!c) return DLV_ERR_ARG;

@@ -20,6 +20,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "dlv_common.cuh"
@@ -56,7 +57,10 @@ __device__ __forceinline__ void uf_union(uint32_t* L, uint32_t a, uint32_t b) {
 struct BgBox { int zmin, zmax, ymin, ymax, xmin, xmax; };
 
 // ---- P1: mask -> bitmask + initial labels (+ bounding box of the background for table row 0)
-// One warp handles 128 consecutive voxels of a row per iteration (4 per lane, 16 B label stores).
+// One warp handles kInitSegs x 128 consecutive voxels per iteration (4 per lane and segment, 16 B label stores); the
+// kInitSegs mask loads are issued before any of them is used, so every thread keeps that many loads in flight
+// (one load per thread and iteration left the kernel latency-bound at 2.6 TB/s).
+constexpr int kInitSegs = 4;
 __global__ void ccl_init_kernel(const uint8_t* __restrict__ mask, CclGeom g, uint32_t* __restrict__ bits,
                                 uint32_t* __restrict__ L, int* __restrict__ bgbox) {
     const int lane = threadIdx.x & 31;
@@ -64,59 +68,78 @@ __global__ void ccl_init_kernel(const uint8_t* __restrict__ mask, CclGeom g, uin
     const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
     const int segs = (g.W + 3) / 4;                       // 128-voxel segments per row
     const int64_t total = g.rows * segs;
-    const bool vec = (g.X % 4) == 0;
+    const int64_t total_it = (total + kInitSegs - 1) / kInitSegs;
+    const bool vec = (g.X % 4) == 0 && (reinterpret_cast<uintptr_t>(mask) & 3u) == 0;
     BgBox bb = {INT_MAX, -1, INT_MAX, -1, INT_MAX, -1};
-    for (int64_t it = warp_global; it < total; it += nwarps) {
-        const int64_t r = it / segs;
-        const int sg = static_cast<int>(it - r * segs);
-        const int64_t x0 = static_cast<int64_t>(sg) * 128 + lane * 4;
-        const int64_t base = r * g.X;
-        uint32_t nib = 0;
-        if (vec) {
-            if (x0 < g.X) {
-                const uint32_t m = *reinterpret_cast<const uint32_t*>(mask + base + x0);
-                nib = ((m & 0xFFu) ? 1u : 0u) | ((m & 0xFF00u) ? 2u : 0u) | ((m & 0xFF0000u) ? 4u : 0u) | ((m & 0xFF000000u) ? 8u : 0u);
-            }
-        } else {
+    for (int64_t it4 = warp_global; it4 < total_it; it4 += nwarps) {
+        uint32_t nibs[kInitSegs];
+        int64_t rr[kInitSegs];
+        int sgs[kInitSegs];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (x0 + j < g.X && mask[base + x0 + j]) nib |= 1u << j;
-        }
-        // assemble the 32-bit word of this lane's 8-lane group
-        uint32_t word = nib << (4 * (lane & 7));
-        word |= __shfl_xor_sync(0xffffffffu, word, 1);
-        word |= __shfl_xor_sync(0xffffffffu, word, 2);
-        word |= __shfl_xor_sync(0xffffffffu, word, 4);
-        const int wi = sg * 4 + (lane >> 3);
-        if ((lane & 7) == 0 && wi < g.W) bits[r * g.W + wi] = word;
-        if (x0 < g.X) {
-            const uint32_t wbase = static_cast<uint32_t>(base + static_cast<int64_t>(wi) * 32);   // 0-based index of bit 0
-            uint32_t lab[4];
-            int nbg = 0, bx0 = INT_MAX, bx1 = -1;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int b = 4 * (lane & 7) + j;
-                if ((word >> b) & 1u) {
-                    const uint32_t zeros_below = ~word & ((1u << b) - 1u);
-                    const int s = zeros_below ? (32 - __clz(zeros_below)) : 0;
-                    lab[j] = wbase + s + 1u;
-                } else {
-                    lab[j] = 0u;
-                    if (x0 + j < g.X) { ++nbg; bx0 = min(bx0, static_cast<int>(x0 + j)); bx1 = max(bx1, static_cast<int>(x0 + j)); }
-                }
-            }
+        for (int u = 0; u < kInitSegs; ++u) {
+            const int64_t it = it4 * kInitSegs + u;
+            nibs[u] = 0;
+            rr[u] = -1; sgs[u] = 0;
+            if (it >= total) continue;
+            const int64_t r = it / segs;
+            const int sg = static_cast<int>(it - r * segs);
+            rr[u] = r; sgs[u] = sg;
+            const int64_t x0 = static_cast<int64_t>(sg) * 128 + lane * 4;
+            const int64_t base = r * g.X;
             if (vec) {
-                *reinterpret_cast<uint4*>(L + base + x0) = make_uint4(lab[0], lab[1], lab[2], lab[3]);
+                if (x0 < g.X) {
+                    const uint32_t m = __ldcs(reinterpret_cast<const uint32_t*>(mask + base + x0));
+                    nibs[u] = ((m & 0xFFu) ? 1u : 0u) | ((m & 0xFF00u) ? 2u : 0u) | ((m & 0xFF0000u) ? 4u : 0u) | ((m & 0xFF000000u) ? 8u : 0u);
+                }
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    if (x0 + j < g.X) L[base + x0 + j] = lab[j];
+                    if (x0 + j < g.X && mask[base + x0 + j]) nibs[u] |= 1u << j;
             }
-            if (nbg) {
-                const int z = static_cast<int>(r / g.Y), y = static_cast<int>(r - static_cast<int64_t>(z) * g.Y);
-                bb.zmin = min(bb.zmin, z); bb.zmax = max(bb.zmax, z);
-                bb.ymin = min(bb.ymin, y); bb.ymax = max(bb.ymax, y);
-                bb.xmin = min(bb.xmin, bx0); bb.xmax = max(bb.xmax, bx1);
+        }
+#pragma unroll
+        for (int u = 0; u < kInitSegs; ++u) {
+            if (rr[u] < 0) continue;                       // warp-uniform
+            const int64_t r = rr[u];
+            const int sg = sgs[u];
+            const int64_t x0 = static_cast<int64_t>(sg) * 128 + lane * 4;
+            const int64_t base = r * g.X;
+            // assemble the 32-bit word of this lane's 8-lane group
+            uint32_t word = nibs[u] << (4 * (lane & 7));
+            word |= __shfl_xor_sync(0xffffffffu, word, 1);
+            word |= __shfl_xor_sync(0xffffffffu, word, 2);
+            word |= __shfl_xor_sync(0xffffffffu, word, 4);
+            const int wi = sg * 4 + (lane >> 3);
+            if ((lane & 7) == 0 && wi < g.W) bits[r * g.W + wi] = word;
+            if (x0 < g.X) {
+                const uint32_t wbase = static_cast<uint32_t>(base + static_cast<int64_t>(wi) * 32);   // 0-based index of bit 0
+                uint32_t lab[4];
+                int nbg = 0, bx0 = INT_MAX, bx1 = -1;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int b = 4 * (lane & 7) + j;
+                    if ((word >> b) & 1u) {
+                        const uint32_t zeros_below = ~word & ((1u << b) - 1u);
+                        const int s = zeros_below ? (32 - __clz(zeros_below)) : 0;
+                        lab[j] = wbase + s + 1u;
+                    } else {
+                        lab[j] = 0u;
+                        if (x0 + j < g.X) { ++nbg; bx0 = min(bx0, static_cast<int>(x0 + j)); bx1 = max(bx1, static_cast<int>(x0 + j)); }
+                    }
+                }
+                if (vec) {
+                    *reinterpret_cast<uint4*>(L + base + x0) = make_uint4(lab[0], lab[1], lab[2], lab[3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (x0 + j < g.X) L[base + x0 + j] = lab[j];
+                }
+                if (nbg) {
+                    const int z = static_cast<int>(r / g.Y), y = static_cast<int>(r - static_cast<int64_t>(z) * g.Y);
+                    bb.zmin = min(bb.zmin, z); bb.zmax = max(bb.zmax, z);
+                    bb.ymin = min(bb.ymin, y); bb.ymax = max(bb.ymax, y);
+                    bb.xmin = min(bb.xmin, bx0); bb.xmax = max(bb.xmax, bx1);
+                }
             }
         }
     }
@@ -142,44 +165,66 @@ __global__ void ccl_init_kernel(const uint8_t* __restrict__ mask, CclGeom g, uin
              _once; _once = 0, _m &= ~((len >= 64 ? ~0ull : ((1ull << len) - 1ull)) << a))
 
 // ---- P2: unions between touching runs
-__global__ void ccl_merge_kernel(CclGeom g, const uint32_t* __restrict__ bits, uint32_t* __restrict__ L) {
+// One thread per bitmask word ENUMERATES the (run, touching run) pairs of its word - all neighbour words are loaded
+// before any is used - and appends them to a per-block queue in shared memory; then the whole block executes the
+// queued unions, one pair per thread.  On blob-like masks only ~15 % of the words are non-zero, so executing the
+// unions where they are found leaves most lanes idle behind a few lanes that walk ~20 dependent L2 round trips
+// each; through the queue the same round trips run side by side.  Pairs beyond the queue capacity (dense masks)
+// are executed in place.  Union-find results do not depend on the order of the unions.
+constexpr int kMergeThreads = 256;
+constexpr int kMergeQueue = 3072;
+__global__ void __launch_bounds__(kMergeThreads) ccl_merge_kernel(CclGeom g, const uint32_t* __restrict__ bits, uint32_t* __restrict__ L) {
+    __shared__ uint2 queue[kMergeQueue];
+    __shared__ unsigned qn;
+    if (threadIdx.x == 0) qn = 0;
+    __syncthreads();
     const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (t >= g.rows * g.W) return;
-    const int64_t r = t / g.W;
-    const int w = static_cast<int>(t - r * g.W);
-    const uint32_t cur = bits[t];
-    if (!cur) return;
-    const int64_t z = r / g.Y, y = r - z * g.Y;
-    const uint32_t vbase = static_cast<uint32_t>(r * g.X + static_cast<int64_t>(w) * 32) + 1u;   // label of bit 0
-    // same row, previous word
-    if ((cur & 1u) && w > 0 && (bits[t - 1] >> 31)) uf_union(L, vbase, vbase - 1u);
-    // raster-predecessor rows
-    int64_t nrows[4];
-    int nn = 0;
-    if (y > 0) nrows[nn++] = r - 1;
-    if (z > 0) {
-        if (y > 0) nrows[nn++] = r - g.Y - 1;
-        nrows[nn++] = r - g.Y;
-        if (y + 1 < g.Y) nrows[nn++] = r - g.Y + 1;
-    }
-    for (int k = 0; k < nn; ++k) {
-        const uint32_t* nb = bits + nrows[k] * g.W;
-        const uint32_t c = nb[w];
-        const uint32_t p = (w > 0) ? nb[w - 1] : 0u;
-        const uint32_t q = (w + 1 < g.W) ? nb[w + 1] : 0u;
-        // bit i of comb <-> neighbour-row voxel x = w*32 + i - 1, i in [0, 34)
-        const unsigned long long comb = (static_cast<unsigned long long>(c) << 1) | (p >> 31) | (static_cast<unsigned long long>(q & 1u) << 33);
-        if (!comb) continue;
-        const uint32_t nbase = static_cast<uint32_t>(nrows[k] * g.X + static_cast<int64_t>(w) * 32);   // label of neighbour bit i is nbase + i
-        DLV_FOR_RUNS64(static_cast<unsigned long long>(cur), a, len) {
-            // run [a, a+len) of the current word touches neighbour bits [a, a+len+2) of comb
-            const unsigned long long span = ((len + 2 >= 64) ? ~0ull : ((1ull << (len + 2)) - 1ull)) << a;
-            DLV_FOR_RUNS64(comb & span, i, ilen) {
-                (void)ilen;
-                uf_union(L, vbase + a, nbase + i);
+    const uint32_t cur = (t < g.rows * g.W) ? bits[t] : 0u;
+    if (cur) {
+        auto push = [&](uint32_t a, uint32_t b) {
+            const unsigned i = atomicAdd(&qn, 1u);
+            if (i < kMergeQueue) queue[i] = make_uint2(a, b); else uf_union(L, a, b);
+        };
+        const int64_t r = t / g.W;
+        const int w = static_cast<int>(t - r * g.W);
+        const int64_t z = r / g.Y, y = r - z * g.Y;
+        const uint32_t vbase = static_cast<uint32_t>(r * g.X + static_cast<int64_t>(w) * 32) + 1u;   // label of bit 0
+        // raster-predecessor rows: (z, y-1), (z-1, y-1), (z-1, y), (z-1, y+1)
+        const int64_t nrows[4] = {r - 1, r - g.Y - 1, r - g.Y, r - g.Y + 1};
+        const bool ok[4] = {y > 0, z > 0 && y > 0, z > 0, z > 0 && y + 1 < g.Y};
+        uint32_t c[4], p[4], q[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            c[k] = p[k] = q[k] = 0u;
+            if (ok[k]) {
+                const uint32_t* nb = bits + nrows[k] * g.W;
+                c[k] = nb[w];
+                if (w > 0) p[k] = nb[w - 1];
+                if (w + 1 < g.W) q[k] = nb[w + 1];
+            }
+        }
+        const uint32_t prevw = (w > 0 && (cur & 1u)) ? bits[t - 1] : 0u;
+        // same row, previous word
+        if (prevw >> 31) push(vbase, vbase - 1u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            // bit i of comb <-> neighbour-row voxel x = w*32 + i - 1, i in [0, 34)
+            const unsigned long long comb = (static_cast<unsigned long long>(c[k]) << 1) | (p[k] >> 31) | (static_cast<unsigned long long>(q[k] & 1u) << 33);
+            if (!comb) continue;
+            const uint32_t nbase = static_cast<uint32_t>(nrows[k] * g.X + static_cast<int64_t>(w) * 32);   // label of neighbour bit i is nbase + i
+            DLV_FOR_RUNS64(static_cast<unsigned long long>(cur), a, len) {
+                // run [a, a+len) of the current word touches neighbour bits [a, a+len+2) of comb
+                const unsigned long long span = ((len + 2 >= 64) ? ~0ull : ((1ull << (len + 2)) - 1ull)) << a;
+                DLV_FOR_RUNS64(comb & span, i, ilen) {
+                    (void)ilen;
+                    push(vbase + a, nbase + i);
+                }
             }
         }
     }
+    __syncthreads();
+    const unsigned n = min(qn, static_cast<unsigned>(kMergeQueue));
+    for (unsigned i = threadIdx.x; i < n; i += kMergeThreads) uf_union(L, queue[i].x, queue[i].y);
 }
 
 // ---- P3: resolve roots per run, flag roots
@@ -310,6 +355,84 @@ __global__ void bbox_init_kernel(int* __restrict__ bbox, int64_t rows, int Z, in
     b[0] = Z; b[1] = -1; b[2] = Y; b[3] = -1; b[4] = X; b[5] = -1;
 }
 
+// ---- P6: table rows in their final host layout: bounding boxes widened to int64, centroids = sum / count in fp64
+// (IEEE division: bit-identical to the host's, count_blobs.py:85), and the foreground totals that define row 0.
+__global__ void ccl_table_finish_kernel(int64_t rows, const unsigned long long* __restrict__ cnt, const unsigned long long* __restrict__ sums,
+                                        const int* __restrict__ bbox, long long* __restrict__ bbox64, double* __restrict__ cent,
+                                        unsigned long long* __restrict__ totals) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    unsigned long long c = 0, sz = 0, sy = 0, sx = 0;
+    if (i < rows) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) bbox64[6 * i + k] = bbox[6 * i + k];
+        if (i > 0) {
+            c = cnt[i]; sz = sums[3 * i]; sy = sums[3 * i + 1]; sx = sums[3 * i + 2];
+            const double dc = static_cast<double>(c);
+            cent[3 * i] = static_cast<double>(sz) / dc;
+            cent[3 * i + 1] = static_cast<double>(sy) / dc;
+            cent[3 * i + 2] = static_cast<double>(sx) / dc;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        c += __shfl_xor_sync(0xffffffffu, c, o); sz += __shfl_xor_sync(0xffffffffu, sz, o);
+        sy += __shfl_xor_sync(0xffffffffu, sy, o); sx += __shfl_xor_sync(0xffffffffu, sx, o);
+    }
+    if ((threadIdx.x & 31) == 0 && (c | sz | sy | sx)) {
+        atomicAdd(totals + 0, c); atomicAdd(totals + 1, sz); atomicAdd(totals + 2, sy); atomicAdd(totals + 3, sx);
+    }
+}
+
+// The table is returned in ONE pinned host block (counts | sums | bbox | centroids) taken from a small process-wide
+// pool, so that the device-to-host copy runs at PCIe speed and a second call of the same size pays neither page
+// faults nor cudaHostAlloc.  dlv_table_free returns the block to the pool.
+struct TableBox {
+    dlv_table pub;      // must stay the first member: dlv_table* <-> TableBox*
+    void* block;        // pinned block (nullptr: the arrays are plain calloc memory)
+    size_t cap;
+};
+struct PinnedBlock { void* p; size_t cap; bool busy; };
+static std::mutex g_pool_mu;
+static std::vector<PinnedBlock> g_pool;
+constexpr size_t kPoolKeep = 4;
+
+static void* pool_take(size_t bytes, size_t* cap_out) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    int best = -1;
+    for (size_t i = 0; i < g_pool.size(); ++i)
+        if (!g_pool[i].busy && g_pool[i].cap >= bytes && (best < 0 || g_pool[i].cap < g_pool[best].cap)) best = static_cast<int>(i);
+    if (best >= 0) { g_pool[best].busy = true; *cap_out = g_pool[best].cap; return g_pool[best].p; }
+    for (size_t i = 0; i < g_pool.size(); ++i)          // an idle block that is too small makes room for the new one
+        if (!g_pool[i].busy) { cudaFreeHost(g_pool[i].p); g_pool.erase(g_pool.begin() + i); break; }
+    void* p = nullptr;
+    const size_t cap = bytes + bytes / 4 + 4096;
+    if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    g_pool.push_back({p, cap, true});
+    *cap_out = cap;
+    return p;
+}
+static void pool_give(void* p) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    size_t idle = 0;
+    for (auto& b : g_pool) idle += b.busy ? 0 : 1;
+    for (size_t i = 0; i < g_pool.size(); ++i)
+        if (g_pool[i].p == p) {
+            if (idle >= kPoolKeep) { cudaFreeHost(p); g_pool.erase(g_pool.begin() + i); }
+            else g_pool[i].busy = false;
+            return;
+        }
+}
+void table_free(dlv_table* t) {
+    if (!t) return;
+    TableBox* b = reinterpret_cast<TableBox*>(t);
+    if (b->block) {
+        pool_give(b->block);
+    } else {
+        free(t->voxel_counts); free(t->sums); free(t->bbox); free(t->centroids);
+    }
+    free(b);
+}
+
 static unsigned nblocks(int64_t n, int bs) { return static_cast<unsigned>((n + bs - 1) / bs); }
 
 int ccl_run(Ctx* ctx, const uint8_t* mask, const int64_t shape[3], uint32_t* L, dlv_table** table_out) {
@@ -325,13 +448,18 @@ int ccl_run(Ctx* ctx, const uint8_t* mask, const int64_t shape[3], uint32_t* L, 
     g.rows = g.Z * g.Y;
     g.W = static_cast<int>((g.X + 31) / 32);
     const int64_t nwords = g.rows * g.W;
-    dlv_table* T = static_cast<dlv_table*>(calloc(1, sizeof(dlv_table)));
+    TableBox* box = static_cast<TableBox*>(calloc(1, sizeof(TableBox)));
+    dlv_table* T = &box->pub;
     uint32_t N = 0;
     int bg[6] = {static_cast<int>(g.Z), -1, static_cast<int>(g.Y), -1, static_cast<int>(g.X), -1};
     uint32_t *bits = nullptr, *rootbits = nullptr, *wprefix = nullptr, *bsum = nullptr, *n_dev = nullptr;
     int* bg_dev = nullptr;
     unsigned long long *cnt = nullptr, *sums = nullptr;
     int* bbox = nullptr;
+    long long* bbox64 = nullptr;
+    double* cent = nullptr;
+    unsigned long long* totals = nullptr;
+    unsigned long long tot[4] = {0, 0, 0, 0};
     int rc = 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr;
     float ms_a = 0.f, ms_b = 0.f;
@@ -349,11 +477,11 @@ int ccl_run(Ctx* ctx, const uint8_t* mask, const int64_t shape[3], uint32_t* L, 
         CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2)); CK(cudaEventCreate(&e3));
         CK(cudaEventRecord(e0, ctx->stream));
         {
-            const int64_t total_warps = g.rows * ((g.W + 3) / 4);
+            const int64_t total_warps = (g.rows * ((g.W + 3) / 4) + kInitSegs - 1) / kInitSegs;
             const unsigned grid = static_cast<unsigned>(std::min<int64_t>((total_warps + 7) / 8, static_cast<int64_t>(ctx->num_sms) * 32));
             ccl_init_kernel<<<grid, 256, 0, ctx->stream>>>(mask, g, bits, L, bg_dev);
         }
-        ccl_merge_kernel<<<nblocks(nwords, 256), 256, 0, ctx->stream>>>(g, bits, L);
+        ccl_merge_kernel<<<nblocks(nwords, kMergeThreads), kMergeThreads, 0, ctx->stream>>>(g, bits, L);
         ccl_compress_kernel<<<nblocks(nwords, 256), 256, 0, ctx->stream>>>(g, bits, L, rootbits);
         scan_block_sums_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, ctx->stream>>>(rootbits, nwords, bsum);
         scan_of_block_sums_kernel<<<1, kScanBlock, 0, ctx->stream>>>(bsum, nb, n_dev);
@@ -368,42 +496,56 @@ int ccl_run(Ctx* ctx, const uint8_t* mask, const int64_t shape[3], uint32_t* L, 
     {
         const size_t rows = static_cast<size_t>(N) + 1;
         T->n = N;
-        T->voxel_counts = static_cast<uint64_t*>(calloc(rows, sizeof(uint64_t)));
-        T->sums = static_cast<uint64_t*>(calloc(rows * 3, sizeof(uint64_t)));
-        T->bbox = static_cast<int64_t*>(calloc(rows * 6, sizeof(int64_t)));
-        if (!T->voxel_counts || !T->sums || !T->bbox) { set_error(ctx, "dlv_ccl: host table allocation failed"); rc = DLV_ERR_ARG; goto done; }
-        std::vector<int> hb(rows * 6);
         if (n > 0) {
+            // one pinned block: counts [rows] | sums [rows][3] | bbox [rows][6] | centroids [rows][3]
+            const size_t bytes = rows * (8 + 24 + 48 + 24);
+            box->block = pool_take(bytes, &box->cap);
+            if (!box->block) { set_error(ctx, "dlv_ccl: pinned host table allocation failed (%zu bytes)", bytes); rc = DLV_ERR_CUDA; goto done; }
+            uint8_t* hb = static_cast<uint8_t*>(box->block);
+            T->voxel_counts = reinterpret_cast<uint64_t*>(hb);
+            T->sums = reinterpret_cast<uint64_t*>(hb + rows * 8);
+            T->bbox = reinterpret_cast<int64_t*>(hb + rows * 32);
+            T->centroids = reinterpret_cast<double*>(hb + rows * 80);
             CK(dmalloc(ctx, &cnt, rows * 8));
             CK(dmalloc(ctx, &sums, rows * 24));
             CK(dmalloc(ctx, &bbox, rows * 24));
+            CK(dmalloc(ctx, &bbox64, rows * 48));
+            CK(dmalloc(ctx, &cent, rows * 24));
+            CK(dmalloc(ctx, &totals, 32));
             CK(cudaMemsetAsync(cnt, 0, rows * 8, ctx->stream));
             CK(cudaMemsetAsync(sums, 0, rows * 24, ctx->stream));
+            CK(cudaMemsetAsync(totals, 0, 32, ctx->stream));
             CK(cudaEventRecord(e2, ctx->stream));
             bbox_init_kernel<<<nblocks(rows, 256), 256, 0, ctx->stream>>>(bbox, rows, static_cast<int>(g.Z), static_cast<int>(g.Y), static_cast<int>(g.X));
             ccl_relabel_stats_kernel<<<nblocks(nwords, 256), 256, 0, ctx->stream>>>(g, bits, L, rootbits, wprefix, cnt, sums, bbox);
-            launches += 2;
+            ccl_table_finish_kernel<<<nblocks(rows, 256), 256, 0, ctx->stream>>>(rows, cnt, sums, bbox, bbox64, cent, totals);
+            launches += 3;
             CK(cudaGetLastError());
             CK(cudaEventRecord(e3, ctx->stream));
             CK(cudaMemcpyAsync(T->voxel_counts, cnt, rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaMemcpyAsync(T->sums, sums, rows * 24, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaMemcpyAsync(hb.data(), bbox, rows * 24, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(T->bbox, bbox64, rows * 48, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(T->centroids, cent, rows * 24, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(tot, totals, 32, cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
             CK(cudaEventElapsedTime(&ms_a, e0, e1));
             CK(cudaEventElapsedTime(&ms_b, e2, e3));
         } else {
-            for (size_t i = 0; i < rows; ++i) { hb[6 * i] = g.Z; hb[6 * i + 1] = -1; hb[6 * i + 2] = g.Y; hb[6 * i + 3] = -1; hb[6 * i + 4] = g.X; hb[6 * i + 5] = -1; }
+            T->voxel_counts = static_cast<uint64_t*>(calloc(rows, sizeof(uint64_t)));
+            T->sums = static_cast<uint64_t*>(calloc(rows * 3, sizeof(uint64_t)));
+            T->bbox = static_cast<int64_t*>(calloc(rows * 6, sizeof(int64_t)));
+            T->centroids = static_cast<double*>(calloc(rows * 3, sizeof(double)));
+            if (!T->voxel_counts || !T->sums || !T->bbox || !T->centroids) { set_error(ctx, "dlv_ccl: host table allocation failed"); rc = DLV_ERR_ARG; goto done; }
         }
-        for (size_t i = 0; i < rows * 6; ++i) T->bbox[i] = hb[i];
         // row 0 = background: everything that is not foreground (exact integer identities)
-        uint64_t fg = 0, sz = 0, sy = 0, sx = 0;
-        for (size_t i = 1; i < rows; ++i) { fg += T->voxel_counts[i]; sz += T->sums[3 * i]; sy += T->sums[3 * i + 1]; sx += T->sums[3 * i + 2]; }
         const uint64_t uz = g.Z, uy = g.Y, ux = g.X;
-        T->voxel_counts[0] = static_cast<uint64_t>(n) - fg;
-        T->sums[0] = (uz ? uy * ux * (uz * (uz - 1) / 2) : 0) - sz;
-        T->sums[1] = (uy ? uz * ux * (uy * (uy - 1) / 2) : 0) - sy;
-        T->sums[2] = (ux ? uz * uy * (ux * (ux - 1) / 2) : 0) - sx;
+        T->voxel_counts[0] = static_cast<uint64_t>(n) - tot[0];
+        T->sums[0] = (uz ? uy * ux * (uz * (uz - 1) / 2) : 0) - tot[1];
+        T->sums[1] = (uy ? uz * ux * (uy * (uy - 1) / 2) : 0) - tot[2];
+        T->sums[2] = (ux ? uz * uy * (ux * (ux - 1) / 2) : 0) - tot[3];
         for (int k = 0; k < 6; ++k) T->bbox[k] = bg[k];
+        for (int k = 0; k < 3; ++k)     // 0 / 0 -> NaN like numpy's divide
+            T->centroids[k] = static_cast<double>(T->sums[k]) / static_cast<double>(T->voxel_counts[0]);
     }
     ctx->ccl_ms = ms_a + ms_b;
     ctx->ccl_launches = launches;
@@ -411,12 +553,12 @@ int ccl_run(Ctx* ctx, const uint8_t* mask, const int64_t shape[3], uint32_t* L, 
 done:
 #undef CK
     dfree(ctx, bits); dfree(ctx, rootbits); dfree(ctx, wprefix); dfree(ctx, bsum); dfree(ctx, n_dev); dfree(ctx, bg_dev);
-    dfree(ctx, cnt); dfree(ctx, sums); dfree(ctx, bbox);
+    dfree(ctx, cnt); dfree(ctx, sums); dfree(ctx, bbox); dfree(ctx, bbox64); dfree(ctx, cent); dfree(ctx, totals);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     if (e2) cudaEventDestroy(e2);
     if (e3) cudaEventDestroy(e3);
-    if (rc) { dlv_table_free(T); return rc; }
+    if (rc) { table_free(T); return rc; }
     *table_out = T;
     return 0;
 }

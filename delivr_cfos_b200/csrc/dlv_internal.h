@@ -125,5 +125,10 @@ constexpr float kSkipLogit = -1000.f;   // sliding_window_inferer.py:199-200
 
 // dlv_ccl.cu
 int ccl_run(Ctx* ctx, const uint8_t* mask_dev, const int64_t shape[3], uint32_t* labels_dev, dlv_table** table_out);
+void table_free(dlv_table* t);
+
+// dlv_paint.cu
+int paint_boxes(Ctx* ctx, const void* mask_any, const int64_t shape[3], const int64_t* boxes_host, const int64_t* values_host,
+                int64_t n, int nch, int elem_bytes, void* const* out_any, int64_t chunk_voxels);
 
 }  // namespace dlv

@@ -35,7 +35,7 @@ typedef struct dlv_ctx dlv_ctx;
 #define DLV_ERR_STATE (-3)
 #define DLV_ERR_UNSUPPORTED (-4)
 
-#define DLV_ABI_VERSION 1
+#define DLV_ABI_VERSION 2
 
 /* ---- lifecycle -------------------------------------------------------- */
 int dlv_abi_version(void);
@@ -108,13 +108,17 @@ int dlv_segment(dlv_ctx* ctx, const void* volume_any, const dlv_seg_params* para
  * cc3d.statistics(labels, no_slice_conversion=True) (count_blobs.py:61,64,85).
  * 26-connectivity; labels 1..N numbered by each component's first voxel in
  * C-order raster scan.  Table rows 0..N (row 0 = background), exact integers;
- * centroid = sum/count is divided in fp64 by the host wrapper.
+ * centroid = (double)sum / (double)count, one IEEE fp64 division per coordinate
+ * (cc3d's definition; evaluated on the device, bit-identical to a host divide).
+ * The arrays live in one pinned host block owned by the library (re-used by
+ * later calls once the table is freed).
  */
 typedef struct dlv_table {
     int64_t n;              /* number of components N                        */
     uint64_t* voxel_counts; /* [N+1]                                         */
     uint64_t* sums;         /* [N+1][3]  sum of z, y, x                      */
     int64_t* bbox;          /* [N+1][6]  zmin,zmax,ymin,ymax,xmin,xmax incl. */
+    double* centroids;      /* [N+1][3]  z, y, x (NaN where count == 0)      */
 } dlv_table;
 
 /* mask: uint8 (Z,Y,X), host or device, non-zero = foreground.
@@ -200,6 +204,26 @@ const char* dlv_tiff_last_error(void);
  * (uint16 wrap-around); else threshold >= 0: v < threshold -> 0; else: unmasked. */
 int dlv_load_tiff_planes(dlv_ctx* ctx, const char* const* paths, int n, int64_t Y, int64_t X, int32_t threshold,
                          const uint8_t* mask_dev_or_null, uint16_t* slab_dev, int64_t SY, int64_t SX, int nthreads);
+
+/* ---- blob painter ----
+ * Replaces the per-cell bounding-box colouring loops of blob_highlighter.py:107-124 (R/G/B uint8 volumes),
+ * :143-151 (region-id uint16 volume) and blob_depthmap.py:198-207 (depth uint16 volume):
+ *     for k in 0..n-1:  out_c[box_k] = mask[box_k] * values[k][c]
+ * evaluated as out_c[v] = mask[v] * values[K(v)][c] with K(v) the LAST box in order that contains v (0 where no
+ * box does) - the same result, overlapping boxes included.  boxes_host int64 [n][6] = z0,z1,y0,y1,x0,x1 are numpy
+ * slice bounds (half-open, clipped at the array end; non-negative; already passed through pad_bb);
+ * values_host int64 [n][nch]; the product is truncated to the output width like numpy's cast on assignment.
+ * mask_any uint8 (Z,Y,X) and out_any[c] (Z,Y,X) of elem_bytes 1 (uint8) or 2 (uint16): host or device, every
+ * voxel of every output is written.  chunk_voxels <= 0: library default z-chunk (bounds the 4 B/voxel scratch). */
+int dlv_paint_boxes(dlv_ctx* ctx, const void* mask_any, const int64_t shape[3], const int64_t* boxes_host,
+                    const int64_t* values_host, int64_t n, int nch, int elem_bytes, void* const* out_any,
+                    int64_t chunk_voxels);
+
+/* Exact Euclidean distance transform of the down-sampled mask stack used to depth-code blobs
+ * (blob_depthmap.py:174-181): dist = scipy.ndimage.distance_transform_edt(np.pad(stack, 1), sampling)[1:-1,1:-1,1:-1],
+ * i.e. distance (in `sampling` units) of every non-zero voxel to the nearest zero voxel, the volume being surrounded
+ * by zeros.  nonzero_any uint8 (Z,Y,X) (stack != 0), dist_out_any float64 (Z,Y,X); host or device. */
+int dlv_edt(dlv_ctx* ctx, const void* nonzero_any, const int64_t shape[3], const double sampling[3], void* dist_out_any);
 
 #ifdef __cplusplus
 }

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", LIB_PATH], capture_output=True, text=True).stdout
     exported = sorted(set(re.findall(r" T (dlv_[a-z0-9_]+)", out)))
     assert exported == declared
-    assert lib.dlv_abi_version() == 1
+    assert lib.dlv_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_gpu():
@@ -57,7 +57,7 @@ def test_struct_layouts_match_header():
     from delivr_cfos_b200._lib import SegParams, SegStats, Table
     assert ctypes.sizeof(SegParams) == 3 * 8 + 3 * 8 + 3 * 4 + 4 + 4 + 4 + 4 + 4 + 8 + 4 + 4 + 4 + 4   # incl. alignment padding
     assert ctypes.sizeof(SegStats) == 4 * 8 + 3 * 8
-    assert ctypes.sizeof(Table) == 8 + 3 * 8
+    assert ctypes.sizeof(Table) == 8 + 4 * 8
 
 
 def test_update_idx_and_memmap_helpers(tmp_path):

@@ -1,14 +1,13 @@
 #!/bin/bash
-# bench variants: $1.. = env assignments to try, e.g. "DLV_IS_T=2" "DLV_IS_T=4"
-mkdir -p gpurun_out
+# usage: gpu_bench.sh "ENV=VAL ..." ...   one short cfg2 bench per environment setting (variant libraries via DLV_LIB)
 for v in "$@"; do
-  tag=$(echo "$v" | tr ' =' '__')
   echo "=== $v"
-  env $v timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
-  python - <<PY
-import json
-d=json.load(open("gpurun_out/bench_$tag.json"))
-r=d["roofline"]
-print("$v", "value", round(d["value"],4), "ms", round(d["ms_per_step"],1), "e2e", round(d["e2e"]["value"],4), "conv_ms", round(r["conv_ms_per_step"],1), "TF", round(r["achieved"],1), "unet_ms", round(r["unet_ms_per_step"],1), "clk", d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
+  env $v timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bv.json 2> gpurun_out/bv.err || { echo "FAILED"; tail -3 gpurun_out/bv.err; continue; }
+  python - "$v" <<'PY'
+import json, sys
+d = json.load(open("gpurun_out/bv.json")); r = d["roofline"]
+print(sys.argv[1], "value", round(d["value"], 4), "ms", round(d["ms_per_step"], 1), "e2e", round(d["e2e"]["value"], 4),
+      "conv_ms", round(r["conv_ms_per_step"], 1), "TF", round(r["achieved"], 1), "unet_ms", round(r["unet_ms_per_step"], 1),
+      "clk", d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
 PY
 done
