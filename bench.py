@@ -250,11 +250,11 @@ def main():
         "dtype": "bf16", "data": f"synthetic; {wdesc}",
         "config": {"workload": wl["name"], "window": list(ROI), "overlap": OVERLAP, "tta": False, "blend": "constant",
                    "windows_total": st["windows_total"], "windows_active": st["windows_active"],
-                   "components": tb["n"], "window_batch": wb or 32, "l2": "inputs larger than L2 (volume + accumulator >> 126 MB)"},
+                   "components": tb["n"], "window_batch": wb or 128, "l2": "inputs larger than L2 (volume + accumulator >> 126 MB)"},
         "gpu_launches": launches,
         "clocks": clocks,
         "e2e": {"value": nvox / (ms_e2e * 1e-3) / 1e9, "unit": "Gvoxels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (all conv/deconv launches of one step)",
+        "roofline": {"bound": "tensor", "kernel": "conv_is_kernel / conv_tc_kernel (all conv/deconv launches of one step; achieved and traffic are per step)",
                      "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_kind": f"bf16_tflops_sustained, {peak_kind}",
                      "conv_ms_per_step": conv_ms, "unet_ms_per_step": st["ms_unet"], "finalise_ms_per_step": st["ms_finalise"],

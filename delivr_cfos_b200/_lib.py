@@ -48,7 +48,7 @@ class Table(ctypes.Structure):
 # every symbol include/delivr_b200.h declares (tests check the .so exports exactly these)
 EXPORTS = [
     "dlv_abi_version", "dlv_init", "dlv_destroy", "dlv_last_error", "dlv_launch_count", "dlv_stream",
-    "dlv_synchronize", "dlv_set_conv_timing", "dlv_load_weights", "dlv_segment", "dlv_ccl", "dlv_table_free",
+    "dlv_synchronize", "dlv_set_conv_timing", "dlv_conv_time_ms", "dlv_load_weights", "dlv_segment", "dlv_ccl", "dlv_table_free",
     "dlv_ccl_last_timing", "dlv_unet_forward", "dlv_op_conv3d", "dlv_op_deconv", "dlv_op_finalise",
     "dlv_window_grid", "dlv_windows_active", "dlv_seg_accumulate", "dlv_seg_average", "dlv_op_finalise_slab",
     "dlv_ccl_boundary_pairs", "dlv_relabel", "dlv_tiff_info", "dlv_tiff_read_u16", "dlv_tiff_last_error",
@@ -83,6 +83,8 @@ def load_library():
     L.dlv_synchronize.argtypes = [c_vp]
     L.dlv_set_conv_timing.restype = ctypes.c_int
     L.dlv_set_conv_timing.argtypes = [c_vp, ctypes.c_int]
+    L.dlv_conv_time_ms.restype = ctypes.c_int
+    L.dlv_conv_time_ms.argtypes = [c_vp, P(ctypes.c_double)]
     L.dlv_load_weights.restype = ctypes.c_int
     L.dlv_load_weights.argtypes = [c_vp, ctypes.c_int, P(ctypes.c_char_p), P(c_vp), P(c_i64)]
     L.dlv_segment.restype = ctypes.c_int
@@ -210,6 +212,11 @@ class Context:
 
     def set_conv_timing(self, enable):
         self._check(self._L.dlv_set_conv_timing(self._h, int(bool(enable))), "dlv_set_conv_timing")
+
+    def conv_time_ms(self):
+        ms = ctypes.c_double()
+        self._check(self._L.dlv_conv_time_ms(self._h, ctypes.byref(ms)), "dlv_conv_time_ms")
+        return ms.value
 
     # ---- weights (inference.py:190-200,217-222)
     def load_weights(self, state_dict):

@@ -96,6 +96,13 @@ int dlv_synchronize(dlv_ctx* c) {
 int dlv_set_conv_timing(dlv_ctx* c, int enable) {
     if (!c) return DLV_ERR_ARG;
     C(c)->time_convs = enable != 0;
+    if (enable) C(c)->conv_ms = 0.0;
+    return DLV_OK;
+}
+
+int dlv_conv_time_ms(const dlv_ctx* c, double* ms_out) {
+    if (!c || !ms_out) return DLV_ERR_ARG;
+    *ms_out = C(c)->conv_ms;
     return DLV_OK;
 }
 

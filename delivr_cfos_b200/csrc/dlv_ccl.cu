@@ -61,84 +61,78 @@ struct BgBox { int zmin, zmax, ymin, ymax, xmin, xmax; };
 // kInitSegs mask loads are issued before any of them is used, so every thread keeps that many loads in flight
 // (one load per thread and iteration left the kernel latency-bound at 2.6 TB/s).
 constexpr int kInitSegs = 4;
-__global__ void ccl_init_kernel(const uint8_t* __restrict__ mask, CclGeom g, uint32_t* __restrict__ bits,
+__global__ void __launch_bounds__(256, 5) ccl_init_kernel(const uint8_t* __restrict__ mask, CclGeom g, uint32_t* __restrict__ bits,
                                 uint32_t* __restrict__ L, int* __restrict__ bgbox) {
     const int lane = threadIdx.x & 31;
     const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
     const int segs = (g.W + 3) / 4;                       // 128-voxel segments per row
-    const int64_t total = g.rows * segs;
-    const int64_t total_it = (total + kInitSegs - 1) / kInitSegs;
     const bool vec = (g.X % 4) == 0 && (reinterpret_cast<uintptr_t>(mask) & 3u) == 0;
+    const uint32_t uY = static_cast<uint32_t>(g.Y);
     BgBox bb = {INT_MAX, -1, INT_MAX, -1, INT_MAX, -1};
-    for (int64_t it4 = warp_global; it4 < total_it; it4 += nwarps) {
-        uint32_t nibs[kInitSegs];
-        int64_t rr[kInitSegs];
-        int sgs[kInitSegs];
+    // rows are dealt to warps; the (z, y) decode is one 32-bit division per row (64-bit divisions per segment made
+    // this kernel instruction-bound)
+    for (int64_t r = warp_global; r < g.rows; r += nwarps) {
+        const int z = static_cast<int>(static_cast<uint32_t>(r) / uY), y = static_cast<int>(static_cast<uint32_t>(r) - static_cast<uint32_t>(z) * uY);
+        const int64_t base = r * g.X;
+        for (int sg0 = 0; sg0 < segs; sg0 += kInitSegs) {
+            uint32_t nibs[kInitSegs];
 #pragma unroll
-        for (int u = 0; u < kInitSegs; ++u) {
-            const int64_t it = it4 * kInitSegs + u;
-            nibs[u] = 0;
-            rr[u] = -1; sgs[u] = 0;
-            if (it >= total) continue;
-            const int64_t r = it / segs;
-            const int sg = static_cast<int>(it - r * segs);
-            rr[u] = r; sgs[u] = sg;
-            const int64_t x0 = static_cast<int64_t>(sg) * 128 + lane * 4;
-            const int64_t base = r * g.X;
-            if (vec) {
-                if (x0 < g.X) {
-                    const uint32_t m = __ldcs(reinterpret_cast<const uint32_t*>(mask + base + x0));
-                    nibs[u] = ((m & 0xFFu) ? 1u : 0u) | ((m & 0xFF00u) ? 2u : 0u) | ((m & 0xFF0000u) ? 4u : 0u) | ((m & 0xFF000000u) ? 8u : 0u);
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (x0 + j < g.X && mask[base + x0 + j]) nibs[u] |= 1u << j;
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < kInitSegs; ++u) {
-            if (rr[u] < 0) continue;                       // warp-uniform
-            const int64_t r = rr[u];
-            const int sg = sgs[u];
-            const int64_t x0 = static_cast<int64_t>(sg) * 128 + lane * 4;
-            const int64_t base = r * g.X;
-            // assemble the 32-bit word of this lane's 8-lane group
-            uint32_t word = nibs[u] << (4 * (lane & 7));
-            word |= __shfl_xor_sync(0xffffffffu, word, 1);
-            word |= __shfl_xor_sync(0xffffffffu, word, 2);
-            word |= __shfl_xor_sync(0xffffffffu, word, 4);
-            const int wi = sg * 4 + (lane >> 3);
-            if ((lane & 7) == 0 && wi < g.W) bits[r * g.W + wi] = word;
-            if (x0 < g.X) {
-                const uint32_t wbase = static_cast<uint32_t>(base + static_cast<int64_t>(wi) * 32);   // 0-based index of bit 0
-                uint32_t lab[4];
-                int nbg = 0, bx0 = INT_MAX, bx1 = -1;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int b = 4 * (lane & 7) + j;
-                    if ((word >> b) & 1u) {
-                        const uint32_t zeros_below = ~word & ((1u << b) - 1u);
-                        const int s = zeros_below ? (32 - __clz(zeros_below)) : 0;
-                        lab[j] = wbase + s + 1u;
-                    } else {
-                        lab[j] = 0u;
-                        if (x0 + j < g.X) { ++nbg; bx0 = min(bx0, static_cast<int>(x0 + j)); bx1 = max(bx1, static_cast<int>(x0 + j)); }
-                    }
-                }
+            for (int u = 0; u < kInitSegs; ++u) {
+                nibs[u] = 0;
+                const int64_t x0 = static_cast<int64_t>(sg0 + u) * 128 + lane * 4;
+                if (sg0 + u >= segs) continue;
                 if (vec) {
-                    *reinterpret_cast<uint4*>(L + base + x0) = make_uint4(lab[0], lab[1], lab[2], lab[3]);
+                    if (x0 < g.X) {
+                        const uint32_t m = __ldcs(reinterpret_cast<const uint32_t*>(mask + base + x0));
+                        nibs[u] = ((m & 0xFFu) ? 1u : 0u) | ((m & 0xFF00u) ? 2u : 0u) | ((m & 0xFF0000u) ? 4u : 0u) | ((m & 0xFF000000u) ? 8u : 0u);
+                    }
                 } else {
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        if (x0 + j < g.X) L[base + x0 + j] = lab[j];
+                        if (x0 + j < g.X && mask[base + x0 + j]) nibs[u] |= 1u << j;
                 }
-                if (nbg) {
-                    const int z = static_cast<int>(r / g.Y), y = static_cast<int>(r - static_cast<int64_t>(z) * g.Y);
-                    bb.zmin = min(bb.zmin, z); bb.zmax = max(bb.zmax, z);
-                    bb.ymin = min(bb.ymin, y); bb.ymax = max(bb.ymax, y);
-                    bb.xmin = min(bb.xmin, bx0); bb.xmax = max(bb.xmax, bx1);
+            }
+#pragma unroll
+            for (int u = 0; u < kInitSegs; ++u) {
+                const int sg = sg0 + u;
+                if (sg >= segs) break;                         // warp-uniform
+                const int64_t x0 = static_cast<int64_t>(sg) * 128 + lane * 4;
+                // assemble the 32-bit word of this lane's 8-lane group
+                uint32_t word = nibs[u] << (4 * (lane & 7));
+                word |= __shfl_xor_sync(0xffffffffu, word, 1);
+                word |= __shfl_xor_sync(0xffffffffu, word, 2);
+                word |= __shfl_xor_sync(0xffffffffu, word, 4);
+                const int wi = sg * 4 + (lane >> 3);
+                if ((lane & 7) == 0 && wi < g.W) bits[r * g.W + wi] = word;
+                if (x0 < g.X) {
+                    const uint32_t wbase = static_cast<uint32_t>(base + static_cast<int64_t>(wi) * 32);   // 0-based index of bit 0
+                    uint32_t lab[4];
+                    int nbg = 0, bx0 = INT_MAX, bx1 = -1;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int b = 4 * (lane & 7) + j;
+                        if ((word >> b) & 1u) {
+                            const uint32_t zeros_below = ~word & ((1u << b) - 1u);
+                            const int s = zeros_below ? (32 - __clz(zeros_below)) : 0;
+                            lab[j] = wbase + s + 1u;
+                        } else {
+                            lab[j] = 0u;
+                            if (x0 + j < g.X) { ++nbg; bx0 = min(bx0, static_cast<int>(x0 + j)); bx1 = max(bx1, static_cast<int>(x0 + j)); }
+                        }
+                    }
+                    if (vec) {
+                        __stcs(reinterpret_cast<uint4*>(L + base + x0), make_uint4(lab[0], lab[1], lab[2], lab[3]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (x0 + j < g.X) L[base + x0 + j] = lab[j];
+                    }
+                    if (nbg) {
+                        bb.zmin = min(bb.zmin, z); bb.zmax = max(bb.zmax, z);
+                        bb.ymin = min(bb.ymin, y); bb.ymax = max(bb.ymax, y);
+                        bb.xmin = min(bb.xmin, bx0); bb.xmax = max(bb.xmax, bx1);
+                    }
                 }
             }
         }
@@ -185,9 +179,9 @@ __global__ void __launch_bounds__(kMergeThreads) ccl_merge_kernel(CclGeom g, con
             const unsigned i = atomicAdd(&qn, 1u);
             if (i < kMergeQueue) queue[i] = make_uint2(a, b); else uf_union(L, a, b);
         };
-        const int64_t r = t / g.W;
+        const int64_t r = static_cast<uint32_t>(t) / static_cast<uint32_t>(g.W);      // t < 2^32 (checked in ccl_run)
         const int w = static_cast<int>(t - r * g.W);
-        const int64_t z = r / g.Y, y = r - z * g.Y;
+        const int64_t z = static_cast<uint32_t>(r) / static_cast<uint32_t>(g.Y), y = r - z * g.Y;
         const uint32_t vbase = static_cast<uint32_t>(r * g.X + static_cast<int64_t>(w) * 32) + 1u;   // label of bit 0
         // raster-predecessor rows: (z, y-1), (z-1, y-1), (z-1, y), (z-1, y+1)
         const int64_t nrows[4] = {r - 1, r - g.Y - 1, r - g.Y, r - g.Y + 1};
@@ -235,7 +229,7 @@ __global__ void ccl_compress_kernel(CclGeom g, const uint32_t* __restrict__ bits
     const uint32_t cur = bits[t];
     uint32_t rb = 0;
     if (cur) {
-        const int64_t r = t / g.W;
+        const int64_t r = static_cast<uint32_t>(t) / static_cast<uint32_t>(g.W);
         const int w = static_cast<int>(t - r * g.W);
         const int64_t vb0 = r * g.X + static_cast<int64_t>(w) * 32;     // 0-based index of bit 0
         DLV_FOR_RUNS64(static_cast<unsigned long long>(cur), a, len) {
@@ -323,15 +317,15 @@ __global__ void ccl_relabel_stats_kernel(CclGeom g, const uint32_t* __restrict__
     if (t >= g.rows * g.W) return;
     const uint32_t cur = bits[t];
     if (!cur) return;
-    const int64_t r = t / g.W;
+    const int64_t r = static_cast<uint32_t>(t) / static_cast<uint32_t>(g.W);
     const int w = static_cast<int>(t - r * g.W);
-    const int z = static_cast<int>(r / g.Y), y = static_cast<int>(r - static_cast<int64_t>(z) * g.Y);
+    const int z = static_cast<int>(static_cast<uint32_t>(r) / static_cast<uint32_t>(g.Y)), y = static_cast<int>(r - static_cast<int64_t>(z) * g.Y);
     const int64_t vb0 = r * g.X + static_cast<int64_t>(w) * 32;
     DLV_FOR_RUNS64(static_cast<unsigned long long>(cur), a, len) {
         const uint32_t lbl = static_cast<uint32_t>(vb0 + a) + 1u;
         const uint32_t root = ((rootbits[t] >> a) & 1u) ? lbl : L[vb0 + a];
         const int64_t ri = static_cast<int64_t>(root) - 1;
-        const int64_t rr = ri / g.X;
+        const int64_t rr = static_cast<uint32_t>(ri) / static_cast<uint32_t>(g.X);
         const int rx = static_cast<int>(ri - rr * g.X);
         const int64_t rw = rr * g.W + (rx >> 5);
         const uint32_t rank = wprefix[rw] + __popc(rootbits[rw] & ((1u << (rx & 31)) - 1u)) + 1u;
@@ -477,7 +471,7 @@ int ccl_run(Ctx* ctx, const uint8_t* mask, const int64_t shape[3], uint32_t* L, 
         CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2)); CK(cudaEventCreate(&e3));
         CK(cudaEventRecord(e0, ctx->stream));
         {
-            const int64_t total_warps = (g.rows * ((g.W + 3) / 4) + kInitSegs - 1) / kInitSegs;
+            const int64_t total_warps = g.rows;     // one row per warp and iteration
             const unsigned grid = static_cast<unsigned>(std::min<int64_t>((total_warps + 7) / 8, static_cast<int64_t>(ctx->num_sms) * 32));
             ccl_init_kernel<<<grid, 256, 0, ctx->stream>>>(mask, g, bits, L, bg_dev);
         }

@@ -59,21 +59,64 @@ __global__ void erode_x_kernel(const uint16_t* __restrict__ vol, PostGeom g, int
     }
 }
 
-// ---- pass Y: thread per (plane, x) column, forward then backward min-plus sweep, in place
+// ---- pass Y: forward then backward min-plus sweep down a column, in place.
+// The sweep is a serial chain, but its LOADS do not depend on it: kSweepBatch rows are fetched before the chain
+// consumes them (a load issued after the previous row's store to the same array is not hoisted by the compiler, which
+// left every row paying a full memory round trip).  erode_y4 handles 4 adjacent columns per thread with byte-wise
+// SIMD min / saturating add on 32-bit words (X % 4 == 0); erode_y is the scalar form for other widths.
+constexpr int kSweepBatch = 8;
+__global__ void erode_y4_kernel(uint8_t* __restrict__ dist, PostGeom g) {
+    const int64_t x4 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t z = blockIdx.y;
+    const int64_t pitch = g.X >> 2;
+    if (x4 >= pitch) return;
+    uint32_t* col = reinterpret_cast<uint32_t*>(dist + z * g.Y * g.X) + x4;
+    const uint32_t cap4 = static_cast<uint32_t>(g.cap) * 0x01010101u, one4 = 0x01010101u;
+    uint32_t d = cap4, v[kSweepBatch];
+    for (int64_t y0 = 0; y0 < g.Y; y0 += kSweepBatch) {
+#pragma unroll
+        for (int k = 0; k < kSweepBatch; ++k) v[k] = (y0 + k < g.Y) ? col[(y0 + k) * pitch] : 0u;
+#pragma unroll
+        for (int k = 0; k < kSweepBatch; ++k) {
+            d = __vminu4(v[k], __vminu4(__vaddus4(d, one4), cap4));
+            if (y0 + k < g.Y) col[(y0 + k) * pitch] = d;
+        }
+    }
+    d = cap4;
+    for (int64_t y0 = g.Y - 1; y0 >= 0; y0 -= kSweepBatch) {
+#pragma unroll
+        for (int k = 0; k < kSweepBatch; ++k) v[k] = (y0 - k >= 0) ? col[(y0 - k) * pitch] : 0u;
+#pragma unroll
+        for (int k = 0; k < kSweepBatch; ++k) {
+            d = __vminu4(v[k], __vminu4(__vaddus4(d, one4), cap4));
+            if (y0 - k >= 0) col[(y0 - k) * pitch] = d;
+        }
+    }
+}
 __global__ void erode_y_kernel(uint8_t* __restrict__ dist, PostGeom g) {
     const int64_t x = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t z = blockIdx.y;
     if (x >= g.X) return;
     uint8_t* col = dist + z * g.Y * g.X + x;
-    int d = g.cap;
-    for (int64_t y = 0; y < g.Y; ++y) {
-        d = min(static_cast<int>(col[y * g.X]), min(d + 1, g.cap));
-        col[y * g.X] = static_cast<uint8_t>(d);
+    int d = g.cap, v[kSweepBatch];
+    for (int64_t y0 = 0; y0 < g.Y; y0 += kSweepBatch) {
+#pragma unroll
+        for (int k = 0; k < kSweepBatch; ++k) v[k] = (y0 + k < g.Y) ? col[(y0 + k) * g.X] : 0;
+#pragma unroll
+        for (int k = 0; k < kSweepBatch; ++k) {
+            d = min(v[k], min(d + 1, g.cap));
+            if (y0 + k < g.Y) col[(y0 + k) * g.X] = static_cast<uint8_t>(d);
+        }
     }
     d = g.cap;
-    for (int64_t y = g.Y - 1; y >= 0; --y) {
-        d = min(static_cast<int>(col[y * g.X]), min(d + 1, g.cap));
-        col[y * g.X] = static_cast<uint8_t>(d);
+    for (int64_t y0 = g.Y - 1; y0 >= 0; y0 -= kSweepBatch) {
+#pragma unroll
+        for (int k = 0; k < kSweepBatch; ++k) v[k] = (y0 - k >= 0) ? col[(y0 - k) * g.X] : 0;
+#pragma unroll
+        for (int k = 0; k < kSweepBatch; ++k) {
+            d = min(v[k], min(d + 1, g.cap));
+            if (y0 - k >= 0) col[(y0 - k) * g.X] = static_cast<uint8_t>(d);
+        }
     }
 }
 
@@ -93,22 +136,38 @@ __global__ void erode_z_final_kernel(uint8_t* __restrict__ dist, PostGeom g, con
     if (l0 >= l1) return;
     const int64_t pstride = g.Y * g.X;
     uint8_t* col = dist + y * g.X + x;
-    int d = g.cap;
-    for (int64_t z = l0; z < l1; ++z) {
-        d = min(static_cast<int>(col[z * pstride]), min(d + 1, g.cap));
-        col[z * pstride] = static_cast<uint8_t>(d);
+    int d = g.cap, v[kSweepBatch];
+    for (int64_t z0 = l0; z0 < l1; z0 += kSweepBatch) {
+#pragma unroll
+        for (int k = 0; k < kSweepBatch; ++k) v[k] = (z0 + k < l1) ? col[(z0 + k) * pstride] : 0;
+#pragma unroll
+        for (int k = 0; k < kSweepBatch; ++k) {
+            d = min(v[k], min(d + 1, g.cap));
+            if (z0 + k < l1) col[(z0 + k) * pstride] = static_cast<uint8_t>(d);
+        }
     }
     d = g.cap;
-    for (int64_t z = l1 - 1; z >= l0; --z) {
-        d = min(static_cast<int>(col[z * pstride]), min(d + 1, g.cap));
-        const int64_t gz = gz0 + z;
-        if (gz >= oz0 && gz < oz1) {
-            // the reference keeps averaged logits in fp16 (inference.py:242,295) and applies an fp32 sigmoid (:65-68)
-            const float a = __half2float(__float2half_rn(avg[(z * g.SY + y) * g.SX + x]));
-            const float s = 1.f / (1.f + expf(-a));
-            const int64_t o = ((gz - oz0) * g.Y + y) * g.X + x;
-            if (sig) sig[o] = s;
-            bin[o] = static_cast<uint8_t>((s >= thr) && (d > iters));
+    for (int64_t z0 = l1 - 1; z0 >= l0; z0 -= kSweepBatch) {
+        float a[kSweepBatch];
+#pragma unroll
+        for (int k = 0; k < kSweepBatch; ++k) {
+            const int64_t z = z0 - k, gz = gz0 + z;
+            v[k] = (z >= l0) ? col[z * pstride] : 0;
+            a[k] = (z >= l0 && gz >= oz0 && gz < oz1) ? avg[(z * g.SY + y) * g.SX + x] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < kSweepBatch; ++k) {
+            const int64_t z = z0 - k, gz = gz0 + z;
+            if (z < l0) break;
+            d = min(v[k], min(d + 1, g.cap));
+            if (gz >= oz0 && gz < oz1) {
+                // the reference keeps averaged logits in fp16 (inference.py:242,295) and applies an fp32 sigmoid (:65-68)
+                const float ah = __half2float(__float2half_rn(a[k]));
+                const float s = 1.f / (1.f + expf(-ah));
+                const int64_t o = ((gz - oz0) * g.Y + y) * g.X + x;
+                if (sig) sig[o] = s;
+                bin[o] = static_cast<uint8_t>((s >= thr) && (d > iters));
+            }
         }
     }
 }
@@ -128,7 +187,10 @@ int post_finalise_slab(Ctx* ctx, const float* avg, const uint16_t* vol, int64_t 
     const size_t smem = static_cast<size_t>(wpb) * nwords * 4;
     const int64_t rows = nplanes * g.Y;
     erode_x_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, smem, ctx->stream>>>(vol, g, nwords, dist);
-    erode_y_kernel<<<dim3(static_cast<unsigned>((g.X + 127) / 128), static_cast<unsigned>(nplanes)), 128, 0, ctx->stream>>>(dist, g);
+    if ((g.X & 3) == 0)     // dist comes from the pool (256 B aligned) and rows are X bytes: every row is word aligned
+        erode_y4_kernel<<<dim3(static_cast<unsigned>((g.X / 4 + 63) / 64), static_cast<unsigned>(nplanes)), 64, 0, ctx->stream>>>(dist, g);
+    else
+        erode_y_kernel<<<dim3(static_cast<unsigned>((g.X + 127) / 128), static_cast<unsigned>(nplanes)), 128, 0, ctx->stream>>>(dist, g);
     const int64_t Zreal = sr[0];
     const int64_t bp = block_planes > 0 ? block_planes : Zreal;
     const int64_t first_block = gz0 / bp;

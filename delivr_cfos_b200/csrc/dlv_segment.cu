@@ -140,12 +140,27 @@ static int blend_weights(Ctx* ctx, int blend_mode, const int32_t roi[3], BlendWe
     return 0;
 }
 
+// Library default for the windows per launch sequence: 128 windows of the reference's 96 x 96 x 64 (larger batches
+// fill the 148 SMs on the low-resolution layers and shorten the share of every kernel's ramp-down tail: cfg2 0.449 /
+// 0.464 / 0.466 / 0.470 Gvoxels/s at 32 / 64 / 96 / 128 windows), scaled inversely
+// with the window volume and kept below half of the free device memory (~480 B of activations per window voxel).
+static int default_window_batch(const int32_t roi[3]) {
+    const int64_t vox = static_cast<int64_t>(roi[0]) * roi[1] * roi[2];
+    int64_t b = std::max<int64_t>(1, std::min<int64_t>(512, (128LL * 96 * 96 * 64) / std::max<int64_t>(vox, 1)));
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+        b = std::max<int64_t>(1, std::min<int64_t>(b, static_cast<int64_t>(free_b / 2) / (480 * vox)));
+    else
+        cudaGetLastError();
+    return static_cast<int>(b);
+}
+
 // run the scheduled windows (origins local to `slab`) and blend them into acc (int32, same extent as slab)
 int seg_accumulate(Ctx* ctx, const uint16_t* slab, int64_t SY, int64_t SX, const std::vector<WindowDesc>& sched,
                    const int32_t roi[3], int batch, int blend_mode, int32_t* acc) {
     if (!ctx->net.loaded) { set_error(ctx, "call dlv_load_weights first"); return DLV_ERR_STATE; }
     if (sched.empty()) return 0;
-    batch = batch > 0 ? batch : 32;
+    batch = batch > 0 ? batch : default_window_batch(roi);
     int rc = engine_prepare(ctx, roi, batch);
     if (rc) return rc;
     batch = engine_batch_capacity(ctx);
@@ -228,7 +243,7 @@ int segment_run(Ctx* ctx, const void* volume_any, const dlv_seg_params* P, void*
         }
     }
     if (P->overlap < 0.f || P->overlap >= 1.f) { set_error(ctx, "overlap must be >= 0 and < 1."); return DLV_ERR_ARG; }
-    const int batch = P->window_batch > 0 ? P->window_batch : 32;
+    const int batch = P->window_batch > 0 ? P->window_batch : default_window_batch(P->roi);
     // DLV_TRACE=1: host wall clock per phase on stderr (adds a stream synchronisation at every mark)
     static const bool trace = getenv("DLV_TRACE") != nullptr;
     auto t_prev = std::chrono::steady_clock::now();

@@ -448,6 +448,17 @@ def balanced_plan(ctx, comm, shape, roi, overlap, planes_fn):
     return SlabPlan(shape, roi, overlap, comm.world, layer_weights=per_layer), per_layer
 
 
+def _roofline(B, workload, windows_active, conv_ms_max, world):
+    tf_peak, _, peak_kind = B.peaks()
+    flop = 2.0 * B.MAC_PER_PATCH_VOXEL * windows_active * B.ROI[0] * B.ROI[1] * B.ROI[2]
+    achieved = flop / (conv_ms_max * 1e-3) / 1e12 / world if conv_ms_max > 0 else 0.0
+    traffic, src = B.conv_traffic(workload, windows_active)
+    return {"bound": "tensor", "kernel": "conv_is_kernel / conv_tc_kernel (all conv/deconv launches of one step)",
+            "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s per GPU", "frac": achieved / tf_peak,
+            "traffic": traffic, "traffic_source": src, "peak_kind": f"bf16_tflops_sustained, {peak_kind}",
+            "conv_ms_per_step_max_rank": conv_ms_max}
+
+
 def bench_main(args, rank, local_rank, world):
     """bench.py --gpus N: weak scaling - an N-times taller volume (N cfg2-sized shares stacked along z), window
     z-layers partitioned over the ranks by active-window count."""
@@ -533,6 +544,13 @@ def bench_main(args, rank, local_rank, world):
     ms_e2e, table_e2e = timed(True, args.steps)
     io = torch.tensor([hslab.numel() * 2, hbin.numel()], device=dev, dtype=torch.int64)
     dist.all_reduce(io)
+    # roofline of the tcgen05 convolutions: one extra step with per-launch event timing on every rank; the job's
+    # algorithmic FLOP / the slowest rank's conv time, per GPU
+    ctx.set_conv_timing(True)
+    step(False)
+    conv = torch.tensor([ctx.conv_time_ms()], device=dev, dtype=torch.float64)
+    ctx.set_conv_timing(False)
+    dist.all_reduce(conv, op=dist.ReduceOp.MAX)
     if rank == 0:
         nvox = int(np.prod(shape))
         v = nvox / (ms * 1e-3) / 1e9
@@ -551,5 +569,6 @@ def bench_main(args, rank, local_rank, world):
             "e2e": {"value": nvox / (ms_e2e * 1e-3) / 1e9, "unit": "Gvoxels/s", "h2d_bytes_per_step": int(io[0].item()),
                     "d2h_bytes_per_step": int(io[1].item()) + nrow * (8 + 24 + 48),
                     "note": "per-rank pinned host slab in, pinned host binaries + merged table out"},
+            "roofline": _roofline(B, args.workload, int(per_layer.sum()), float(conv.item()), world),
         }))
     dist.destroy_process_group()

@@ -51,6 +51,9 @@ int dlv_synchronize(dlv_ctx* ctx);
 /* enable != 0: bracket every convolution launch with CUDA events and accumulate the device time into
  * dlv_seg_stats.ms_conv (serialises the stream; used by bench.py for the roofline line only). */
 int dlv_set_conv_timing(dlv_ctx* ctx, int enable);
+/* Device time accumulated in the convolution kernels since timing was last enabled / the last dlv_segment started
+ * (the slab-level entry points do not reset it). */
+int dlv_conv_time_ms(const dlv_ctx* ctx, double* ms_out);
 
 /* ---- network weights --------------------------------------------------
  * Replaces BasicUNet(...) + load_state_dict(checkpoint["state_dict"])

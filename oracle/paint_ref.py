@@ -26,7 +26,8 @@ def pad_bb(bb, stack_shape):
 
 def paint_boxes_ref(mask, boxes, values, dtype):
     """The literal loop: for k in order, out_c[box_k] = mask[box_k] * values[k][c] (numpy cast on assignment)."""
-    values = np.asarray(values, dtype=np.int64).reshape(len(boxes), -1)
+    values = np.asarray(values, dtype=np.int64)
+    values = values.reshape(len(boxes), values.shape[1] if values.ndim == 2 else 1)
     outs = [np.zeros(mask.shape, dtype=dtype) for _ in range(values.shape[1])]
     for k, bb in enumerate(boxes):
         sl = (slice(int(bb[0]), int(bb[1])), slice(int(bb[2]), int(bb[3])), slice(int(bb[4]), int(bb[5])))

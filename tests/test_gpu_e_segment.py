@@ -119,3 +119,33 @@ def test_against_oracle_random_weights(shape, roi, tta, tmp_path):
     assert agree >= 0.999
     assert (d <= 1.0 + 0.02 * np.abs(ref[mask])).all()
     assert np.array_equal(b[~mask], np.zeros_like(b[~mask]))
+
+
+@pytest.mark.parametrize("shape,roi,overlap", [((60, 90, 70), (32, 32, 32), 0.25), ((40, 70, 66), (32, 32, 32), 0.75),
+                                               ((70, 130, 64), (64, 64, 64), 0.25), ((50, 100, 48), (48, 32, 16), 0.75),
+                                               ((130, 140, 64), (128, 128, 64), 0.5)])
+def test_window_and_overlap_sweep_against_oracle(shape, roi, overlap):
+    """BASELINE.json configs[4] (patch-size / overlap sweep) at oracle-sized volumes: window grid of
+    sliding_window_inferer.py:140-143 for overlaps 0.25 / 0.5 / 0.75 and other window shapes, averaged logits and
+    binaries against the torch-fp32 restatement."""
+    from gpu_common import ctx_with
+    ctx, sd, onet = ctx_with("random")
+    vol = P.synth_volume(shape, 41, roi=roi)
+    vol[:shape[0], :shape[1], :shape[2]][vol[:shape[0], :shape[1], :shape[2]] == 0] = 500
+    vol[:6] = 0
+    shape_pad = vol.shape
+    pred = lambda t: onet(t.cuda()).cpu()
+    avg = P.infer_average(vol, roi, overlap, pred, 4)
+    ref_b = P.create_binaries(avg, vol, shape, 0.5)
+    b = np.empty(shape, dtype=np.uint8)
+    mine = np.empty(shape_pad, dtype=np.float32)
+    st = ctx.segment(vol, shape_pad, shape, roi, b, overlap=overlap, avg_logits_out=mine)
+    grid = [len(s) for s in __import__("delivr_cfos_b200")._lib.window_grid(shape_pad, roi, overlap)]
+    assert st["windows_total"] == grid[0] * grid[1] * grid[2]
+    mask = P.ccl_ref.erode6((vol[:shape[0], :shape[1], :shape[2]] > 0).astype(np.uint8), 30) > 0
+    ref = avg[:shape[0], :shape[1], :shape[2]].astype(np.float32)
+    d = np.abs(mine[:shape[0], :shape[1], :shape[2]] - ref)[mask]
+    print("windows", st["windows_total"], "agreement", (b == ref_b).mean(), "max diff", d.max() if d.size else None)
+    assert mask.any()
+    assert (b == ref_b).mean() >= 0.999
+    assert (d <= 1.0 + 0.02 * np.abs(ref[mask])).all()
