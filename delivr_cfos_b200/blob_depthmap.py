@@ -21,6 +21,7 @@ import numpy as np
 
 from .blob_highlighter import _write_planes, padded_boxes
 from .count_blobs import _context, load_cached_stats
+from .slabs import ccl_any_size
 
 
 def blob_depths(stats, distances, settings):
@@ -51,7 +52,7 @@ def depth_map_blobs(settings, brain, stack_shape, device=0):
     print(f"{datetime.datetime.now()} : calculating connected-component analysis")
     cached = load_cached_stats(settings, brain)
     if not cached:
-        table = ctx.ccl(mask, shape)
+        table = ccl_any_size(ctx, mask, shape)
         stats = {"voxel_counts": table["voxel_counts"], "bounding_boxes": np.array(table["bounding_boxes"]),
                  "centroids": table["centroids"]}
     else:

@@ -22,6 +22,7 @@ import shutil
 import numpy as np
 
 from .count_blobs import _context, load_cached_stats
+from .slabs import ccl_any_size
 
 
 def pad_bb(bb, stack_shape):
@@ -89,7 +90,7 @@ def blob_highlighter(settings, brain_item, stack_shape, device=0):
     ctx = _context(device)
     cached = load_cached_stats(settings, brain)
     if not cached:
-        table = ctx.ccl(np.ascontiguousarray(bin_img), shape)
+        table = ccl_any_size(ctx, np.ascontiguousarray(bin_img), shape)
         stats = {"voxel_counts": table["voxel_counts"], "bounding_boxes": np.array(table["bounding_boxes"]),
                  "centroids": table["centroids"]}
     else:

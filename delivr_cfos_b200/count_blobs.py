@@ -103,7 +103,8 @@ def count_blobs(settings, path_in, brain_i, brain, stack_shape, min_size=-1, max
     if not cached_brain:
         print("No cached brain found, performing connected components on the GPU...")
         labels = np.empty(bin_img.shape, dtype=np.uint32)
-        table = _context(device).ccl(np.ascontiguousarray(bin_img), bin_img.shape, labels_out=labels)
+        from .slabs import ccl_any_size          # whole-brain volumes exceed one 32-bit label space: z sub-slabs, exact merge
+        table = ccl_any_size(_context(device), np.ascontiguousarray(bin_img), bin_img.shape, labels_out=labels)
         N = table["n"]
         np.save(os.path.join(path_out, f"{brain}-{N}-cc3d.npy"), labels)
         stats = {k: table[k] for k in ("voxel_counts", "bounding_boxes", "centroids")}

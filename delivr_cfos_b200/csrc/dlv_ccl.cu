@@ -107,20 +107,23 @@ __global__ void __launch_bounds__(256, 5) ccl_init_kernel(const uint8_t* __restr
                 if ((lane & 7) == 0 && wi < g.W) bits[r * g.W + wi] = word;
                 if (x0 < g.X) {
                     const uint32_t wbase = static_cast<uint32_t>(base + static_cast<int64_t>(wi) * 32);   // 0-based index of bit 0
+                    // label = 1 + index of the first voxel of the x-run inside this word: walk the lane's 4 bits with a
+                    // running run start (the highest zero bit below the lane's first bit starts it)
+                    const int b0 = 4 * (lane & 7);
+                    const uint32_t zeros_below = ~word & ((1u << b0) - 1u);
+                    int run = zeros_below ? (32 - __clz(zeros_below)) : 0;
                     uint32_t lab[4];
-                    int nbg = 0, bx0 = INT_MAX, bx1 = -1;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const int b = 4 * (lane & 7) + j;
-                        if ((word >> b) & 1u) {
-                            const uint32_t zeros_below = ~word & ((1u << b) - 1u);
-                            const int s = zeros_below ? (32 - __clz(zeros_below)) : 0;
-                            lab[j] = wbase + s + 1u;
-                        } else {
-                            lab[j] = 0u;
-                            if (x0 + j < g.X) { ++nbg; bx0 = min(bx0, static_cast<int>(x0 + j)); bx1 = max(bx1, static_cast<int>(x0 + j)); }
-                        }
+                        const bool fg = (word >> (b0 + j)) & 1u;
+                        lab[j] = fg ? wbase + run + 1u : 0u;
+                        run = fg ? run : b0 + j + 1;
                     }
+                    // background voxels of this lane (inside the row): x-range from the nibble's zero bits
+                    uint32_t bgn = ~nibs[u] & 0xFu;
+                    if (x0 + 4 > g.X) bgn &= (1u << (g.X - x0)) - 1u;
+                    const int nbg = bgn != 0;
+                    const int bx0 = static_cast<int>(x0) + (__ffs(bgn) - 1), bx1 = static_cast<int>(x0) + (31 - __clz(bgn));
                     if (vec) {
                         __stcs(reinterpret_cast<uint4*>(L + base + x0), make_uint4(lab[0], lab[1], lab[2], lab[3]));
                     } else {

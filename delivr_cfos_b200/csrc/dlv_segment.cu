@@ -89,6 +89,46 @@ __global__ void average_kernel(const int32_t* __restrict__ acc, float* __restric
     avg[i] = s / (wsum * a.passes);     // acc and avg may alias (same element, same thread)
 }
 
+// Constant blend (what the reference computes): the number of windows covering a voxel, and how many of them were
+// skipped, only change where a window starts or ends.  Each axis is cut into cells of constant (lo, hi); a small
+// table holds (count, skipped) per 3-D cell and the volume pass is a pure stream: 16 B in, 16 B out per thread.
+struct CellArgs {
+    const int32_t *lo_z, *hi_z, *lo_y, *hi_y, *lo_x, *hi_x;   // per CELL
+    int ncz, ncy, ncx, ny, nx;
+    const int32_t* active;
+};
+__global__ void cell_table_kernel(CellArgs c, float2* __restrict__ table) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.ncz * c.ncy * c.ncx) return;
+    const int cx = i % c.ncx, cy = (i / c.ncx) % c.ncy, cz = i / (c.ncx * c.ncy);
+    float wsum = 0.f, wskip = 0.f;
+    for (int iz = c.lo_z[cz]; iz <= c.hi_z[cz]; ++iz)
+        for (int iy = c.lo_y[cy]; iy <= c.hi_y[cy]; ++iy)
+            for (int ix = c.lo_x[cx]; ix <= c.hi_x[cx]; ++ix) {
+                wsum += 1.f;
+                if (!c.active[(static_cast<int64_t>(iz) * c.ny + iy) * c.nx + ix]) wskip += 1.f;
+            }
+    table[i] = make_float2(wsum, wskip);
+}
+__global__ void average_const_kernel(const int4* __restrict__ acc, float4* __restrict__ avg, int64_t PY, int64_t PX4, int64_t gz0,
+                                     const int32_t* __restrict__ cid_z, const int32_t* __restrict__ cid_y,
+                                     const int4* __restrict__ cid_x4, int ncy, int ncx, const float2* __restrict__ table, int passes) {
+    const int64_t x4 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t y = blockIdx.y, z = blockIdx.z;
+    if (x4 >= PX4) return;
+    const float2* row = table + (static_cast<int64_t>(cid_z[gz0 + z]) * ncy + cid_y[y]) * ncx;
+    const int4 cx = cid_x4[x4];
+    const int64_t i = (z * PY + y) * PX4 + x4;
+    const int4 v = acc[i];
+    const float2 t0 = row[cx.x], t1 = row[cx.y], t2 = row[cx.z], t3 = row[cx.w];
+    float4 o;      // same expression as average_kernel: (acc / 2^12 + (-1000) * skipped * passes) / (count * passes)
+    o.x = (static_cast<float>(v.x) * (1.f / kAccScale) + kSkipLogit * t0.y * passes) / (t0.x * passes);
+    o.y = (static_cast<float>(v.y) * (1.f / kAccScale) + kSkipLogit * t1.y * passes) / (t1.x * passes);
+    o.z = (static_cast<float>(v.z) * (1.f / kAccScale) + kSkipLogit * t2.y * passes) / (t2.x * passes);
+    o.w = (static_cast<float>(v.w) * (1.f / kAccScale) + kSkipLogit * t3.y * passes) / (t3.x * passes);
+    avg[i] = o;      // acc and avg may alias (same 16 bytes, same thread)
+}
+
 struct DevBuf {
     void* p = nullptr;
     cudaStream_t s = nullptr;
@@ -205,6 +245,46 @@ int seg_average(Ctx* ctx, int32_t* acc, int64_t nplanes, int64_t gz0, const int6
     if ((rc = dev_upload(ctx, t_sx, s32))) return rc;
     std::vector<int32_t> act(active_host, active_host + nwin);
     if ((rc = dev_upload(ctx, d_active, act))) return rc;
+    if (blend_mode == 0 && (PX & 3) == 0 && (reinterpret_cast<uintptr_t>(acc) & 15u) == 0) {
+        // cells of constant window cover per axis
+        auto cells = [](const std::vector<int32_t>& lo_v, const std::vector<int32_t>& hi_v, std::vector<int32_t>& cid,
+                        std::vector<int32_t>& clo, std::vector<int32_t>& chi) {
+            cid.resize(lo_v.size()); clo.clear(); chi.clear();
+            for (size_t g = 0; g < lo_v.size(); ++g) {
+                if (g == 0 || lo_v[g] != lo_v[g - 1] || hi_v[g] != hi_v[g - 1]) { clo.push_back(lo_v[g]); chi.push_back(hi_v[g]); }
+                cid[g] = static_cast<int32_t>(clo.size()) - 1;
+            }
+        };
+        std::vector<int32_t> lz, hz, ly, hy, lx, hx, cidz, cidy, cidx, cloz, chiz, cloy, chiy, clox, chix;
+        cover_tables(sz, roi[0], PZ, lz, hz); cells(lz, hz, cidz, cloz, chiz);
+        cover_tables(sy, roi[1], PY, ly, hy); cells(ly, hy, cidy, cloy, chiy);
+        cover_tables(sx, roi[2], PX, lx, hx); cells(lx, hx, cidx, clox, chix);
+        DevBuf d_cidz, d_cidy, d_cidx, d_cloz, d_chiz, d_cloy, d_chiy, d_clox, d_chix, d_table;
+        if ((rc = dev_upload(ctx, d_cidz, cidz)) || (rc = dev_upload(ctx, d_cidy, cidy)) || (rc = dev_upload(ctx, d_cidx, cidx)) ||
+            (rc = dev_upload(ctx, d_cloz, cloz)) || (rc = dev_upload(ctx, d_chiz, chiz)) || (rc = dev_upload(ctx, d_cloy, cloy)) ||
+            (rc = dev_upload(ctx, d_chiy, chiy)) || (rc = dev_upload(ctx, d_clox, clox)) || (rc = dev_upload(ctx, d_chix, chix)))
+            return rc;
+        CellArgs c;
+        c.lo_z = d_cloz.as<int32_t>(); c.hi_z = d_chiz.as<int32_t>(); c.lo_y = d_cloy.as<int32_t>(); c.hi_y = d_chiy.as<int32_t>();
+        c.lo_x = d_clox.as<int32_t>(); c.hi_x = d_chix.as<int32_t>();
+        c.ncz = static_cast<int>(cloz.size()); c.ncy = static_cast<int>(cloy.size()); c.ncx = static_cast<int>(clox.size());
+        c.ny = static_cast<int>(sy.size()); c.nx = static_cast<int>(sx.size()); c.active = d_active.as<int32_t>();
+        const int64_t ncell = static_cast<int64_t>(c.ncz) * c.ncy * c.ncx;
+        if (ncell < (1ll << 31)) {
+            if ((rc = dev_alloc(ctx, d_table, static_cast<size_t>(ncell) * sizeof(float2)))) return rc;
+            cell_table_kernel<<<static_cast<unsigned>((ncell + 255) / 256), 256, 0, ctx->stream>>>(c, d_table.as<float2>());
+            dim3 grid(static_cast<unsigned>((PX / 4 + 127) / 128), static_cast<unsigned>(PY), static_cast<unsigned>(nplanes));
+            average_const_kernel<<<grid, 128, 0, ctx->stream>>>(reinterpret_cast<const int4*>(acc), reinterpret_cast<float4*>(acc), PY, PX / 4,
+                                                                gz0, d_cidz.as<int32_t>(), d_cidy.as<int32_t>(),
+                                                                reinterpret_cast<const int4*>(d_cidx.as<int32_t>()), c.ncy, c.ncx,
+                                                                d_table.as<float2>(), passes);
+            ctx->launches += 2;
+            cudaError_t e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // lookup tables are freed on return
+            if (e != cudaSuccess) { set_error(ctx, "average kernel: %s", cudaGetErrorString(e)); return DLV_ERR_CUDA; }
+            return 0;
+        }
+    }
     AvgArgs a;
     a.PZ = nplanes; a.PY = PY; a.PX = PX; a.gz0 = gz0;
     a.lo_z = t_loz.as<int32_t>(); a.hi_z = t_hiz.as<int32_t>();

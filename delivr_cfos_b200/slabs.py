@@ -176,6 +176,64 @@ def merge_tables(tables, luts, z_offsets, n_global, shape_real):
     return {"n": n_global, "voxel_counts": counts, "sums": sums, "bounding_boxes": bbox, "centroids": cent}
 
 
+# ------------------------------------------------------------------------------------------- volumes beyond one label space
+MAX_CCL_VOXELS = (1 << 32) - 2       # dlv_ccl labels provisional components with 32-bit voxel indices
+
+
+def ccl_any_size(ctx, mask, shape, labels_out=None, max_voxels=MAX_CCL_VOXELS):
+    """``Context.ccl`` for volumes of any size (count_blobs.py:61,85 on a whole brain: 2.4e10 voxels).
+
+    A volume with more voxels than one 32-bit label space is cut along z into sub-slabs that are labelled one after
+    the other on the same GPU and merged exactly like the slabs of different GPUs are: 26-adjacent label pairs across
+    every cut (dlv_ccl_boundary_pairs) -> global numbering by first voxel in raster order (resolve_global_labels) ->
+    dlv_relabel per sub-slab, integer tables merged associatively.  ``mask`` / ``labels_out``: numpy arrays or device
+    tensors of shape ``shape`` (uint8 / uint32-or-int32).  Same return value as ``Context.ccl``."""
+    import torch
+    Z, Y, X = (int(v) for v in shape)
+    plane = Y * X
+    if Z * plane <= max_voxels:
+        return ctx.ccl(mask, shape, labels_out=labels_out)
+    if plane > max_voxels:
+        raise ValueError(f"one plane ({Y}x{X}) exceeds the {max_voxels}-voxel label space of a sub-slab")
+    zs = max(1, max_voxels // plane)
+    dev = torch.device("cuda", ctx.device)
+    stream = torch.cuda.ExternalStream(ctx._L.dlv_stream(ctx._h), device=dev)
+    m3 = mask.reshape(Z, Y, X) if isinstance(mask, np.ndarray) else mask.view(Z, Y, X)
+    l3 = None
+    if labels_out is not None:
+        l3 = labels_out.reshape(Z, Y, X) if isinstance(labels_out, np.ndarray) else labels_out.view(Z, Y, X)
+    host_labels = isinstance(l3, np.ndarray)
+    cuts = list(range(0, Z, zs)) + [Z]
+    tables, counts, pairs, prev_last = [], [], [None], None
+    with torch.cuda.stream(stream):
+        for z0, z1 in zip(cuts[:-1], cuts[1:]):
+            sub = (z1 - z0, Y, X)
+            # labels of this sub-slab: the caller's buffer when it is on the device, else a device scratch (the first
+            # and last planes are needed on the device for the seam pairs anyway)
+            lab = l3[z0:z1] if (l3 is not None and not host_labels) else torch.empty(sub, dtype=torch.int32, device=dev)
+            t = ctx.ccl(m3[z0:z1], sub, labels_out=lab)
+            tables.append(t)
+            counts.append(t["n"])
+            if prev_last is not None:
+                pairs.append(ctx.ccl_boundary_pairs(prev_last, lab[0]))
+            prev_last = lab[-1].clone()
+            if host_labels:
+                l3[z0:z1] = lab.cpu().numpy().view(l3.dtype)
+            del lab
+        luts, n_global = resolve_global_labels(counts, pairs)
+        if l3 is not None:
+            for (z0, z1), lut in zip(zip(cuts[:-1], cuts[1:]), luts):
+                lut_dev = torch.from_numpy(lut.view(np.int32)).to(dev)
+                if host_labels:
+                    lab = torch.from_numpy(np.ascontiguousarray(l3[z0:z1]).view(np.int32)).to(dev)
+                    ctx.relabel(lab, lut_dev)
+                    l3[z0:z1] = lab.cpu().numpy().view(l3.dtype)
+                else:
+                    ctx.relabel(l3[z0:z1], lut_dev)
+        ctx.synchronize()
+    return merge_tables(tables, luts, cuts[:-1], n_global, (Z, Y, X))
+
+
 # ------------------------------------------------------------------------------------------- communication
 class TorchComm:
     """torch.distributed point-to-point + all_gather_object (NCCL on GPUs, gloo on CPU)."""
@@ -271,7 +329,8 @@ class CudaSlabWorker:
         if self.binaries.shape[0] == 0:
             self.table = None
             return 0
-        self.table = self.ctx.ccl(self.binaries, self.binaries.shape, labels_out=self.labels)
+        # a slab thicker than one 32-bit label space (cfg4 on 2 or 4 GPUs) is labelled in sub-slabs
+        self.table = ccl_any_size(self.ctx, self.binaries, tuple(self.binaries.shape), labels_out=self.labels)
         return self.table["n"]
 
     def first_plane(self):
@@ -460,8 +519,8 @@ def _roofline(B, workload, windows_active, conv_ms_max, world):
 
 
 def bench_main(args, rank, local_rank, world):
-    """bench.py --gpus N: weak scaling - an N-times taller volume (N cfg2-sized shares stacked along z), window
-    z-layers partitioned over the ranks by active-window count."""
+    """bench.py --gpus N: weak scaling - N copies of the workload's volume stacked along z (the job at N = 1 is the
+    single-GPU workload itself), window z-layers partitioned over the ranks by active-window count."""
     import json
     import torch
     import torch.distributed as dist
@@ -486,8 +545,11 @@ def bench_main(args, rank, local_rank, world):
     def planes(z0, z1_):
         full = torch.zeros((z1_ - z0, PY, PX), dtype=torch.uint16, device=dev)
         r0, r1 = min(z0, shape[0]), min(z1_, shape[0])
-        if r1 > r0:
-            full[: r1 - r0, :Y, :X] = synth_volume_cuda(shape, wl["seed"], device=dev, z_range=(r0, r1))
+        # plane z of the job = plane z mod z1 of the workload's own volume: every GPU added brings one more copy of
+        # the single-GPU workload (same active-window fraction), plus the window layer that straddles the seam
+        for k in range(r0 // z1, (r1 + z1 - 1) // z1 if r1 > r0 else 0):
+            a, b = max(r0, k * z1), min(r1, (k + 1) * z1)
+            full[a - z0: b - z0, :Y, :X] = synth_volume_cuda((z1, Y, X), wl["seed"], device=dev, z_range=(a - k * z1, b - k * z1))
         return full
 
     from .inference.inference import erosion_block_planes
@@ -559,7 +621,7 @@ def bench_main(args, rank, local_rank, world):
             "metric": "Gvoxels/s seg+CC", "value": v, "unit": "Gvoxels/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": f"synthetic; {wdesc}",
-            "config": {"workload": f"{wl['name']} x {world} stacked along z ({shape[0]}x{Y}x{X}), z-slab sharded",
+            "config": {"workload": f"{world} copies of {wl['name']} stacked along z ({shape[0]}x{Y}x{X}), z-slab sharded",
                        "window": list(B.ROI), "overlap": B.OVERLAP, "tta": False, "blend": "constant", "components": table["n"],
                        "layers_per_rank": plan.layers, "active_windows_per_layer": [int(c) for c in per_layer],
                        "windows_active": int(per_layer.sum()),

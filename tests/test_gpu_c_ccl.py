@@ -110,3 +110,35 @@ def test_ccl_full_size_cfg3_properties():
     assert t2["n"] == n and torch.equal(labels, labels2)
     for k in ("voxel_counts", "sums", "bounding_boxes"):
         assert np.array_equal(t[k], t2[k]), k
+
+
+@pytest.mark.parametrize("shape,planes,host", [((23, 40, 50), 5, True), ((23, 40, 50), 5, False), ((16, 33, 65), 1, False),
+                                               ((40, 64, 64), 16, True)])
+def test_ccl_any_size_equals_single_call(shape, planes, host):
+    """Volumes beyond one 32-bit label space (whole brain, count_blobs.py:61) are labelled in z sub-slabs and merged:
+    forced here with a tiny label space; labels, N and the table must equal the single-call result bit for bit."""
+    from delivr_cfos_b200 import Context
+    from delivr_cfos_b200.slabs import ccl_any_size
+    ctx = Context(0)
+    mask = P.synth_mask(shape, 1003, kind="bernoulli", p=0.12)
+    # long structures crossing many cuts, including one that only connects through a later sub-slab (U shape)
+    mask[:, 3, 3] = 1
+    mask[2:shape[0] - 1, 10, 10] = 1
+    mask[2:shape[0] - 1, 10, 14] = 1
+    mask[shape[0] - 2, 10, 10:15] = 1
+    lab1 = np.empty(shape, dtype=np.uint32)
+    t1 = ctx.ccl(mask, shape, labels_out=lab1)
+    maxv = planes * shape[1] * shape[2]
+    if host:
+        labn = np.empty(shape, dtype=np.uint32)
+        tn = ccl_any_size(ctx, mask, shape, labels_out=labn, max_voxels=maxv)
+    else:
+        ld = torch.empty(shape, dtype=torch.int32, device="cuda")
+        tn = ccl_any_size(ctx, torch.from_numpy(mask).cuda(), shape, labels_out=ld, max_voxels=maxv)
+        labn = ld.cpu().numpy().view(np.uint32)
+    assert tn["n"] == t1["n"] and np.array_equal(labn, lab1)
+    for k in ("voxel_counts", "sums", "bounding_boxes"):
+        assert np.array_equal(tn[k], t1[k]), k
+    assert np.array_equal(tn["centroids"], t1["centroids"], equal_nan=True)
+    t0 = ccl_any_size(ctx, mask, shape, max_voxels=maxv)          # table only
+    assert t0["n"] == t1["n"] and np.array_equal(t0["voxel_counts"], t1["voxel_counts"])
