@@ -41,8 +41,13 @@ __global__ void boundary_pairs_kernel(const uint32_t* __restrict__ lo, const uin
     }
 }
 
-__global__ void relabel_kernel(uint32_t* __restrict__ labels, int64_t n, const uint32_t* __restrict__ map) {
-    const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+// `head` = elements in front of the first 16-byte boundary (a sub-slab of a volume whose planes are not a multiple of
+// 4 voxels starts anywhere): they and the tail are handled one by one, the aligned middle four at a time.
+__global__ void relabel_kernel(uint32_t* __restrict__ labels, int64_t n, const uint32_t* __restrict__ map, int head) {
+    const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t i = head + t * 4;
+    if (t == 0)
+        for (int64_t j = 0; j < head && j < n; ++j) { const uint32_t l = labels[j]; if (l) labels[j] = map[l]; }
     if (i + 3 < n) {
         uint4 v = *reinterpret_cast<uint4*>(labels + i);
         if (v.x | v.y | v.z | v.w) {
@@ -161,8 +166,9 @@ int dlv_relabel(dlv_ctx* c, uint32_t* labels_dev, int64_t n, const uint32_t* map
     if (!labels_dev || !map_dev || n < 0 || nmap < 1) { dlv::set_error(ctx, "dlv_relabel: bad argument"); return DLV_ERR_ARG; }
     cudaSetDevice(ctx->device);
     if (n > 0) {
-        const int64_t nthreads = (n + 3) / 4;
-        dlv::relabel_kernel<<<static_cast<unsigned>((nthreads + 255) / 256), 256, 0, ctx->stream>>>(labels_dev, n, map_dev);
+        const int head = static_cast<int>(((16 - (reinterpret_cast<uintptr_t>(labels_dev) & 15u)) & 15u) / 4);
+        const int64_t nthreads = (n + 3) / 4 + 1;
+        dlv::relabel_kernel<<<static_cast<unsigned>((nthreads + 255) / 256), 256, 0, ctx->stream>>>(labels_dev, n, map_dev, head);
         ctx->launches++;
     }
     DLV_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));

@@ -1,11 +1,11 @@
 """z-slab sharding of the blob_detection hot path over the GPUs of one box (one process per GPU).
 
-The volume's *window z-layers* are partitioned contiguously over the ranks.  Each rank gathers and runs its own
-windows and blends them into a local fixed-point accumulator; three small exchanges make the result identical to
-a single-GPU run, bit for bit:
+The volume's *windows* (z-major order) are partitioned contiguously over the ranks, cut at window granularity so that
+every rank runs the same number of active windows.  Each rank gathers and runs its own windows and blends them into
+a local fixed-point accumulator; three small exchanges make the result identical to a single-GPU run, bit for bit:
 
-1. logits  - the planes shared by the last window layer of rank r and the first of rank r+1 are sent r -> r+1
-             and added (int32 adds: exact, order independent); rank r+1 owns those planes afterwards;
+1. logits  - the planes a rank touched beyond the ones it owns are sent down the chain r -> r+1 and added (int32
+             adds: exact, order independent); the owner of a plane ends up with the complete sum;
 2. activity- the per-window "input max > 0" flags are all-gathered (the averaging needs the skipped windows);
 3. labels  - after a per-slab labelling, rank r sends its last label plane to r+1, which lists the 26-adjacent
              label pairs; pairs + per-slab component counts are all-gathered and every rank resolves the same
@@ -28,9 +28,16 @@ EROSION_ITERS = 30
 
 # ------------------------------------------------------------------------------------------- planning (pure host)
 class SlabPlan:
-    """Partition of the window z-layers and the plane ranges that follow from it."""
+    """Partition of the windows (z-major order of dense_patch_slices) and the plane ranges that follow from it.
 
-    def __init__(self, shape_real, roi, overlap, world, starts=None, erosion_iters=EROSION_ITERS, layer_weights=None):
+    Rank r runs the contiguous window range ``wrange[r]`` - cut at WINDOW granularity so that every rank gets the
+    same share of the (active) windows; a window z-layer may therefore be shared by two or more ranks.  Rank r owns
+    the planes from the first plane of the layer its range starts in up to the next rank's first such plane; sums
+    for planes beyond its ownership travel down the chain r -> r+1 (-> r+2 ... when a rank owns less than it is sent).
+    """
+
+    def __init__(self, shape_real, roi, overlap, world, starts=None, erosion_iters=EROSION_ITERS, layer_weights=None,
+                 window_weights=None):
         self.shape_real = tuple(int(s) for s in shape_real)
         self.roi = tuple(int(r) for r in roi)
         self.overlap = float(overlap)
@@ -42,64 +49,74 @@ class SlabPlan:
             starts = window_grid(self.shape_pad, self.roi, self.overlap)
         self.sz, self.sy, self.sx = ([int(v) for v in s] for s in starts)
         nz = len(self.sz)
-        w = np.ones(nz) if layer_weights is None else np.maximum(np.asarray(layer_weights, dtype=np.float64), 1e-9)
-        # contiguous partition of the layers minimising the largest per-rank weight (active-window count); exact DP,
-        # nz and world are tiny.  Ranks beyond the layer count get empty ranges at the end.
+        self.per_layer = len(self.sy) * len(self.sx)
+        nwin = nz * self.per_layer
+        if window_weights is not None:
+            w = np.maximum(np.asarray(window_weights, dtype=np.float64).reshape(-1), 1e-9)
+            assert len(w) == nwin
+        elif layer_weights is not None:
+            w = np.repeat(np.maximum(np.asarray(layer_weights, dtype=np.float64), 1e-9) / self.per_layer, self.per_layer)
+        else:
+            w = np.ones(nwin)
         cum = np.concatenate([[0.0], np.cumsum(w)])
-        k = min(self.world, nz)
-        INF = float("inf")
-        best = [[INF] * (nz + 1) for _ in range(k + 1)]
-        cut = [[0] * (nz + 1) for _ in range(k + 1)]
-        best[0][0] = 0.0
-        for r in range(1, k + 1):
-            for j in range(r, nz - (k - r) + 1):
-                for i in range(r - 1, j):
-                    c = max(best[r - 1][i], cum[j] - cum[i])
-                    if c < best[r][j]:
-                        best[r][j], cut[r][j] = c, i
-        bounds = [nz]
-        for r in range(k, 0, -1):
-            bounds.append(cut[r][bounds[-1]])
-        bounds = bounds[::-1] + [nz] * (self.world - k)
-        self.layers = [(bounds[r], bounds[r + 1]) for r in range(self.world)]
+        k = min(self.world, nwin)               # ranks beyond the window count get empty ranges at the end
+        cuts = [0]
+        for r in range(1, k):
+            c = int(np.searchsorted(cum, cum[-1] * r / k, side="left"))
+            cuts.append(min(max(c, cuts[-1] + 1), nwin - (k - r)))
+        cuts += [nwin] * (self.world - k + 1)
+        self.wrange = [(cuts[r], cuts[r + 1]) for r in range(self.world)]
+        # window layers touched by each rank (half-open; neighbouring ranks may share one) - reporting / emptiness
+        self.layers = [((c0 // self.per_layer, (c1 - 1) // self.per_layer + 1) if c1 > c0 else (nz, nz)) for c0, c1 in self.wrange]
+        self._info = {}
 
     def rank(self, r):
         """Plane ranges of rank r (global plane numbers, half-open)."""
-        a, b = self.layers[r]
+        if r in self._info:
+            return self._info[r]
+        c0, c1 = self.wrange[r]
         PZ, Z = self.shape_pad[0], self.shape_real[0]
         rz = self.roi[0]
-        if a == b:       # more ranks than window layers: nothing to do
-            return dict(layers=(a, b), win=(0, 0), own=(0, 0), slab=(0, 0), send=None, recv=None, own_real=(0, 0))
-        last = self._next_nonempty(r) is None
-        first = self._prev_nonempty(r) is None
-        win = (self.sz[a], self.sz[b - 1] + rz)
-        own = (0 if first else self.sz[a], PZ if last else self.sz[b])
-        slab = (max(0, own[0] - (self.iters + 1)), max(win[1], min(PZ, own[1] + self.iters + 1)))
-        send = None if last else (self.sz[b], win[1])                 # planes owned by the next rank that we touched
-        recv = None
-        p = self._prev_nonempty(r)
-        if p is not None:
-            pa, pb = self.layers[p]
-            recv = (self.sz[a], self.sz[pb - 1] + rz)
-        own_real = (min(own[0], Z), min(own[1], Z))
-        return dict(layers=(a, b), win=win, own=own, slab=slab, send=send, recv=recv, own_real=own_real)
+        if c0 == c1:     # more ranks than windows: nothing to do
+            info = dict(layers=self.layers[r], win=(0, 0), own=(0, 0), slab=(0, 0), send=None, recv=None, own_real=(0, 0))
+            self._info[r] = info
+            return info
+        la, lb = self.layers[r][0], self.layers[r][1] - 1
+        prv, nxt = self._prev_nonempty(r), self._next_nonempty(r)
+        win = (self.sz[la], self.sz[lb] + rz)
+        own = (0 if prv is None else self.sz[la], PZ if nxt is None else self.sz[self.layers[nxt][0]])
+        recv = None if prv is None else self.rank(prv)["send"]          # what the previous rank touched beyond its planes
+        touched_end = max(win[1], recv[1] if recv else 0)
+        send = (own[1], touched_end) if (nxt is not None and touched_end > own[1]) else None
+        slab = (max(0, min(win[0], own[0] - (self.iters + 1))), max(touched_end, min(PZ, own[1] + self.iters + 1)))
+        info = dict(layers=self.layers[r], win=win, own=own, slab=slab, send=send, recv=recv,
+                    own_real=(min(own[0], Z), min(own[1], Z)))
+        self._info[r] = info
+        return info
 
     def _next_nonempty(self, r):
         for q in range(r + 1, self.world):
-            if self.layers[q][0] < self.layers[q][1]:
+            if self.wrange[q][0] < self.wrange[q][1]:
                 return q
         return None
 
     def _prev_nonempty(self, r):
         for q in range(r - 1, -1, -1):
-            if self.layers[q][0] < self.layers[q][1]:
+            if self.wrange[q][0] < self.wrange[q][1]:
                 return q
         return None
 
     def windows_of(self, r):
         """int32 [n,3] global origins of rank r's windows, z-major / x fastest (dense_patch_slices order)."""
-        a, b = self.layers[r]
-        return np.array([(z, y, x) for z in self.sz[a:b] for y in self.sy for x in self.sx], dtype=np.int32).reshape(-1, 3)
+        c0, c1 = self.wrange[r]
+        if c1 <= c0:
+            return np.zeros((0, 3), dtype=np.int32)
+        idx = np.arange(c0, c1, dtype=np.int64)
+        iz, rem = idx // self.per_layer, idx % self.per_layer
+        iy, ix = rem // len(self.sx), rem % len(self.sx)
+        out = np.stack([np.asarray(self.sz, dtype=np.int32)[iz], np.asarray(self.sy, dtype=np.int32)[iy],
+                        np.asarray(self.sx, dtype=np.int32)[ix]], axis=1)
+        return np.ascontiguousarray(out, dtype=np.int32).reshape(-1, 3)
 
 
 def resolve_global_labels(counts, pairs):
@@ -433,23 +450,16 @@ def _run_distributed(worker, plan, comm):
     info = plan.rank(r)
     active = worker.accumulate()
     nxt, prv = plan._next_nonempty(r), plan._prev_nonempty(r)
-    have = info["layers"][1] > info["layers"][0]
-    # exchange 1 (even ranks send first to avoid head-of-line blocking on blocking backends)
-    def _send():
-        if have and info["send"] is not None and nxt is not None:
-            g0, g1 = info["send"]
-            comm.send(worker.acc_planes(g0, g1), r, nxt, "acc")
-
-    def _recv():
-        if have and info["recv"] is not None and prv is not None:
-            g0, g1 = info["recv"]
-            buf = worker.acc_planes(g0, g1).clone()
-            worker.add_planes(g0, g1, comm.recv(buf, prv, r, "acc"))
-
-    if r % 2 == 0:
-        _send(); _recv()
-    else:
-        _recv(); _send()
+    have = plan.wrange[r][1] > plan.wrange[r][0]
+    # exchange 1: a chain - receive and add first, then send (what is sent may contain what was just received, when
+    # this rank owns fewer planes than the previous one touched); stream-ordered on NCCL, blocking pairs on gloo
+    if have and info["recv"] is not None and prv is not None:
+        g0, g1 = info["recv"]
+        buf = worker.acc_planes(g0, g1).clone()
+        worker.add_planes(g0, g1, comm.recv(buf, prv, r, "acc"))
+    if have and info["send"] is not None and nxt is not None:
+        g0, g1 = info["send"]
+        comm.send(worker.acc_planes(g0, g1), r, nxt, "acc")
     active_global = np.concatenate(comm.allgather(np.asarray(active, dtype=np.int32)))     # exchange 2
     worker.finalise(active_global)
     n_local = worker.ccl()
@@ -489,13 +499,13 @@ def _run_distributed(worker, plan, comm):
 
 # ------------------------------------------------------------------------------------------- bench entry (N > 1)
 def balanced_plan(ctx, comm, shape, roi, overlap, planes_fn):
-    """Load-balanced partition: every rank scans the windows of an equal-thickness share
-    with the skip rule's max pre-pass (dlv_windows_active), the per-layer active-window counts are all-gathered and the
-    layers are re-partitioned by active count.  -> (SlabPlan, active counts per window layer)"""
+    """Load-balanced partition: every rank scans an equal share of the windows with the
+    skip rule's max pre-pass (dlv_windows_active), the per-window flags are all-gathered and the window list is
+    re-cut so that every rank runs the same number of ACTIVE windows.  -> (SlabPlan, active counts per window layer)"""
     plan0 = SlabPlan(shape, roi, overlap, comm.world)
     info = plan0.rank(comm.rank)
     act = np.zeros(0, dtype=np.int32)
-    if info["layers"][1] > info["layers"][0]:
+    if plan0.wrange[comm.rank][1] > plan0.wrange[comm.rank][0]:
         z0, z1 = info["win"]
         slab0 = planes_fn(z0, z1)
         local = plan0.windows_of(comm.rank).copy()
@@ -504,7 +514,7 @@ def balanced_plan(ctx, comm, shape, roi, overlap, planes_fn):
         del slab0
     all_act = np.concatenate([np.asarray(a, dtype=np.int32) for a in comm.allgather(act)])
     per_layer = all_act.reshape(len(plan0.sz), -1).sum(axis=1)
-    return SlabPlan(shape, roi, overlap, comm.world, layer_weights=per_layer), per_layer
+    return SlabPlan(shape, roi, overlap, comm.world, window_weights=all_act), per_layer
 
 
 def _roofline(B, workload, windows_active, conv_ms_max, world):
@@ -534,7 +544,10 @@ def bench_main(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=dev)
     wl = B.WORKLOADS[args.workload]
     z1, Y, X = wl["shape"]
-    shape = (z1 * world, Y, X)
+    tta = bool(getattr(args, "tta", False))
+    evaluated = 3 if tta else 1                # 13 reference passes = 3 distinct ones blended 5 / 4 / 4 times
+    whole = bool(wl.get("whole"))              # one fixed volume sharded over the ranks (strong scaling) instead of N copies
+    shape = (z1, Y, X) if whole else (z1 * world, Y, X)
     sd, wdesc = B.state_dict()
     ctx = Context(local_rank)
     ctx.load_weights(sd)
@@ -572,7 +585,7 @@ def bench_main(args, rank, local_rank, world):
             d = torch.empty(slab.shape, dtype=torch.uint16, device=dev)
             d.copy_(hslab, non_blocking=True)
             return d
-        w = CudaSlabWorker(ctx, plan, rank, load, erosion_block_planes=ebp)
+        w = CudaSlabWorker(ctx, plan, rank, load, erosion_block_planes=ebp, tta=tta)
         table = run_distributed(w, plan, comm)
         if host:
             with torch.cuda.stream(stream):
@@ -619,11 +632,15 @@ def bench_main(args, rank, local_rank, world):
         nrow = table_e2e["n"] + 1
         print(json.dumps({
             "metric": "Gvoxels/s seg+CC", "value": v, "unit": "Gvoxels/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if whole else "weak", "vs_baseline": None,
             "dtype": "bf16", "data": f"synthetic; {wdesc}",
-            "config": {"workload": f"{world} copies of {wl['name']} stacked along z ({shape[0]}x{Y}x{X}), z-slab sharded",
-                       "window": list(B.ROI), "overlap": B.OVERLAP, "tta": False, "blend": "constant", "components": table["n"],
-                       "layers_per_rank": plan.layers, "active_windows_per_layer": [int(c) for c in per_layer],
+            "config": {"workload": (f"{wl['name']}, z-slab sharded over {world} GPUs" if whole else
+                                    f"{world} copies of {wl['name']} stacked along z ({shape[0]}x{Y}x{X}), z-slab sharded"),
+                       "seconds_per_volume": ms * 1e-3, "seconds_per_volume_e2e": ms_e2e * 1e-3,
+                       "window": list(B.ROI), "overlap": B.OVERLAP, "tta": tta, "passes_evaluated": evaluated, "blend": "constant",
+                       "components": table["n"],
+                       "layers_per_rank": plan.layers, "windows_per_rank": [c1 - c0 for c0, c1 in plan.wrange],
+                       "active_windows_per_layer": [int(c) for c in per_layer],
                        "windows_active": int(per_layer.sum()),
                        "timing": "CUDA events on the library stream between barriers, max over ranks",
                        "l2": "inputs larger than L2 (slab + accumulator >> 126 MB)"},
@@ -631,6 +648,6 @@ def bench_main(args, rank, local_rank, world):
             "e2e": {"value": nvox / (ms_e2e * 1e-3) / 1e9, "unit": "Gvoxels/s", "h2d_bytes_per_step": int(io[0].item()),
                     "d2h_bytes_per_step": int(io[1].item()) + nrow * (8 + 24 + 48),
                     "note": "per-rank pinned host slab in, pinned host binaries + merged table out"},
-            "roofline": _roofline(B, args.workload, int(per_layer.sum()), float(conv.item()), world),
+            "roofline": _roofline(B, args.workload, int(per_layer.sum()) * evaluated, float(conv.item()), world),
         }))
     dist.destroy_process_group()

@@ -19,23 +19,49 @@ def _starts(shape_pad, roi, overlap):
 
 def test_plan_covers_volume_once():
     for shape, roi, world in [((1500, 400, 400), (96, 96, 64), 8), ((256, 64, 64), (96, 96, 64), 2), ((100, 80, 70), (32, 32, 32), 3),
-                              ((64, 64, 64), (32, 32, 32), 5)]:
+                              ((64, 64, 64), (32, 32, 32), 5), ((40, 24, 24), (16, 16, 16), 7), ((20, 40, 40), (16, 16, 16), 6)]:
         pad = P.padded_shape(shape, roi)
         plan = slabs.SlabPlan(shape, roi, 0.5, world, starts=_starts(pad, roi, 0.5))
         owned = np.zeros(pad[0], int)
-        layers = []
+        wins = []
+        nwin = len(plan.sz) * len(plan.sy) * len(plan.sx)
         for r in range(world):
             info = plan.rank(r)
-            layers += list(range(*info["layers"]))
+            c0, c1 = plan.wrange[r]
+            wins += list(range(c0, c1))
             owned[info["own"][0]:info["own"][1]] += 1
-            if info["layers"][1] > info["layers"][0]:
-                assert info["slab"][0] <= info["own"][0] and info["slab"][1] >= info["win"][1]
+            assert len(plan.windows_of(r)) == c1 - c0
+            if c1 > c0:
+                w = plan.windows_of(r)
+                assert info["win"] == (int(w[:, 0].min()), int(w[:, 0].max()) + roi[0])
+                assert info["slab"][0] <= min(info["own"][0], info["win"][0]) and info["slab"][1] >= info["win"][1]
                 assert info["slab"][0] <= max(0, info["own"][0] - 31) and info["slab"][1] >= min(pad[0], info["own"][1] + 31)
+                for rng in (info["send"], info["recv"]):
+                    if rng:
+                        assert info["slab"][0] <= rng[0] < rng[1] <= info["slab"][1]
                 if info["send"]:
                     q = plan._next_nonempty(r)
-                    assert plan.rank(q)["recv"] == info["send"]
-        assert layers == list(range(len(plan.sz)))
+                    assert plan.rank(q)["recv"] == info["send"] and info["send"][0] == info["own"][1]
+                # everything a rank touches beyond its own planes is handed on
+                touched = max(info["win"][1], info["recv"][1] if info["recv"] else 0)
+                assert (info["send"] is None) == (plan._next_nonempty(r) is None or touched <= info["own"][1])
+        assert wins == list(range(nwin))                      # every window exactly once, in dense_patch_slices order
         assert (owned == 1).all()
+        # balance: window counts differ by at most one between the ranks that have work
+        sizes = [c1 - c0 for c0, c1 in plan.wrange if c1 > c0]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_plan_balances_active_windows():
+    shape, roi, world = (300, 200, 200), (32, 32, 32), 4
+    pad = P.padded_shape(shape, roi)
+    st = _starts(pad, roi, 0.5)
+    n = len(st[0]) * len(st[1]) * len(st[2])
+    act = (np.random.default_rng(0).random(n) < 0.6).astype(np.int32)
+    act[: n // 5] = 0
+    plan = slabs.SlabPlan(shape, roi, 0.5, world, starts=st, window_weights=act)
+    per_rank = [int(act[c0:c1].sum()) for c0, c1 in plan.wrange]
+    assert max(per_rank) - min(per_rank) <= 2 and sum(per_rank) == int(act.sum())
 
 
 def _slab_tables(mask, cuts):
@@ -173,8 +199,9 @@ def _gloo_worker(rank, world, port, shape, roi, q):
     dist.destroy_process_group()
 
 
-def test_distributed_driver_gloo_world2():
-    shape, roi, world = (40, 24, 24), (16, 16, 16), 2
+@pytest.mark.parametrize("world", [2, 7])      # 7: ranks cut inside window layers, one of them owning no plane
+def test_distributed_driver_gloo(world):
+    shape, roi = (40, 24, 24), (16, 16, 16)
     volume = _make_volume(shape, roi)
     w1, t1 = _single(volume, shape, roi)
     with socket.socket() as s:
@@ -205,7 +232,7 @@ def test_virtual_slabs_equal_single_oracle():
     shape, roi = (50, 24, 24), (16, 16, 16)
     volume = _make_volume(shape, roi)
     w1, t1 = _single(volume, shape, roi)
-    for world in (2, 3, 6):
+    for world in (2, 3, 6, 12, 20):          # 12, 20: several ranks inside one window layer (ranks that own no plane, forwarding)
         plan = slabs.SlabPlan(shape, roi, 0.5, world, starts=_starts(volume.shape, roi, 0.5), erosion_iters=3)
         ws = [OracleWorker(plan, r, volume) for r in range(world)]
         t = slabs.run_virtual(ws, plan)
