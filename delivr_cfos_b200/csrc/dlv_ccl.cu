@@ -32,7 +32,6 @@ struct CclGeom {
     int64_t Z, Y, X;
     int64_t rows;      // Z*Y
     int W;             // bitmask words per row
-    int sparse;        // 1: the label array was cleared with a memset, ccl_init writes foreground quads only
 };
 
 __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) { return __ldcg(p); }
@@ -126,8 +125,7 @@ __global__ void __launch_bounds__(256, 5) ccl_init_kernel(const uint8_t* __restr
                     const int nbg = bgn != 0;
                     const int bx0 = static_cast<int>(x0) + (__ffs(bgn) - 1), bx1 = static_cast<int>(x0) + (31 - __clz(bgn));
                     if (vec) {
-                        if (!g.sparse || (lab[0] | lab[1] | lab[2] | lab[3]))
-                            __stcs(reinterpret_cast<uint4*>(L + base + x0), make_uint4(lab[0], lab[1], lab[2], lab[3]));
+                        __stcs(reinterpret_cast<uint4*>(L + base + x0), make_uint4(lab[0], lab[1], lab[2], lab[3]));
                     } else {
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
@@ -437,7 +435,7 @@ static unsigned nblocks(int64_t n, int bs) { return static_cast<unsigned>((n + b
 int ccl_run(Ctx* ctx, const uint8_t* mask, const int64_t shape[3], uint32_t* L, dlv_table** table_out) {
     *table_out = nullptr;
     CclGeom g;
-    g.Z = shape[0]; g.Y = shape[1]; g.X = shape[2]; g.sparse = 0;
+    g.Z = shape[0]; g.Y = shape[1]; g.X = shape[2];
     if (g.Z < 0 || g.Y < 0 || g.X < 0) { set_error(ctx, "dlv_ccl: negative shape"); return DLV_ERR_ARG; }
     const int64_t n = g.Z * g.Y * g.X;
     if (n >= 0xFFFFFFFFLL || g.Z > INT_MAX || g.Y > INT_MAX || g.X > INT_MAX) {
@@ -476,9 +474,6 @@ int ccl_run(Ctx* ctx, const uint8_t* mask, const int64_t shape[3], uint32_t* L, 
         CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2)); CK(cudaEventCreate(&e3));
         CK(cudaEventRecord(e0, ctx->stream));
         {
-            static const bool sparse_env = getenv("DLV_CCL_SPARSE_INIT") && atoi(getenv("DLV_CCL_SPARSE_INIT")) != 0;
-            g.sparse = sparse_env && (g.X % 4) == 0 && (reinterpret_cast<uintptr_t>(mask) & 3u) == 0;
-            if (g.sparse) CK(cudaMemsetAsync(L, 0, static_cast<size_t>(n) * 4, ctx->stream));
             const int64_t total_warps = g.rows;     // one row per warp and iteration
             const unsigned grid = static_cast<unsigned>(std::min<int64_t>((total_warps + 7) / 8, static_cast<int64_t>(ctx->num_sms) * 32));
             ccl_init_kernel<<<grid, 256, 0, ctx->stream>>>(mask, g, bits, L, bg_dev);
