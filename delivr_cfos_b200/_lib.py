@@ -51,7 +51,7 @@ EXPORTS = [
     "dlv_synchronize", "dlv_set_conv_timing", "dlv_conv_time_ms", "dlv_load_weights", "dlv_segment", "dlv_ccl", "dlv_table_free",
     "dlv_ccl_last_timing", "dlv_unet_forward", "dlv_op_conv3d", "dlv_op_deconv", "dlv_op_finalise",
     "dlv_window_grid", "dlv_windows_active", "dlv_seg_accumulate", "dlv_seg_average", "dlv_op_finalise_slab",
-    "dlv_ccl_boundary_pairs", "dlv_relabel", "dlv_tiff_info", "dlv_tiff_read_u16", "dlv_tiff_last_error",
+    "dlv_ccl_boundary_pairs", "dlv_relabel", "dlv_table_merge", "dlv_tiff_info", "dlv_tiff_read_u16", "dlv_tiff_last_error",
     "dlv_load_tiff_planes", "dlv_paint_boxes", "dlv_edt",
 ]
 
@@ -129,6 +129,9 @@ def load_library():
                                        ctypes.c_int]
     L.dlv_paint_boxes.restype = ctypes.c_int
     L.dlv_paint_boxes.argtypes = [c_vp, c_vp, P(c_i64), c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, P(c_vp), c_i64]
+    L.dlv_table_merge.restype = ctypes.c_int
+    L.dlv_table_merge.argtypes = [c_i64, ctypes.c_int, P(c_i64), P(c_vp), P(c_vp), P(c_vp), P(c_vp), P(c_i64), P(c_i64),
+                                  c_vp, c_vp, c_vp, c_vp]
     L.dlv_edt.restype = ctypes.c_int
     L.dlv_edt.argtypes = [c_vp, c_vp, P(c_i64), P(ctypes.c_double), c_vp]
     if L.dlv_abi_version() != 2:
@@ -422,6 +425,39 @@ def tiff_read_u16(path):
     if L.dlv_tiff_read_u16(os.fsencode(path), out.ctypes.data, h, w) != 0:
         raise DlvError(f"dlv_tiff_read_u16: {L.dlv_tiff_last_error().decode()}")
     return out
+
+
+def table_merge(tables, luts, z_offsets, n_global, shape_real):
+    """dlv_table_merge (host only): per-slab tables + label maps -> global table dict (see slabs.merge_tables)."""
+    L = load_library()
+    nt = len(tables)
+    keep = []                                           # keep the contiguous copies alive during the call
+    rows = (c_i64 * nt)()
+    lp, cp, sp, bp = (c_vp * nt)(), (c_vp * nt)(), (c_vp * nt)(), (c_vp * nt)()
+    for i, (t, lut) in enumerate(zip(tables, luts)):
+        if t is None:
+            rows[i] = 0
+            lp[i] = cp[i] = sp[i] = bp[i] = None
+            continue
+        a = [np.ascontiguousarray(lut, dtype=np.uint32), np.ascontiguousarray(t["voxel_counts"], dtype=np.uint64),
+             np.ascontiguousarray(t["sums"], dtype=np.uint64), np.ascontiguousarray(t["bounding_boxes"], dtype=np.int64)]
+        if not (len(a[0]) == len(a[1]) == len(a[2]) == len(a[3])):
+            raise ValueError("table / label-map row counts differ")
+        keep.append(a)
+        rows[i] = len(a[0])
+        lp[i], cp[i], sp[i], bp[i] = (x.ctypes.data for x in a)
+    n = int(n_global)
+    counts = np.empty(n + 1, dtype=np.uint64)
+    sums = np.empty((n + 1, 3), dtype=np.uint64)
+    bbox = np.empty((n + 1, 6), dtype=np.int64)
+    cent = np.empty((n + 1, 3), dtype=np.float64)
+    zo = (c_i64 * nt)(*[int(z) for z in z_offsets])
+    shp = (c_i64 * 3)(*[int(v) for v in shape_real])
+    rc = L.dlv_table_merge(n, nt, rows, lp, cp, sp, bp, zo, shp, counts.ctypes.data, sums.ctypes.data, bbox.ctypes.data,
+                           cent.ctypes.data)
+    if rc != 0:
+        raise DlvError(f"dlv_table_merge failed ({rc}): a label map points outside rows 0..{n}")
+    return {"n": n, "voxel_counts": counts, "sums": sums, "bounding_boxes": bbox, "centroids": cent}
 
 
 def window_grid(shape_pad, roi, overlap):

@@ -175,4 +175,43 @@ int dlv_relabel(dlv_ctx* c, uint32_t* labels_dev, int64_t n, const uint32_t* map
     return DLV_OK;
 }
 
+/* Host-only: exact merge of per-slab statistics tables into the global table (see include/delivr_b200.h). */
+int dlv_table_merge(int64_t n_global, int ntables, const int64_t* rows, const uint32_t* const* luts,
+                    const uint64_t* const* counts, const uint64_t* const* sums, const int64_t* const* bbox,
+                    const int64_t* z_offsets, const int64_t shape[3], uint64_t* counts_out, uint64_t* sums_out,
+                    int64_t* bbox_out, double* centroids_out) {
+    if (n_global < 0 || ntables < 0 || !shape || !counts_out || !sums_out || !bbox_out || !centroids_out) return DLV_ERR_ARG;
+    const int64_t R = n_global + 1;
+    for (int64_t g = 0; g < R; ++g) {
+        counts_out[g] = 0;
+        sums_out[3 * g] = sums_out[3 * g + 1] = sums_out[3 * g + 2] = 0;
+        int64_t* b = bbox_out + 6 * g;
+        b[0] = shape[0]; b[1] = -1; b[2] = shape[1]; b[3] = -1; b[4] = shape[2]; b[5] = -1;
+    }
+    for (int t = 0; t < ntables; ++t) {
+        if (!luts[t] || !counts[t] || !sums[t] || !bbox[t]) continue;          /* a rank without planes */
+        const uint64_t z0 = static_cast<uint64_t>(z_offsets[t]);
+        for (int64_t l = 0; l < rows[t]; ++l) {
+            const int64_t g = luts[t][l];
+            if (g < 0 || g >= R) return DLV_ERR_ARG;
+            const uint64_t c = counts[t][l];
+            counts_out[g] += c;
+            sums_out[3 * g] += sums[t][3 * l] + c * z0;
+            sums_out[3 * g + 1] += sums[t][3 * l + 1];
+            sums_out[3 * g + 2] += sums[t][3 * l + 2];
+            const int64_t* b = bbox[t] + 6 * l;
+            if (b[1] < 0) continue;                                              /* row without voxels: neutral box */
+            int64_t* o = bbox_out + 6 * g;
+            o[0] = std::min(o[0], b[0] + z_offsets[t]); o[1] = std::max(o[1], b[1] + z_offsets[t]);
+            o[2] = std::min(o[2], b[2]); o[3] = std::max(o[3], b[3]);
+            o[4] = std::min(o[4], b[4]); o[5] = std::max(o[5], b[5]);
+        }
+    }
+    for (int64_t g = 0; g < R; ++g) {
+        const double c = static_cast<double>(counts_out[g]);                    /* 0 / 0 -> NaN like numpy */
+        for (int k = 0; k < 3; ++k) centroids_out[3 * g + k] = static_cast<double>(sums_out[3 * g + k]) / c;
+    }
+    return DLV_OK;
+}
+
 }  // extern "C"

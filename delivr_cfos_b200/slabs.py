@@ -167,38 +167,11 @@ def resolve_global_labels(counts, pairs):
 
 
 def merge_tables(tables, luts, z_offsets, n_global, shape_real):
-    """Exact merge of per-slab statistics (local z coordinates) into the global table rows 0..N.
-
-    Rows are grouped by their global label with a stable sort + ``reduceat`` (integer adds / min / max, no float
-    round trip); ``np.add.at`` on millions of rows cost a second per step at whole-brain scale."""
-    counts = np.zeros(n_global + 1, dtype=np.uint64)
-    sums = np.zeros((n_global + 1, 3), dtype=np.uint64)
-    Z, Y, X = shape_real
-    bbox = np.tile(np.array([Z, -1, Y, -1, X, -1], dtype=np.int64), (n_global + 1, 1))
-    for t, lut, z0 in zip(tables, luts, z_offsets):
-        if t is None:
-            continue
-        g = lut.astype(np.int64)            # row l -> global row (row 0 -> 0 = background)
-        c = t["voxel_counts"].astype(np.uint64)
-        s = t["sums"].astype(np.uint64).copy()
-        s[:, 0] += c * np.uint64(z0)
-        b = t["bounding_boxes"].astype(np.int64).copy()
-        has = b[:, 1] >= 0                  # rows without voxels keep the neutral box (dim, -1, ...)
-        b[has, 0] += z0
-        b[has, 1] += z0
-        order = np.argsort(g, kind="stable")
-        gs = g[order]
-        first = np.flatnonzero(np.concatenate([[True], gs[1:] != gs[:-1]]))
-        ug = gs[first]
-        counts[ug] += np.add.reduceat(c[order], first)
-        sums[ug] += np.add.reduceat(s[order], first, axis=0)
-        bo = b[order]
-        for k in (0, 2, 4):
-            bbox[ug, k] = np.minimum(bbox[ug, k], np.minimum.reduceat(bo[:, k], first))
-            bbox[ug, k + 1] = np.maximum(bbox[ug, k + 1], np.maximum.reduceat(bo[:, k + 1], first))
-    with np.errstate(invalid="ignore", divide="ignore"):
-        cent = sums.astype(np.float64) / counts.astype(np.float64)[:, None]
-    return {"n": n_global, "voxel_counts": counts, "sums": sums, "bounding_boxes": bbox, "centroids": cent}
+    """Exact merge of per-slab statistics (local z coordinates) into the global table rows 0..N: integer adds /
+    min / max per global label, then one fp64 divide per centroid coordinate.  Runs in the library's host code
+    (dlv_table_merge) - numpy scatter / sort formulations cost 0.3-0.6 s per step at 6e5 components."""
+    from ._lib import table_merge
+    return table_merge(tables, luts, z_offsets, n_global, shape_real)
 
 
 # ------------------------------------------------------------------------------------------- volumes beyond one label space
@@ -638,7 +611,7 @@ def bench_main(args, rank, local_rank, world):
         nvox = int(np.prod(shape))
         v = nvox / (ms * 1e-3) / 1e9
         nrow = table_e2e["n"] + 1
-        print(json.dumps({
+        B.emit({
             "metric": "Gvoxels/s seg+CC", "value": v, "unit": "Gvoxels/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if whole else "weak", "vs_baseline": None,
             "dtype": "bf16", "data": f"synthetic; {wdesc}",
@@ -657,5 +630,5 @@ def bench_main(args, rank, local_rank, world):
                     "d2h_bytes_per_step": int(io[1].item()) + nrow * (8 + 24 + 48),
                     "note": "per-rank pinned host slab in, pinned host binaries + merged table out"},
             "roofline": _roofline(B, args.workload, int(per_layer.sum()) * evaluated, float(conv.item()), world),
-        }))
+        })
     dist.destroy_process_group()

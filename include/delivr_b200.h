@@ -190,6 +190,16 @@ int dlv_ccl_boundary_pairs(dlv_ctx* ctx, const uint32_t* labels_lo_plane_dev, co
 /* labels[i] = map[labels[i]] for non-zero labels (local -> global component numbers). */
 int dlv_relabel(dlv_ctx* ctx, uint32_t* labels_dev, int64_t n, const uint32_t* map_dev, int64_t nmap);
 
+/* Host-only (no ctx, no GPU): exact merge of `ntables` per-slab statistics tables into the global table rows
+ * 0..n_global.  Table t has rows[t] rows (local labels 0..N_t) with local z coordinates; luts[t][l] is the global
+ * row of local row l (row 0 -> 0), z_offsets[t] the global plane of the slab's first plane; a NULL luts[t] skips
+ * the table.  Integer adds / min / max (associative: any slab partition gives the same table), then one fp64
+ * divide per centroid coordinate.  Outputs: counts [n+1], sums [n+1][3], bbox [n+1][6], centroids [n+1][3]. */
+int dlv_table_merge(int64_t n_global, int ntables, const int64_t* rows, const uint32_t* const* luts,
+                    const uint64_t* const* counts, const uint64_t* const* sums, const int64_t* const* bbox,
+                    const int64_t* z_offsets, const int64_t shape[3], uint64_t* counts_out, uint64_t* sums_out,
+                    int64_t* bbox_out, double* centroids_out);
+
 /* ---- raw TIFF planes -> device-resident masked volume ----
  * Replaces the masked_nifti.npy producer loop (downsample/downsample_and_mask.py:398-414: cv2.imread(plane, -1),
  * mask rule, copy into the zero-padded array) and get_real_size (downsample_and_mask.py:25-30), so that the
