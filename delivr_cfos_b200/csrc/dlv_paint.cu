@@ -170,7 +170,14 @@ int paint_boxes(Ctx* ctx, const void* mask_any, const int64_t shape[3], const in
     std::vector<uint16_t> vals(static_cast<size_t>(std::max<int64_t>(n, 1)) * nch);
     for (int64_t i = 0; i < n * nch; ++i) vals[i] = static_cast<uint16_t>(static_cast<uint64_t>(values_host[i]) & (elem_bytes == 1 ? 0xFFu : 0xFFFFu));
 
-    if (chunk_voxels <= 0) chunk_voxels = 1ll << 28;
+    if (chunk_voxels <= 0) {
+        // every z-chunk scans the whole box list, so the default is as few chunks as memory allows: the 4 B/voxel owner
+        // scratch may take a quarter of the free device memory (cfg3: one chunk, 16.8 GB)
+        size_t free_b = 0, total_b = 0;
+        chunk_voxels = 1ll << 28;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) chunk_voxels = std::max<int64_t>(chunk_voxels, static_cast<int64_t>(free_b / 16));
+        else cudaGetLastError();
+    }
     const int64_t cz = std::max<int64_t>(1, std::min(Z, chunk_voxels / plane));
     const int64_t cvox = cz * plane;
     int64_t* boxes = nullptr; uint16_t* values = nullptr; uint32_t *owner = nullptr, *big = nullptr, *nbig = nullptr;
