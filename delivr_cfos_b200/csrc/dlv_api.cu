@@ -76,6 +76,7 @@ void dlv_destroy(dlv_ctx* c) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     dlv::engine_free(ctx);
     dlv::net_free(ctx);
+    if (ctx->paint_owner) cudaFree(ctx->paint_owner);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

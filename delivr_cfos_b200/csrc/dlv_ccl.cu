@@ -393,7 +393,7 @@ static std::mutex g_pool_mu;
 static std::vector<PinnedBlock> g_pool;
 constexpr size_t kPoolKeep = 4;
 
-static void* pool_take(size_t bytes, size_t* cap_out) {
+void* pinned_take(size_t bytes, size_t* cap_out) {
     std::lock_guard<std::mutex> lk(g_pool_mu);
     int best = -1;
     for (size_t i = 0; i < g_pool.size(); ++i)
@@ -408,7 +408,8 @@ static void* pool_take(size_t bytes, size_t* cap_out) {
     *cap_out = cap;
     return p;
 }
-static void pool_give(void* p) {
+void pinned_give(void* p) {
+    if (!p) return;
     std::lock_guard<std::mutex> lk(g_pool_mu);
     size_t idle = 0;
     for (auto& b : g_pool) idle += b.busy ? 0 : 1;
@@ -423,7 +424,7 @@ void table_free(dlv_table* t) {
     if (!t) return;
     TableBox* b = reinterpret_cast<TableBox*>(t);
     if (b->block) {
-        pool_give(b->block);
+        pinned_give(b->block);
     } else {
         free(t->voxel_counts); free(t->sums); free(t->bbox); free(t->centroids);
     }
@@ -496,7 +497,7 @@ int ccl_run(Ctx* ctx, const uint8_t* mask, const int64_t shape[3], uint32_t* L, 
         if (n > 0) {
             // one pinned block: counts [rows] | sums [rows][3] | bbox [rows][6] | centroids [rows][3]
             const size_t bytes = rows * (8 + 24 + 48 + 24);
-            box->block = pool_take(bytes, &box->cap);
+            box->block = pinned_take(bytes, &box->cap);
             if (!box->block) { set_error(ctx, "dlv_ccl: pinned host table allocation failed (%zu bytes)", bytes); rc = DLV_ERR_CUDA; goto done; }
             uint8_t* hb = static_cast<uint8_t*>(box->block);
             T->voxel_counts = reinterpret_cast<uint64_t*>(hb);

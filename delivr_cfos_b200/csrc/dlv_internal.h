@@ -72,6 +72,9 @@ struct Ctx {
     int64_t ccl_launches = 0;
     bool use_fused = true;      // Cout = 32 layers on the input-stationary fused kernel (DLV_FUSED=0 selects the per-tap kernel)
     int is_tiles = 0;           // 0 = heuristic; 2 / 4 force the tile count per column (DLV_IS_T)
+    uint32_t* paint_owner = nullptr;   // painter scratch (dlv_paint.cu), all-zero between calls when paint_owner_clean
+    size_t paint_owner_cap = 0;        // voxels
+    bool paint_owner_clean = false;
 };
 
 void set_error(Ctx* ctx, const char* fmt, ...);
@@ -126,6 +129,9 @@ constexpr float kSkipLogit = -1000.f;   // sliding_window_inferer.py:199-200
 // dlv_ccl.cu
 int ccl_run(Ctx* ctx, const uint8_t* mask_dev, const int64_t shape[3], uint32_t* labels_dev, dlv_table** table_out);
 void table_free(dlv_table* t);
+// pinned host blocks from the library's small process-wide pool (table rows, painter box lists)
+void* pinned_take(size_t bytes, size_t* cap_out);
+void pinned_give(void* p);
 
 // dlv_paint.cu
 int paint_boxes(Ctx* ctx, const void* mask_any, const int64_t shape[3], const int64_t* boxes_host, const int64_t* values_host,

@@ -15,7 +15,13 @@
 //                    are reset on the way, so the scratch is cleared once, not once per chunk.
 // Algorithmic bytes per voxel: 1 (mask) + nch * elem_bytes (outputs); the owner scratch (4 B, touched only around
 // foreground) is overhead counted against the achieved fraction.
+#include <limits.h>
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <algorithm>
+#include <chrono>
+#include <thread>
 #include <vector>
 
 #include "dlv_internal.h"
@@ -29,16 +35,16 @@ struct PaintGeom {
 
 constexpr int64_t kPaintBigBox = 1 << 15;   // voxels (after clipping to the chunk) above which a box is painted by the whole grid
 
-__device__ __forceinline__ bool clip_box(const int64_t* __restrict__ b, const PaintGeom& g, int64_t Z, int64_t& za, int64_t& zb,
+__device__ __forceinline__ bool clip_box(const int32_t* __restrict__ b, const PaintGeom& g, int64_t Z, int64_t& za, int64_t& zb,
                                          int64_t& ya, int64_t& yb, int64_t& xa, int64_t& xb) {
     // numpy slice semantics for non-negative bounds: clipped at the array end, empty when start >= stop
-    za = max(b[0], g.z0); zb = min(min(b[1], Z), g.z1);
-    ya = b[2]; yb = min(b[3], g.Y);
-    xa = b[4]; xb = min(b[5], g.X);
+    za = max(static_cast<int64_t>(b[0]), g.z0); zb = min(min(static_cast<int64_t>(b[1]), Z), g.z1);
+    ya = b[2]; yb = min(static_cast<int64_t>(b[3]), g.Y);
+    xa = b[4]; xb = min(static_cast<int64_t>(b[5]), g.X);
     return za < zb && ya < yb && xa < xb;
 }
 
-__global__ void paint_owner_small_kernel(const uint8_t* __restrict__ mask, const int64_t* __restrict__ boxes, int64_t n, int64_t Z,
+__global__ void paint_owner_small_kernel(const uint8_t* __restrict__ mask, const int32_t* __restrict__ boxes, int64_t n, int64_t Z,
                                          PaintGeom g, uint32_t* __restrict__ owner, uint32_t* __restrict__ big, uint32_t* __restrict__ nbig) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -61,7 +67,7 @@ __global__ void paint_owner_small_kernel(const uint8_t* __restrict__ mask, const
     }
 }
 
-__global__ void paint_owner_big_kernel(const uint8_t* __restrict__ mask, const int64_t* __restrict__ boxes, int64_t Z, PaintGeom g,
+__global__ void paint_owner_big_kernel(const uint8_t* __restrict__ mask, const int32_t* __restrict__ boxes, int64_t Z, PaintGeom g,
                                        uint32_t* __restrict__ owner, const uint32_t* __restrict__ big, const uint32_t* __restrict__ nbig) {
     const uint32_t nb = *nbig;
     const int64_t t0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -84,34 +90,56 @@ struct PaintOut {
     void* p[3];
 };
 
-// 4 voxels per thread (owner uint4, mask uchar4, outputs 4 or 8 B per channel); `n4` whole quads, then a scalar tail.
+// Resolve.  Each lane takes 16 consecutive voxels: one 16 B mask load and 16 B (uint8) / 2 x 16 B (uint16) streaming
+// ZERO stores per channel - 98 % of a blob volume is background and this is all that happens there.  Lanes whose 16
+// voxels contain foreground are then served one after the other by the first 16 lanes of the warp, one voxel per
+// lane: owner lookup + reset, value lookup, element store over the zeros (ordered by __syncwarp).  Doing the 16 x nch
+// conditional look-ups inside the lane that owns the group made nearly every warp walk ~600 predicated instructions
+// (1.5-1.8 TB/s, instruction-bound).  `n16` whole groups when every pointer of the chunk is 16 B aligned (vec),
+// then a scalar tail.
 template <typename T>
 __global__ void paint_resolve_kernel(const uint8_t* __restrict__ mask, uint32_t* __restrict__ owner, int64_t nvox,
                                      const uint16_t* __restrict__ values, int nch, PaintOut out, int vec) {
-    const int64_t n4 = vec ? (nvox >> 2) : 0;       // vec: mask and outputs of this chunk are aligned for 4-voxel accesses
+    const int64_t n16 = vec ? (nvox >> 4) : 0;
+    const int lane = threadIdx.x & 31;
     const int64_t t0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t nt = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    for (int64_t q = t0; q < n4; q += nt) {
-        const uchar4 m = reinterpret_cast<const uchar4*>(mask)[q];
-        uint4 o = make_uint4(0u, 0u, 0u, 0u);
-        if (m.x | m.y | m.z | m.w) {                    // owner is non-zero only on foreground voxels
-            o = reinterpret_cast<const uint4*>(owner)[q];
-            if (o.x | o.y | o.z | o.w) reinterpret_cast<uint4*>(owner)[q] = make_uint4(0u, 0u, 0u, 0u);
+    for (int64_t qb = t0 - lane; qb < n16; qb += nt) {       // warp-uniform trip count
+        const int64_t q = qb + lane;
+        uint4 m4 = make_uint4(0u, 0u, 0u, 0u);
+        if (q < n16) {
+            m4 = __ldcs(reinterpret_cast<const uint4*>(mask) + q);
+            const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+            for (int c = 0; c < nch; ++c) {
+                uint4* o = reinterpret_cast<uint4*>(out.p[c]) + q * sizeof(T);
+                __stcs(o, z4);
+                if (sizeof(T) == 2) __stcs(o + 1, z4);
+            }
         }
-        for (int c = 0; c < nch; ++c) {
-            T r[4];
-            r[0] = o.x ? static_cast<T>(static_cast<uint32_t>(m.x) * values[static_cast<int64_t>(o.x - 1) * nch + c]) : T(0);
-            r[1] = o.y ? static_cast<T>(static_cast<uint32_t>(m.y) * values[static_cast<int64_t>(o.y - 1) * nch + c]) : T(0);
-            r[2] = o.z ? static_cast<T>(static_cast<uint32_t>(m.z) * values[static_cast<int64_t>(o.z - 1) * nch + c]) : T(0);
-            r[3] = o.w ? static_cast<T>(static_cast<uint32_t>(m.w) * values[static_cast<int64_t>(o.w - 1) * nch + c]) : T(0);
-            if (sizeof(T) == 1) {
-                reinterpret_cast<uchar4*>(out.p[c])[q] = make_uchar4(r[0], r[1], r[2], r[3]);
-            } else {
-                reinterpret_cast<ushort4*>(out.p[c])[q] = make_ushort4(r[0], r[1], r[2], r[3]);
+        unsigned pending = __ballot_sync(0xffffffffu, (m4.x | m4.y | m4.z | m4.w) != 0u);
+        if (!pending) continue;
+        __syncwarp();                                        // the zero stores above precede the element stores below
+        while (pending) {
+            const int src = __ffs(pending) - 1;
+            pending &= pending - 1;
+            const uint32_t mx = __shfl_sync(0xffffffffu, m4.x, src), my = __shfl_sync(0xffffffffu, m4.y, src);
+            const uint32_t mz = __shfl_sync(0xffffffffu, m4.z, src), mw = __shfl_sync(0xffffffffu, m4.w, src);
+            if (lane < 16) {
+                const uint32_t word = (lane & 8) ? ((lane & 4) ? mw : mz) : ((lane & 4) ? my : mx);
+                const uint32_t mb = (word >> (8 * (lane & 3))) & 0xFFu;
+                if (mb) {
+                    const int64_t v = ((qb + src) << 4) + lane;
+                    const uint32_t o = owner[v];
+                    if (o) {
+                        owner[v] = 0u;
+                        for (int c = 0; c < nch; ++c)
+                            static_cast<T*>(out.p[c])[v] = static_cast<T>(mb * values[static_cast<int64_t>(o - 1) * nch + c]);
+                    }
+                }
             }
         }
     }
-    for (int64_t v = (n4 << 2) + t0; v < nvox; v += nt) {
+    for (int64_t v = (n16 << 4) + t0; v < nvox; v += nt) {
         const uint32_t m = mask[v];
         uint32_t o = 0;
         if (m) { o = owner[v]; if (o) owner[v] = 0; }
@@ -151,13 +179,21 @@ static bool is_dev(const void* p) {
 int paint_boxes(Ctx* ctx, const void* mask_any, const int64_t shape[3], const int64_t* boxes_host, const int64_t* values_host,
                 int64_t n, int nch, int elem_bytes, void* const* out_any, int64_t chunk_voxels) {
     const int64_t Z = shape[0], Y = shape[1], X = shape[2];
+    // DLV_TRACE=1: host wall clock per phase on stderr (adds a stream synchronisation at every mark)
+    static const bool trace = getenv("DLV_TRACE") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (!trace) return;
+        cudaStreamSynchronize(ctx->stream);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[dlv_paint] %-22s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
     if (Z < 0 || Y < 0 || X < 0 || n < 0 || nch < 1 || nch > 3 || (elem_bytes != 1 && elem_bytes != 2)) {
         set_error(ctx, "dlv_paint_boxes: bad shape / channel count / element size");
         return DLV_ERR_ARG;
     }
     if (n >= 0xFFFFFFFFll) { set_error(ctx, "dlv_paint_boxes: more than 2^32 - 2 boxes"); return DLV_ERR_UNSUPPORTED; }
-    for (int64_t i = 0; i < n * 6; ++i)
-        if (boxes_host[i] < 0) { set_error(ctx, "dlv_paint_boxes: negative slice bound in box %lld", static_cast<long long>(i / 6)); return DLV_ERR_ARG; }
     const int64_t plane = Y * X;
     if (Z == 0 || plane == 0) return 0;
     const bool mask_dev = is_dev(mask_any);
@@ -166,10 +202,47 @@ int paint_boxes(Ctx* ctx, const void* mask_any, const int64_t shape[3], const in
         if (!out_any[c]) { set_error(ctx, "dlv_paint_boxes: null output %d", c); return DLV_ERR_ARG; }
         out_dev[c] = is_dev(out_any[c]);
     }
-    // the multiply happens modulo the output width (numpy casts the int64 product on assignment)
-    std::vector<uint16_t> vals(static_cast<size_t>(std::max<int64_t>(n, 1)) * nch);
-    for (int64_t i = 0; i < n * nch; ++i) vals[i] = static_cast<uint16_t>(static_cast<uint64_t>(values_host[i]) & (elem_bytes == 1 ? 0xFFu : 0xFFFFu));
+    // Box list and values are narrowed (slice bounds clipped to int32 - anything larger is beyond the array anyway -
+    // values modulo the output width, which is what numpy's cast of the int64 product does) straight into one pinned
+    // block from the library's pool, on a few host threads: the upload then runs at PCIe speed instead of through the
+    // driver's pageable staging (71 MB of int64 for the 1.3 M boxes of cfg3).
+    const size_t nbox = static_cast<size_t>(std::max<int64_t>(n, 1));
+    const size_t stage_bytes = nbox * 24 + nbox * nch * 2;
+    size_t stage_cap = 0;
+    uint8_t* stage = static_cast<uint8_t*>(pinned_take(stage_bytes, &stage_cap));
+    if (!stage) { set_error(ctx, "dlv_paint_boxes: pinned staging allocation failed (%zu bytes)", stage_bytes); return DLV_ERR_CUDA; }
+    int32_t* hbox = reinterpret_cast<int32_t*>(stage);
+    uint16_t* hval = reinterpret_cast<uint16_t*>(stage + nbox * 24);
+    {
+        const uint64_t vmask = elem_bytes == 1 ? 0xFFu : 0xFFFFu;
+        const int nthr = n > 200000 ? static_cast<int>(std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()))) : 1;
+        std::vector<int64_t> bad(nthr, -1);
+        auto work = [&](int t) {
+            const int64_t i0 = n * t / nthr, i1 = n * (t + 1) / nthr;
+            for (int64_t i = i0; i < i1; ++i) {
+                for (int k = 0; k < 6; ++k) {
+                    const int64_t v = boxes_host[6 * i + k];
+                    if (v < 0 && bad[t] < 0) bad[t] = i;
+                    hbox[6 * i + k] = static_cast<int32_t>(std::min<int64_t>(std::max<int64_t>(v, 0), INT32_MAX));
+                }
+                for (int c = 0; c < nch; ++c) hval[i * nch + c] = static_cast<uint16_t>(static_cast<uint64_t>(values_host[i * nch + c]) & vmask);
+            }
+        };
+        if (nthr == 1) work(0);
+        else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < nthr; ++t) th.emplace_back(work, t);
+            for (auto& x : th) x.join();
+        }
+        for (int t = 0; t < nthr; ++t)
+            if (bad[t] >= 0) {
+                pinned_give(stage);
+                set_error(ctx, "dlv_paint_boxes: negative slice bound in box %lld", static_cast<long long>(bad[t]));
+                return DLV_ERR_ARG;
+            }
+    }
 
+    mark("narrow to pinned");
     if (chunk_voxels <= 0) {
         // every z-chunk scans the whole box list, so the default is as few chunks as memory allows: the 4 B/voxel owner
         // scratch may take a quarter of the free device memory (cfg3: one chunk, 16.8 GB)
@@ -180,10 +253,12 @@ int paint_boxes(Ctx* ctx, const void* mask_any, const int64_t shape[3], const in
     }
     const int64_t cz = std::max<int64_t>(1, std::min(Z, chunk_voxels / plane));
     const int64_t cvox = cz * plane;
-    int64_t* boxes = nullptr; uint16_t* values = nullptr; uint32_t *owner = nullptr, *big = nullptr, *nbig = nullptr;
+    int32_t* boxes = nullptr; uint16_t* values = nullptr; uint32_t *owner = nullptr, *big = nullptr, *nbig = nullptr;
     uint8_t* mask_buf = nullptr; void* out_buf[3] = {nullptr, nullptr, nullptr};
     auto cleanup = [&]() {
-        dfree(ctx, boxes); dfree(ctx, values); dfree(ctx, owner); dfree(ctx, big); dfree(ctx, nbig); dfree(ctx, mask_buf);
+        cudaStreamSynchronize(ctx->stream);          // the pinned block must not return to the pool while a copy reads it
+        pinned_give(stage);
+        dfree(ctx, boxes); dfree(ctx, values); dfree(ctx, big); dfree(ctx, nbig); dfree(ctx, mask_buf);
         for (int c = 0; c < 3; ++c) dfree(ctx, out_buf[c]);
     };
 #define PAINT_OK(expr)                                                                                                   \
@@ -191,18 +266,29 @@ int paint_boxes(Ctx* ctx, const void* mask_any, const int64_t shape[3], const in
         cudaError_t _e = (expr);                                                                                         \
         if (_e != cudaSuccess) { set_error(ctx, "dlv_paint_boxes: %s failed: %s", #expr, cudaGetErrorString(_e)); cleanup(); return DLV_ERR_CUDA; } \
     } while (0)
-    PAINT_OK(dmalloc(ctx, &boxes, static_cast<size_t>(std::max<int64_t>(n, 1)) * 48));
-    PAINT_OK(dmalloc(ctx, &values, vals.size() * 2));
-    PAINT_OK(dmalloc(ctx, &owner, static_cast<size_t>(cvox) * 4));
+    PAINT_OK(dmalloc(ctx, &boxes, nbox * 24));
+    PAINT_OK(dmalloc(ctx, &values, nbox * nch * 2));
+    // The owner scratch is kept by the context between calls: paint_resolve leaves it all-zero, so only a new (or larger)
+    // scratch - or one left behind by a failed call - has to be cleared (16.8 GB for cfg3: 3-4 ms per call otherwise).
+    if (ctx->paint_owner_cap < static_cast<size_t>(cvox)) {
+        dfree(ctx, ctx->paint_owner);
+        ctx->paint_owner = nullptr; ctx->paint_owner_cap = 0;
+        PAINT_OK(dmalloc(ctx, &ctx->paint_owner, static_cast<size_t>(cvox) * 4));
+        ctx->paint_owner_cap = static_cast<size_t>(cvox);
+        ctx->paint_owner_clean = false;
+    }
+    owner = ctx->paint_owner;
+    if (!ctx->paint_owner_clean) PAINT_OK(cudaMemsetAsync(owner, 0, ctx->paint_owner_cap * 4, ctx->stream));
+    ctx->paint_owner_clean = false;
     PAINT_OK(dmalloc(ctx, &big, static_cast<size_t>(std::max<int64_t>(n, 1)) * 4));
     PAINT_OK(dmalloc(ctx, &nbig, 4));
     if (!mask_dev) PAINT_OK(dmalloc(ctx, &mask_buf, static_cast<size_t>(cvox)));
     for (int c = 0; c < nch; ++c)
         if (!out_dev[c]) PAINT_OK(dmalloc(ctx, &out_buf[c], static_cast<size_t>(cvox) * elem_bytes));
-    if (n > 0) PAINT_OK(cudaMemcpyAsync(boxes, boxes_host, static_cast<size_t>(n) * 48, cudaMemcpyHostToDevice, ctx->stream));
-    PAINT_OK(cudaMemcpyAsync(values, vals.data(), vals.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
-    PAINT_OK(cudaMemsetAsync(owner, 0, static_cast<size_t>(cvox) * 4, ctx->stream));
+    PAINT_OK(cudaMemcpyAsync(boxes, hbox, nbox * 24, cudaMemcpyHostToDevice, ctx->stream));
+    PAINT_OK(cudaMemcpyAsync(values, hval, nbox * nch * 2, cudaMemcpyHostToDevice, ctx->stream));
 
+    mark("alloc + upload");
     const int grid = ctx->num_sms * 8;
     for (int64_t z0 = 0; z0 < Z; z0 += cz) {
         const int64_t z1 = std::min(Z, z0 + cz), nv = (z1 - z0) * plane;
@@ -221,11 +307,13 @@ int paint_boxes(Ctx* ctx, const void* mask_any, const int64_t shape[3], const in
             paint_owner_big_kernel<<<grid, 256, 0, ctx->stream>>>(m, boxes, Z, g, owner, big, nbig);
             ctx->launches += 2;
         }
-        int vec = (reinterpret_cast<uintptr_t>(m) & 3u) == 0;
-        for (int c = 0; c < nch; ++c) vec = vec && (reinterpret_cast<uintptr_t>(po.p[c]) & (4u * elem_bytes - 1u)) == 0;
+        mark("owner kernels");
+        int vec = (reinterpret_cast<uintptr_t>(m) & 15u) == 0;       // the owner scratch is always aligned
+        for (int c = 0; c < nch; ++c) vec = vec && (reinterpret_cast<uintptr_t>(po.p[c]) & 15u) == 0;
         if (elem_bytes == 1) paint_resolve_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>(m, owner, nv, values, nch, po, vec);
         else paint_resolve_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(m, owner, nv, values, nch, po, vec);
         ctx->launches += 1;
+        mark("resolve kernel");
         for (int c = 0; c < nch; ++c)
             if (!out_dev[c])
                 PAINT_OK(cudaMemcpyAsync(static_cast<uint8_t*>(out_any[c]) + z0 * plane * elem_bytes, out_buf[c],
@@ -235,7 +323,9 @@ int paint_boxes(Ctx* ctx, const void* mask_any, const int64_t shape[3], const in
     PAINT_OK(cudaGetLastError());
     PAINT_OK(cudaStreamSynchronize(ctx->stream));
 #undef PAINT_OK
+    ctx->paint_owner_clean = true;                   // every entry that was set has been reset by paint_resolve
     cleanup();
+    mark("release");
     return 0;
 }
 

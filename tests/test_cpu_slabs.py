@@ -239,3 +239,23 @@ def test_virtual_slabs_equal_single_oracle():
         assert np.array_equal(np.concatenate([w.binaries.numpy() for w in ws]), w1.binaries.numpy())
         assert np.array_equal(np.concatenate([w.labels.numpy() for w in ws]), w1.labels.numpy())
         assert t["n"] == t1["n"] and np.array_equal(t["sums"], t1["sums"])
+
+
+@pytest.mark.parametrize("overlap,shape,roi", [(0.25, (50, 24, 24), (16, 16, 16)), (0.75, (40, 24, 24), (16, 16, 16)),
+                                               (0.5, (33, 40, 20), (16, 32, 16))])
+def test_virtual_slabs_other_overlaps(overlap, shape, roi):
+    """BASELINE.json configs[4] sweeps the overlap: with 0.75 a plane is covered by four window layers, so the sums a
+    rank touches beyond its own planes reach further down the chain; with 0.25 layers barely overlap."""
+    volume = _make_volume(shape, roi)
+    st = _starts(volume.shape, roi, overlap)
+    plan1 = slabs.SlabPlan(shape, roi, overlap, 1, starts=st, erosion_iters=3)
+    w1 = OracleWorker(plan1, 0, volume)
+    t1 = slabs.run_virtual([w1], plan1)
+    nwin = len(st[0]) * len(st[1]) * len(st[2])
+    for world in (2, 3, 5, 9, nwin + 2):
+        plan = slabs.SlabPlan(shape, roi, overlap, world, starts=st, erosion_iters=3)
+        ws = [OracleWorker(plan, r, volume) for r in range(world)]
+        t = slabs.run_virtual(ws, plan)
+        assert np.array_equal(np.concatenate([w.binaries.numpy() for w in ws]), w1.binaries.numpy()), world
+        assert np.array_equal(np.concatenate([w.labels.numpy() for w in ws]), w1.labels.numpy()), world
+        assert t["n"] == t1["n"] and np.array_equal(t["sums"], t1["sums"]) and np.array_equal(t["bounding_boxes"], t1["bounding_boxes"])
