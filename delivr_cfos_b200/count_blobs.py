@@ -60,25 +60,26 @@ def csv_text(stats, n):
 
 
 def statistics_from_labels(labels):
-    """cc3d.statistics equivalent for a cached label volume (count_blobs.py:71-76,85): exact host reduction."""
+    """cc3d.statistics equivalent for a cached label volume (count_blobs.py:71-76,85): exact host reduction, one
+    stable sort of the label volume and segment reductions (no per-label Python loop)."""
     lab = np.asarray(labels)
     n = int(lab.max()) if lab.size else 0
     flat = lab.reshape(-1).astype(np.int64)
     counts = np.bincount(flat, minlength=n + 1).astype(np.uint64)
     sums = np.zeros((n + 1, 3), dtype=np.uint64)
     bbox = np.zeros((n + 1, 6), dtype=np.int64)
-    idx = np.arange(flat.size, dtype=np.int64)
-    coords = np.unravel_index(idx, lab.shape)
     order = np.argsort(flat, kind="stable")
-    bounds = np.searchsorted(flat[order], np.arange(n + 2))
+    bounds = np.concatenate([[0], np.cumsum(counts.astype(np.int64))])
+    present = counts > 0
+    starts = bounds[:-1][present]                       # reduceat needs non-empty, increasing segments
+    coords = np.unravel_index(order, lab.shape)          # coordinates in label-sorted order
     for ax in range(3):
-        c = coords[ax][order]
-        csum = np.concatenate([[0], np.cumsum(c, dtype=np.uint64)])
-        sums[:, ax] = csum[bounds[1:]] - csum[bounds[:-1]]
-        for l in range(n + 1):
-            seg = c[bounds[l]:bounds[l + 1]]
-            bbox[l, 2 * ax] = seg.min() if seg.size else lab.shape[ax]
-            bbox[l, 2 * ax + 1] = seg.max() if seg.size else -1
+        c = coords[ax].astype(np.int64)
+        bbox[:, 2 * ax], bbox[:, 2 * ax + 1] = lab.shape[ax], -1          # labels without voxels: neutral box
+        if len(starts):
+            sums[present, ax] = np.add.reduceat(c.astype(np.uint64), starts)
+            bbox[present, 2 * ax] = np.minimum.reduceat(c, starts)
+            bbox[present, 2 * ax + 1] = np.maximum.reduceat(c, starts)
     with np.errstate(invalid="ignore", divide="ignore"):
         cent = sums.astype(np.float64) / counts.astype(np.float64)[:, None]
     return {"voxel_counts": counts, "bounding_boxes": bbox, "centroids": cent}

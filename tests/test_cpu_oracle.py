@@ -119,3 +119,23 @@ def test_arrayterator_blocks_match_numpy():
     from delivr_cfos_b200.inference.inference import erosion_block_planes
     assert erosion_block_planes((1500, 4000, 4000)) == 62                    # SURVEY finding 8
     assert erosion_block_planes((64, 512, 512)) == 0
+
+
+@pytest.mark.parametrize("shape,p", [((20, 33, 17), 0.08), ((16, 16, 16), 0.5), ((1, 1, 1), 1.0), ((40, 64, 64), 0.1)])
+def test_statistics_from_cached_labels(shape, p):
+    """count_blobs.py:71-76: a cached label volume without a cached statistics pickle -> statistics from the labels.
+    The host reduction (product code, no GPU involved) equals the oracle, also when a label value is missing."""
+    from delivr_cfos_b200.count_blobs import statistics_from_labels
+    m = P.synth_mask(shape, 3, kind="bernoulli", p=p)
+    lab, n = ccl_ref.connected_components26(m)
+    r = ccl_ref.statistics(lab, n)
+    s = statistics_from_labels(lab)
+    assert np.array_equal(s["voxel_counts"], r["voxel_counts"])
+    assert np.array_equal(s["bounding_boxes"], r["bounding_boxes"])
+    assert np.array_equal(s["centroids"], r["centroids"], equal_nan=True)
+    if n >= 3:
+        lab2 = lab.copy()
+        lab2[lab2 == 2] = 0
+        s2 = statistics_from_labels(lab2)
+        assert s2["voxel_counts"][2] == 0 and tuple(s2["bounding_boxes"][2]) == (shape[0], -1, shape[1], -1, shape[2], -1)
+        assert np.array_equal(s2["voxel_counts"][3:], r["voxel_counts"][3:])
