@@ -52,10 +52,10 @@ def csv_text(stats, n):
     Header ``,Blob,Coords,Size``; one row per label 1..N-1: index column always 0,
     Coords = str(list of python floats) quoted because it contains commas.
     """
-    cent, cnt = stats["centroids"], stats["voxel_counts"]
+    cent = np.asarray(stats["centroids"])[1:n].tolist()          # python floats: str(list) prints their repr
+    cnt = np.asarray(stats["voxel_counts"])[1:n].tolist()
     out = [",Blob,Coords,Size\n"]
-    for i in range(1, n):
-        out.append(f'0,{i},"{[float(c) for c in cent[i]]}",{int(cnt[i])}\n')
+    out.extend(f'0,{i},"{c}",{k}\n' for i, (c, k) in enumerate(zip(cent, cnt), 1))
     return "".join(out)
 
 
