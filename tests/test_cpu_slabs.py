@@ -259,3 +259,65 @@ def test_virtual_slabs_other_overlaps(overlap, shape, roi):
         assert np.array_equal(np.concatenate([w.binaries.numpy() for w in ws]), w1.binaries.numpy()), world
         assert np.array_equal(np.concatenate([w.labels.numpy() for w in ws]), w1.labels.numpy()), world
         assert t["n"] == t1["n"] and np.array_equal(t["sums"], t1["sums"]) and np.array_equal(t["bounding_boxes"], t1["bounding_boxes"])
+
+
+def test_plan_invariants_random_configs():
+    """Seeded sweep over window shapes, overlaps (0.25 / 0.5 / 0.75) and rank counts - the plan must hand every window
+    to exactly one rank, every plane to exactly one owner, keep everything a rank touches inside its slab, and pass
+    on whatever it touches beyond its own planes."""
+    rng = np.random.default_rng(11)
+    for _ in range(120):
+        roi = tuple(int(16 * rng.integers(1, 5)) for _ in range(3))
+        shape = tuple(int(rng.integers(r // 2 + 1, 5 * r)) for r in roi)
+        overlap = float(rng.choice([0.25, 0.5, 0.75]))
+        world = int(rng.integers(1, 12))
+        pad = P.padded_shape(shape, roi)
+        st = _starts(pad, roi, overlap)
+        nwin = len(st[0]) * len(st[1]) * len(st[2])
+        act = (rng.random(nwin) < 0.7).astype(np.int32)
+        plan = slabs.SlabPlan(shape, roi, overlap, world, starts=st, window_weights=act if rng.random() < 0.5 else None)
+        owned = np.zeros(pad[0], int)
+        wins = []
+        for r in range(world):
+            info = plan.rank(r)
+            c0, c1 = plan.wrange[r]
+            wins += list(range(c0, c1))
+            owned[info["own"][0]:info["own"][1]] += 1
+            if c1 == c0:
+                continue
+            w = plan.windows_of(r)
+            assert info["win"] == (int(w[:, 0].min()), int(w[:, 0].max()) + roi[0])
+            touched = max(info["win"][1], info["recv"][1] if info["recv"] else 0)
+            assert info["slab"][0] <= min(info["own"][0], info["win"][0]) and info["slab"][1] >= touched
+            assert info["slab"][0] <= max(0, info["own"][0] - 31) and info["slab"][1] >= min(pad[0], info["own"][1] + 31)
+            nxt = plan._next_nonempty(r)
+            if nxt is None:
+                assert info["send"] is None and info["own"][1] == pad[0]
+            else:
+                assert (info["send"] is None) == (touched <= info["own"][1])
+                if info["send"]:
+                    assert info["send"] == (info["own"][1], touched) == plan.rank(nxt)["recv"]
+            # nothing a rank computes lands on a plane below its own planes
+            assert info["win"][0] >= info["own"][0]
+        assert wins == list(range(nwin)) and (owned == 1).all(), (shape, roi, overlap, world)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_virtual_slabs_random_configs(seed):
+    rng = np.random.default_rng(seed)
+    roi = tuple(int(16 * rng.integers(1, 3)) for _ in range(3))
+    shape = tuple(int(rng.integers(r, 3 * r)) for r in roi)
+    overlap = float(rng.choice([0.25, 0.5, 0.75]))
+    volume = _make_volume(shape, roi)
+    st = _starts(volume.shape, roi, overlap)
+    plan1 = slabs.SlabPlan(shape, roi, overlap, 1, starts=st, erosion_iters=3)
+    w1 = OracleWorker(plan1, 0, volume)
+    t1 = slabs.run_virtual([w1], plan1)
+    for world in (2, 4, 7):
+        act = (rng.random(len(st[0]) * len(st[1]) * len(st[2])) < 0.8).astype(np.int32)
+        plan = slabs.SlabPlan(shape, roi, overlap, world, starts=st, erosion_iters=3, window_weights=act)
+        ws = [OracleWorker(plan, r, volume) for r in range(world)]
+        t = slabs.run_virtual(ws, plan)
+        assert np.array_equal(np.concatenate([w.binaries.numpy() for w in ws]), w1.binaries.numpy()), (shape, roi, overlap, world)
+        assert np.array_equal(np.concatenate([w.labels.numpy() for w in ws]), w1.labels.numpy())
+        assert t["n"] == t1["n"] and np.array_equal(t["voxel_counts"], t1["voxel_counts"])
