@@ -52,7 +52,7 @@ EXPORTS = [
     "dlv_ccl_last_timing", "dlv_unet_forward", "dlv_op_conv3d", "dlv_op_deconv", "dlv_op_finalise",
     "dlv_window_grid", "dlv_windows_active", "dlv_seg_accumulate", "dlv_seg_average", "dlv_op_finalise_slab",
     "dlv_ccl_boundary_pairs", "dlv_relabel", "dlv_table_merge", "dlv_tiff_info", "dlv_tiff_read_u16", "dlv_tiff_last_error",
-    "dlv_load_tiff_planes", "dlv_paint_boxes", "dlv_edt",
+    "dlv_load_tiff_planes", "dlv_tiff_write_planes", "dlv_tiff_write_last_error", "dlv_paint_boxes", "dlv_edt",
 ]
 
 _lib = None
@@ -129,6 +129,10 @@ def load_library():
                                        ctypes.c_int]
     L.dlv_paint_boxes.restype = ctypes.c_int
     L.dlv_paint_boxes.argtypes = [c_vp, c_vp, P(c_i64), c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, P(c_vp), c_i64]
+    L.dlv_tiff_write_planes.restype = ctypes.c_int
+    L.dlv_tiff_write_planes.argtypes = [P(ctypes.c_char_p), ctypes.c_int, c_vp, c_i64, c_i64, c_i32, c_i32, ctypes.c_int]
+    L.dlv_tiff_write_last_error.restype = ctypes.c_char_p
+    L.dlv_tiff_write_last_error.argtypes = []
     L.dlv_table_merge.restype = ctypes.c_int
     L.dlv_table_merge.argtypes = [c_i64, ctypes.c_int, P(c_i64), P(c_vp), P(c_vp), P(c_vp), P(c_vp), P(c_i64), P(c_i64),
                                   c_vp, c_vp, c_vp, c_vp]
@@ -425,6 +429,19 @@ def tiff_read_u16(path):
     if L.dlv_tiff_read_u16(os.fsencode(path), out.ctypes.data, h, w) != 0:
         raise DlvError(f"dlv_tiff_read_u16: {L.dlv_tiff_last_error().decode()}")
     return out
+
+
+def tiff_write_planes(paths, volume, compression=5, nthreads=0):
+    """Plane z of ``volume`` ((Z, Y, X) uint8 or uint16, host) -> paths[z]; LZW by default like the reference's
+    tifffile.imwrite(..., compression='lzw') (blob_highlighter.py:131-133); planes are compressed on all host threads."""
+    L = load_library()
+    v = np.ascontiguousarray(volume)
+    if v.ndim != 3 or v.dtype not in (np.uint8, np.uint16) or len(paths) != v.shape[0]:
+        raise ValueError("volume must be (Z, Y, X) uint8 / uint16 with one path per plane")
+    arr = (ctypes.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+    if L.dlv_tiff_write_planes(arr, len(paths), v.ctypes.data, v.shape[1], v.shape[2], v.dtype.itemsize * 8, int(compression),
+                               int(nthreads)) != 0:
+        raise DlvError(f"dlv_tiff_write_planes: {L.dlv_tiff_write_last_error().decode()}")
 
 
 def table_merge(tables, luts, z_offsets, n_global, shape_real):

@@ -2,7 +2,8 @@
 
 Same signature, config keys (``visualization.*``, ``postprocessing.output_location``, ``FLAGS.LOAD_ALL_RAM``) and
 output files (``<out>/<brain>_rgb_tiffs/<brain>rgb_C0{0,1,2}_zNNNN.tif`` uint8 and
-``<out>/<brain>/<brain>_region_id_tiffs/region_id_NNNN.tif`` uint16, LZW).  The per-cell Python loops that paint
+``<out>/<brain>/<brain>_region_id_tiffs/region_id_NNNN.tif`` uint16, LZW; written by ``dlv_tiff_write_planes`` on all
+host threads - same pixels, not the same bytes as tifffile's).  The per-cell Python loops that paint
 every blob through its bounding box (blob_highlighter.py:107-124, :143-151) run as ``dlv_paint_boxes`` on the GPU;
 connected components, when no cached statistics exist (:81-90), run as ``dlv_ccl`` instead of a second cc3d pass.
 
@@ -54,10 +55,10 @@ def padded_boxes(stats, cc_ids, stack_shape):
 
 
 def _write_planes(fmt, vol):
-    import cv2
-    for z in range(vol.shape[0]):
-        if not cv2.imwrite(fmt.format(z=str(z).zfill(4)), vol[z]):      # TIFF, LZW (OpenCV's default)
-            raise IOError(f"cannot write {fmt.format(z=str(z).zfill(4))}")
+    """One LZW TIFF per z plane (blob_highlighter.py:127-133: tifffile.imwrite(..., compression='lzw') in a loop),
+    compressed on all host threads by the library's writer."""
+    from ._lib import tiff_write_planes
+    tiff_write_planes([fmt.format(z=str(z).zfill(4)) for z in range(vol.shape[0])], vol, compression=5)
 
 
 def blob_highlighter(settings, brain_item, stack_shape, device=0):

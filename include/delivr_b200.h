@@ -218,6 +218,16 @@ const char* dlv_tiff_last_error(void);
 int dlv_load_tiff_planes(dlv_ctx* ctx, const char* const* paths, int n, int64_t Y, int64_t X, int32_t threshold,
                          const uint8_t* mask_dev_or_null, uint16_t* slab_dev, int64_t SY, int64_t SX, int nthreads);
 
+/* Host-only TIFF plane writer for the painter's outputs: plane i of volume_host (n planes of height x width samples,
+ * `bits` = 8 or 16, unsigned) -> paths[i], classic little-endian TIFF, strips, compression 1 (none) / 5 (LZW) /
+ * 8 (Deflate), planes compressed on `nthreads` host threads (<= 0: all cores).  Replaces the sequential
+ * tifffile.imwrite(path, plane, compression='lzw') loops (blob_highlighter.py:127-133, :158-161;
+ * blob_depthmap.py:209-213); any baseline reader returns the pixels that were written.  Message:
+ * dlv_tiff_write_last_error() (thread-local). */
+int dlv_tiff_write_planes(const char* const* paths, int n, const void* volume_host, int64_t height, int64_t width, int32_t bits,
+                          int32_t compression, int nthreads);
+const char* dlv_tiff_write_last_error(void);
+
 /* ---- blob painter ----
  * Replaces the per-cell bounding-box colouring loops of blob_highlighter.py:107-124 (R/G/B uint8 volumes),
  * :143-151 (region-id uint16 volume) and blob_depthmap.py:198-207 (depth uint16 volume):
