@@ -51,7 +51,7 @@ EXPORTS = [
     "dlv_synchronize", "dlv_set_conv_timing", "dlv_conv_time_ms", "dlv_load_weights", "dlv_segment", "dlv_ccl", "dlv_table_free",
     "dlv_ccl_last_timing", "dlv_unet_forward", "dlv_op_conv3d", "dlv_op_deconv", "dlv_op_finalise",
     "dlv_window_grid", "dlv_windows_active", "dlv_seg_accumulate", "dlv_seg_average", "dlv_op_finalise_slab",
-    "dlv_ccl_boundary_pairs", "dlv_relabel", "dlv_table_merge", "dlv_tiff_info", "dlv_tiff_read_u16", "dlv_tiff_last_error",
+    "dlv_ccl_boundary_pairs", "dlv_relabel", "dlv_table_merge", "dlv_resolve_labels", "dlv_tiff_info", "dlv_tiff_read_u16", "dlv_tiff_last_error",
     "dlv_load_tiff_planes", "dlv_tiff_write_planes", "dlv_tiff_write_last_error", "dlv_paint_boxes", "dlv_edt",
 ]
 
@@ -133,6 +133,8 @@ def load_library():
     L.dlv_tiff_write_planes.argtypes = [P(ctypes.c_char_p), ctypes.c_int, c_vp, c_i64, c_i64, c_i32, c_i32, ctypes.c_int]
     L.dlv_tiff_write_last_error.restype = ctypes.c_char_p
     L.dlv_tiff_write_last_error.argtypes = []
+    L.dlv_resolve_labels.restype = ctypes.c_int
+    L.dlv_resolve_labels.argtypes = [ctypes.c_int, P(c_i64), P(c_vp), P(c_i64), P(c_vp), P(c_i64)]
     L.dlv_table_merge.restype = ctypes.c_int
     L.dlv_table_merge.argtypes = [c_i64, ctypes.c_int, P(c_i64), P(c_vp), P(c_vp), P(c_vp), P(c_vp), P(c_i64), P(c_i64),
                                   c_vp, c_vp, c_vp, c_vp]
@@ -442,6 +444,29 @@ def tiff_write_planes(paths, volume, compression=5, nthreads=0):
     if L.dlv_tiff_write_planes(arr, len(paths), v.ctypes.data, v.shape[1], v.shape[2], v.dtype.itemsize * 8, int(compression),
                                int(nthreads)) != 0:
         raise DlvError(f"dlv_tiff_write_planes: {L.dlv_tiff_write_last_error().decode()}")
+
+
+def resolve_labels(counts, pairs):
+    """dlv_resolve_labels (host only): per-slab component counts + seam pairs -> (uint32 lookup tables, N_global)."""
+    L = load_library()
+    ns = len(counts)
+    cnt = (c_i64 * ns)(*[int(c) for c in counts])
+    keep, pp, npp = [], (c_vp * ns)(), (c_i64 * ns)()
+    for r in range(ns):
+        p = pairs[r] if r < len(pairs) else None
+        if r == 0 or p is None or len(p) == 0:
+            pp[r], npp[r] = None, 0
+            continue
+        a = np.ascontiguousarray(p, dtype=np.uint32).reshape(-1, 2)
+        keep.append(a)
+        pp[r], npp[r] = a.ctypes.data, len(a)
+    luts = [np.empty(int(c) + 1, dtype=np.uint32) for c in counts]
+    lp = (c_vp * ns)(*[l.ctypes.data for l in luts])
+    n = c_i64()
+    rc = L.dlv_resolve_labels(ns, cnt, pp, npp, lp, ctypes.byref(n))
+    if rc != 0:
+        raise DlvError(f"dlv_resolve_labels failed ({rc}): a seam pair names a label outside its slab's 1..N")
+    return luts, int(n.value)
 
 
 def table_merge(tables, luts, z_offsets, n_global, shape_real):

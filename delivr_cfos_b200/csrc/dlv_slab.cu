@@ -214,4 +214,48 @@ int dlv_table_merge(int64_t n_global, int ntables, const int64_t* rows, const ui
     return DLV_OK;
 }
 
+/* Host-only: global component numbering from per-slab counts and seam pairs (see include/delivr_b200.h). */
+int dlv_resolve_labels(int nslabs, const int64_t* counts, const uint32_t* const* pairs, const int64_t* npairs,
+                       uint32_t* const* luts_out, int64_t* n_global_out) {
+    if (nslabs < 0 || !counts || !pairs || !npairs || !luts_out || !n_global_out) return DLV_ERR_ARG;
+    std::vector<int64_t> off(static_cast<size_t>(nslabs) + 1, 0);
+    for (int r = 0; r < nslabs; ++r) {
+        if (counts[r] < 0) return DLV_ERR_ARG;
+        off[r + 1] = off[r] + counts[r];
+    }
+    const int64_t total = off[nslabs];
+    if (total >= 0xFFFFFFFFll) return DLV_ERR_UNSUPPORTED;
+    // node id of (slab r, local label l >= 1) = off[r] + l; the root of a set is its smallest id = the component's
+    // member in the lowest slab with the lowest local label = its first voxel in raster order
+    std::vector<uint32_t> parent(static_cast<size_t>(total) + 1);
+    for (int64_t i = 0; i <= total; ++i) parent[i] = static_cast<uint32_t>(i);
+    auto find = [&](uint32_t a) {
+        while (parent[a] != a) { parent[a] = parent[parent[a]]; a = parent[a]; }
+        return a;
+    };
+    for (int r = 1; r < nslabs; ++r) {
+        if (!pairs[r] || npairs[r] <= 0) continue;
+        for (int64_t k = 0; k < npairs[r]; ++k) {
+            const int64_t lo = pairs[r][2 * k], hi = pairs[r][2 * k + 1];
+            if (lo == 0 || hi == 0) continue;                                  // background: no adjacency
+            if (lo > counts[r - 1] || hi > counts[r]) return DLV_ERR_ARG;
+            const uint32_t a = find(static_cast<uint32_t>(off[r - 1] + lo)), b = find(static_cast<uint32_t>(off[r] + hi));
+            if (a < b) parent[b] = a; else if (b < a) parent[a] = b;
+        }
+    }
+    std::vector<uint32_t> label(static_cast<size_t>(total) + 1, 0u);
+    uint32_t n = 0;
+    for (int64_t i = 1; i <= total; ++i) {
+        const uint32_t root = find(static_cast<uint32_t>(i));
+        label[i] = (root == i) ? ++n : label[root];          // root < i: already numbered
+    }
+    for (int r = 0; r < nslabs; ++r) {
+        if (!luts_out[r]) return DLV_ERR_ARG;
+        luts_out[r][0] = 0u;
+        for (int64_t l = 1; l <= counts[r]; ++l) luts_out[r][l] = label[off[r] + l];
+    }
+    *n_global_out = n;
+    return DLV_OK;
+}
+
 }  // extern "C"

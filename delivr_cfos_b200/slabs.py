@@ -125,45 +125,11 @@ def resolve_global_labels(counts, pairs):
     counts[r] = N_r; pairs[r] = uint32 [k,2] of (label in slab r-1, label in slab r) (pairs[0] is empty).
     Components are numbered by their first voxel in raster order: slabs in z order, a merged component takes the
     number of its member in the lowest slab.  -> (list of uint32 lookup tables [N_r+1], N_global)
+    Runs in the library's host code (dlv_resolve_labels): a Python union-find over the ~1.4e5 seam pairs of a whole
+    brain on 8 GPUs cost ~0.4 s per step on every rank.
     """
-    counts = [int(c) for c in counts]
-    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)     # node id of (r, l) = off[r] + l, l >= 1
-    total = int(off[-1])
-    parent = {}
-
-    def find(a):
-        root = a
-        while parent.get(root, root) != root:
-            root = parent[root]
-        while parent.get(a, a) != root:
-            parent[a], a = root, parent[a]
-        return root
-
-    for r, p in enumerate(pairs):
-        if r == 0 or p is None or len(p) == 0:
-            continue
-        for lo, hi in np.asarray(p, dtype=np.int64):
-            a, b = find(off[r - 1] + lo), find(off[r] + hi)
-            if a != b:
-                if a < b:
-                    parent[b] = a
-                else:
-                    parent[a] = b
-    is_new = np.ones(total + 1, dtype=bool)
-    is_new[0] = False
-    merged = [n for n in parent if find(n) != n]
-    if merged:
-        is_new[np.array(merged, dtype=np.int64)] = False
-    glabel = np.cumsum(is_new).astype(np.int64)
-    for n in merged:
-        glabel[n] = glabel[find(n)]
-    n_global = int(is_new.sum())
-    luts = []
-    for r in range(len(counts)):
-        lut = np.zeros(counts[r] + 1, dtype=np.uint32)
-        lut[1:] = glabel[off[r] + 1: off[r] + counts[r] + 1]
-        luts.append(lut)
-    return luts, n_global
+    from ._lib import resolve_labels
+    return resolve_labels(counts, pairs)
 
 
 def merge_tables(tables, luts, z_offsets, n_global, shape_real):

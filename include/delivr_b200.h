@@ -190,6 +190,14 @@ int dlv_ccl_boundary_pairs(dlv_ctx* ctx, const uint32_t* labels_lo_plane_dev, co
 /* labels[i] = map[labels[i]] for non-zero labels (local -> global component numbers). */
 int dlv_relabel(dlv_ctx* ctx, uint32_t* labels_dev, int64_t n, const uint32_t* map_dev, int64_t nmap);
 
+/* Host-only (no ctx, no GPU): global component numbering for `nslabs` slabs stacked along z.  counts[r] = N_r local
+ * components of slab r; pairs[r] = npairs[r] x {label in slab r-1, label in slab r} of 26-adjacent voxels across
+ * the seam below slab r (pairs[0] ignored; duplicates allowed).  Components are numbered by their first voxel in
+ * raster order (cc3d's order): slabs in z order, a merged component takes the number of its member in the lowest
+ * slab.  luts_out[r] (uint32 [N_r + 1], caller-allocated): local label -> global label, 0 -> 0. */
+int dlv_resolve_labels(int nslabs, const int64_t* counts, const uint32_t* const* pairs, const int64_t* npairs,
+                       uint32_t* const* luts_out, int64_t* n_global_out);
+
 /* Host-only (no ctx, no GPU): exact merge of `ntables` per-slab statistics tables into the global table rows
  * 0..n_global.  Table t has rows[t] rows (local labels 0..N_t) with local z coordinates; luts[t][l] is the global
  * row of local row l (row 0 -> 0), z_offsets[t] the global plane of the slab's first plane; a NULL luts[t] skips
