@@ -82,6 +82,15 @@ def conv_traffic(workload, windows_active):
     return d["dram_bytes_per_window"] * windows_active, d["source"]
 
 
+def tensor_pipe_pct():
+    """ncu sm__pipe_tensor_cycles_active of the dominant kernel per layer kind, from the committed capture (BASELINE.json
+    names "conv tensor-pipe %" next to the throughput metric); None when the capture is absent."""
+    p = os.path.join(ROOT, "profiles", "conv_traffic.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p)).get("tensor_pipe")
+
+
 def state_dict():
     from oracle import unet_ref  # only to synthesise random-init weights of the architecture when no checkpoint
     w = os.path.join(ROOT, "baseline", "_ref", "inference_weights.tar")
@@ -286,7 +295,7 @@ def main():
         "roofline": {"bound": "tensor", "kernel": "conv_is_kernel / conv_tc_kernel (all conv/deconv launches of one step; achieved and traffic are per step)",
                      "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_kind": f"bf16_tflops_sustained, {peak_kind}",
-                     "conv_ms_per_step": conv_ms, "unet_ms_per_step": st["ms_unet"], "finalise_ms_per_step": st["ms_finalise"],
+                     "tensor_pipe_ncu": tensor_pipe_pct(), "conv_ms_per_step": conv_ms, "unet_ms_per_step": st["ms_unet"], "finalise_ms_per_step": st["ms_finalise"],
                      "ccl_ms_per_step": ccl_ms, "ccl_gbs_algorithmic": 9.0 * nvox / (ccl_ms * 1e-3) / 1e9 if ccl_ms else None,
                      "ccl_frac_of_hbm": (9.0 * nvox / (ccl_ms * 1e-3) / 1e9 / hbm_peak) if ccl_ms else None},
     }
