@@ -241,6 +241,29 @@ __device__ __forceinline__ void umma_bf16_lh(uint32_t d_tmem, uint32_t a_lo, uin
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
                  :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Same, with a collector hint for the A operand: COLL = 1 "fill" (keep A in the collector buffer after this MMA),
+// COLL = 2 "lastuse" (take A from the collector instead of shared memory).  Used where two consecutive MMAs multiply
+// the SAME A tile against different B tiles: the second one then costs no shared-memory A fetch.
+template <int COLL>
+__device__ __forceinline__ void umma_bf16_lh_coll(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+    if (COLL == 1) {
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+                     "setp.ne.b32 p, %5, 0;\n\t"
+                     "mov.b64 da, {%1, %3};\n\t"
+                     "mov.b64 db, {%2, %3};\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], da, db, %4, p;\n\t}"
+                     :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate) : "memory");
+    } else if (COLL == 2) {
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+                     "setp.ne.b32 p, %5, 0;\n\t"
+                     "mov.b64 da, {%1, %3};\n\t"
+                     "mov.b64 db, {%2, %3};\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], da, db, %4, p;\n\t}"
+                     :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        umma_bf16_lh(d_tmem, a_lo, b_lo, hi, idesc, accumulate);
+    }
+}
 // Arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"

@@ -144,88 +144,220 @@ def merge_tables(tables, luts, z_offsets, n_global, shape_real):
 MAX_CCL_VOXELS = (1 << 32) - 2       # dlv_ccl labels provisional components with 32-bit voxel indices
 
 
-def ccl_any_size(ctx, mask, shape, labels_out=None, max_voxels=MAX_CCL_VOXELS):
+def ccl_any_size(ctx, mask, shape, labels_out=None, max_voxels=MAX_CCL_VOXELS, labels_sink=None, bytes_free=None):
     """``Context.ccl`` for volumes of any size (count_blobs.py:61,85 on a whole brain: 2.4e10 voxels).
 
-    A volume with more voxels than one 32-bit label space is cut along z into sub-slabs that are labelled one after
-    the other on the same GPU and merged exactly like the slabs of different GPUs are: 26-adjacent label pairs across
-    every cut (dlv_ccl_boundary_pairs) -> global numbering by first voxel in raster order (resolve_global_labels) ->
-    dlv_relabel per sub-slab, integer tables merged associatively.  ``mask`` / ``labels_out``: numpy arrays or device
-    tensors of shape ``shape`` (uint8 / uint32-or-int32).  Same return value as ``Context.ccl``."""
+    A volume with more voxels than one 32-bit label space - or, for host-resident masks, than the device can hold
+    next to its labels - is cut along z into sub-slabs that are labelled one after the other on the same GPU and
+    merged exactly like the slabs of different GPUs are: 26-adjacent label pairs across every cut
+    (dlv_ccl_boundary_pairs) -> global numbering by first voxel in raster order (resolve_global_labels) ->
+    dlv_relabel per sub-slab, integer tables merged associatively.  ``mask`` / ``labels_out``: numpy arrays (memmaps)
+    or device tensors of shape ``shape`` (uint8 / uint32-or-int32).  ``labels_sink(z0, z1, labels_dev)``: called
+    once per sub-slab, in z order, with the globally numbered int32 device labels of planes [z0, z1) (count_blobs
+    streams them into the ``-cc3d.npy`` file instead of holding 4 B/voxel in host memory); sub-slabs whose labels
+    do not fit on the device next to the others are labelled a second time for it (20 ms per 4e9 voxels).
+    Same return value as ``Context.ccl``."""
     import torch
     Z, Y, X = (int(v) for v in shape)
     plane = Y * X
-    if Z * plane <= max_voxels:
-        return ctx.ccl(mask, shape, labels_out=labels_out)
+    host_mask = isinstance(mask, np.ndarray)
+    dev_labels = labels_out is not None and not isinstance(labels_out, np.ndarray)
     if plane > max_voxels:
         raise ValueError(f"one plane ({Y}x{X}) exceeds the {max_voxels}-voxel label space of a sub-slab")
     zs = max(1, max_voxels // plane)
+    if not dev_labels and (host_mask or labels_sink is not None):
+        # per sub-slab: uploaded mask (1 B) + labels (4 B) + bit mask / scan scratch (< 1 B per voxel)
+        free = int(bytes_free) if bytes_free is not None else int(torch.cuda.mem_get_info(ctx.device)[0])
+        zs = max(1, min(zs, int(free * 0.7) // (6 * plane)))
+    else:
+        free = int(bytes_free) if bytes_free is not None else 0
+    if zs >= Z and labels_sink is None:
+        return ctx.ccl(mask, shape, labels_out=labels_out)
     dev = torch.device("cuda", ctx.device)
     stream = torch.cuda.ExternalStream(ctx._L.dlv_stream(ctx._h), device=dev)
-    m3 = mask.reshape(Z, Y, X) if isinstance(mask, np.ndarray) else mask.view(Z, Y, X)
+    m3 = mask.reshape(Z, Y, X) if host_mask else mask.view(Z, Y, X)
     l3 = None
     if labels_out is not None:
         l3 = labels_out.reshape(Z, Y, X) if isinstance(labels_out, np.ndarray) else labels_out.view(Z, Y, X)
     host_labels = isinstance(l3, np.ndarray)
     cuts = list(range(0, Z, zs)) + [Z]
+    spans = list(zip(cuts[:-1], cuts[1:]))
     tables, counts, pairs, prev_last = [], [], [None], None
+    kept, kept_bytes = {}, 0                       # device labels held for the second pass (sink / host copy)
+    second = labels_sink is not None or host_labels
     with torch.cuda.stream(stream):
-        for z0, z1 in zip(cuts[:-1], cuts[1:]):
+        for i, (z0, z1) in enumerate(spans):
             sub = (z1 - z0, Y, X)
             # labels of this sub-slab: the caller's buffer when it is on the device, else a device scratch (the first
             # and last planes are needed on the device for the seam pairs anyway)
-            lab = l3[z0:z1] if (l3 is not None and not host_labels) else torch.empty(sub, dtype=torch.int32, device=dev)
+            lab = l3[z0:z1] if dev_labels else torch.empty(sub, dtype=torch.int32, device=dev)
             t = ctx.ccl(m3[z0:z1], sub, labels_out=lab)
             tables.append(t)
             counts.append(t["n"])
             if prev_last is not None:
                 pairs.append(ctx.ccl_boundary_pairs(prev_last, lab[0]))
             prev_last = lab[-1].clone()
-            if host_labels:
-                l3[z0:z1] = lab.cpu().numpy().view(l3.dtype)
+            if second and not dev_labels and kept_bytes + lab.numel() * 4 <= free * 0.7 - 6 * zs * plane:
+                kept[i] = lab
+                kept_bytes += lab.numel() * 4
             del lab
         luts, n_global = resolve_global_labels(counts, pairs)
-        if l3 is not None:
-            for (z0, z1), lut in zip(zip(cuts[:-1], cuts[1:]), luts):
+        if l3 is not None or labels_sink is not None:
+            for i, ((z0, z1), lut) in enumerate(zip(spans, luts)):
                 lut_dev = torch.from_numpy(lut.view(np.int32)).to(dev)
+                if dev_labels:
+                    lab = l3[z0:z1]
+                elif i in kept:
+                    lab = kept.pop(i)
+                else:                       # did not fit: label the sub-slab again (same local numbering)
+                    lab = torch.empty((z1 - z0, Y, X), dtype=torch.int32, device=dev)
+                    ctx.ccl(m3[z0:z1], (z1 - z0, Y, X), labels_out=lab)
+                ctx.relabel(lab, lut_dev)
                 if host_labels:
-                    lab = torch.from_numpy(np.ascontiguousarray(l3[z0:z1]).view(np.int32)).to(dev)
-                    ctx.relabel(lab, lut_dev)
                     l3[z0:z1] = lab.cpu().numpy().view(l3.dtype)
-                else:
-                    ctx.relabel(l3[z0:z1], lut_dev)
+                if labels_sink is not None:
+                    ctx.synchronize()
+                    labels_sink(z0, z1, lab)
+                del lab
         ctx.synchronize()
     return merge_tables(tables, luts, cuts[:-1], n_global, (Z, Y, X))
 
 
 # ------------------------------------------------------------------------------------------- communication
 class TorchComm:
-    """torch.distributed point-to-point + all_gather_object (NCCL on GPUs, gloo on CPU)."""
+    """torch.distributed plumbing of the slab drivers (NCCL on GPUs, gloo in the CPU tests).
 
-    def __init__(self):
+    Point-to-point transfers go through ``batch_isend_irecv`` (NCCL otherwise warns that un-batched P2P ops are
+    serialised with every other op on the communicator); the small host-side arrays (activity flags, seam pairs,
+    statistics tables) are exchanged as padded fixed-width integer tensors, not as pickled objects.
+    ``device``: where collective buffers live - the rank's GPU under NCCL, None (CPU) under gloo."""
+
+    def __init__(self, device=None):
+        import torch
         import torch.distributed as dist
-        self.dist = dist
+        self.torch, self.dist = torch, dist
         self.world = dist.get_world_size()
         self.rank = dist.get_rank()
+        self.device = device
+
+    def _p2p(self, op, tensor, peer):
+        for w in self.dist.batch_isend_irecv([self.dist.P2POp(op, tensor, peer)]):
+            w.wait()
 
     def send(self, tensor, src, dst, tag):
-        self.dist.send(tensor.contiguous(), dst=dst)
+        self._p2p(self.dist.isend, tensor.contiguous(), dst)
 
     def recv(self, like, src, dst, tag):
-        self.dist.recv(like, src=src)
+        self._p2p(self.dist.irecv, like, src)
         return like
 
+    def barrier(self):
+        self.dist.barrier()
+
+    def allgather_array(self, arr):
+        """Every rank's array (same dtype and trailing dimensions, any length) -> list of numpy arrays, one per rank."""
+        torch = self.torch
+        a = np.ascontiguousarray(arr)
+        kind = {1: np.uint8, 2: np.int16, 4: np.int32, 8: np.int64}[a.dtype.itemsize]
+        flat = torch.from_numpy(a.reshape(-1).view(kind).copy())
+        n = torch.tensor([flat.numel()], dtype=torch.int64)
+        if self.device is not None:
+            n = n.to(self.device)
+        sizes = [torch.empty_like(n) for _ in range(self.world)]
+        self.dist.all_gather(sizes, n)
+        sizes = [int(x.item()) for x in sizes]
+        cap = max(max(sizes), 1)
+        buf = torch.zeros(cap, dtype=flat.dtype, device=self.device if self.device is not None else "cpu")
+        buf[:flat.numel()] = flat.to(buf.device)
+        out = torch.empty(self.world * cap, dtype=flat.dtype, device=buf.device)
+        self.dist.all_gather_into_tensor(out, buf)
+        out = out.cpu().numpy().reshape(self.world, cap)
+        trail = a.shape[1:]
+        return [out[r, :sizes[r]].view(a.dtype).reshape((-1,) + trail) for r in range(self.world)]
+
+    def allgather_int(self, v):
+        return [int(x[0]) for x in self.allgather_array(np.array([int(v)], dtype=np.int64))]
+
     def allgather(self, obj):
+        """Pickled objects - kept for callers outside the per-step path."""
         out = [None] * self.world
         self.dist.all_gather_object(out, obj)
         return out
 
 
-# ------------------------------------------------------------------------------------------- CUDA worker
-class CudaSlabWorker:
+def pack_table(table):
+    """Statistics table -> one int64 [N+1, 10] array (count, 3 coordinate sums, 6 box bounds; uint64 bit patterns kept)."""
+    if table is None:
+        return np.zeros((0, 10), dtype=np.int64)
+    n1 = int(table["n"]) + 1
+    out = np.empty((n1, 10), dtype=np.int64)
+    out[:, 0] = np.asarray(table["voxel_counts"]).view(np.int64)
+    out[:, 1:4] = np.asarray(table["sums"]).view(np.int64).reshape(n1, 3)
+    out[:, 4:10] = np.asarray(table["bounding_boxes"]).reshape(n1, 6)
+    return out
+
+
+def unpack_table(rows):
+    if len(rows) == 0:
+        return None
+    rows = np.ascontiguousarray(rows)
+    return {"n": len(rows) - 1, "voxel_counts": rows[:, 0].copy().view(np.uint64),
+            "sums": np.ascontiguousarray(rows[:, 1:4]).view(np.uint64), "bounding_boxes": np.ascontiguousarray(rows[:, 4:10])}
+
+
+# ------------------------------------------------------------------------------------------- CUDA workers
+class _CudaLabelOps:
+    """Labelling stage of a slab of device-resident binaries (``self.binaries``): local labels + table, the seam
+    planes and pairs, the final relabelling.  Needs self.ctx / torch / dev / stream / binaries."""
+
+    def ccl(self):
+        torch = self.torch
+        with torch.cuda.stream(self.stream):
+            self.labels = torch.empty(self.binaries.shape, dtype=torch.int32, device=self.dev)
+        if self.binaries.shape[0] == 0:
+            self.table = None
+            return 0
+        # a slab thicker than one 32-bit label space (cfg4 on 2 or 4 GPUs) is labelled in sub-slabs
+        self.table = ccl_any_size(self.ctx, self.binaries, tuple(self.binaries.shape), labels_out=self.labels)
+        return self.table["n"]
+
+    def first_plane(self):
+        return self.labels[0]
+
+    def last_plane(self):
+        return self.labels[-1]
+
+    def empty_plane(self):
+        with self.torch.cuda.stream(self.stream):
+            return self.torch.empty(tuple(self.binaries.shape[1:]), dtype=self.torch.int32, device=self.dev)
+
+    def boundary_pairs(self, lo_plane):
+        return self.ctx.ccl_boundary_pairs(lo_plane, self.labels[0])
+
+    def relabel(self, lut):
+        if self.labels.numel():
+            with self.torch.cuda.stream(self.stream):
+                lut_dev = self.torch.from_numpy(lut.view(np.int32)).to(self.dev)
+            self.ctx.relabel(self.labels, lut_dev)
+
+
+class CudaLabelSlab(_CudaLabelOps):
+    """A slab of binaries on the device, for the labelling stage alone (count_blobs over several GPUs)."""
+
+    def __init__(self, ctx, binaries):
+        import torch
+        self.torch, self.ctx = torch, ctx
+        self.dev = torch.device("cuda", ctx.device)
+        self.stream = torch.cuda.ExternalStream(ctx._L.dlv_stream(ctx._h), device=self.dev)
+        self.binaries = binaries
+        self.labels = self.table = None
+
+
+class CudaSlabWorker(_CudaLabelOps):
     """One rank's compute, every stage through libdelivr_b200.so."""
 
-    def __init__(self, ctx, plan, rank, planes_fn, window_batch=0, threshold=0.5, tta=False, erosion_block_planes=0):
+    def __init__(self, ctx, plan, rank, planes_fn, window_batch=0, threshold=0.5, tta=False, erosion_block_planes=0,
+                 blend_mode=0, want_sigmoid=False, keep_avg=False):
         import torch
         self.torch = torch
         self.ctx, self.plan, self.r = ctx, plan, rank
@@ -235,6 +367,8 @@ class CudaSlabWorker:
         # own (non-blocking) stream, so it is ordered with the kernels without any cross-stream event
         self.stream = torch.cuda.ExternalStream(ctx._L.dlv_stream(ctx._h), device=self.dev)
         self.window_batch, self.threshold, self.tta, self.ebp = window_batch, threshold, tta, erosion_block_planes
+        self.blend_mode, self.want_sigmoid, self.keep_avg = blend_mode, want_sigmoid, keep_avg
+        self.sigmoid = self.avg_own = None
         z0, z1 = self.info["slab"]
         with torch.cuda.stream(self.stream):
             self.slab = planes_fn(z0, z1) if z1 > z0 else None        # uint16 (z1-z0, PY, PX) on the device
@@ -257,7 +391,7 @@ class CudaSlabWorker:
             if len(sel) else np.zeros((0, 4), dtype=np.int32)
         with torch.cuda.stream(self.stream):
             self.acc = torch.zeros(self.slab.shape, dtype=torch.int32, device=self.dev)
-        self.ctx.seg_accumulate(self.slab, sched, self.plan.roi, self.acc, window_batch=self.window_batch)
+        self.ctx.seg_accumulate(self.slab, sched, self.plan.roi, self.acc, window_batch=self.window_batch, blend_mode=self.blend_mode)
         return active
 
     def acc_planes(self, g0, g1):
@@ -279,42 +413,20 @@ class CudaSlabWorker:
             return self.binaries
         z0, z1 = self.info["slab"]
         self.ctx.seg_average(self.acc, z1 - z0, z0, self.plan.shape_pad, self.plan.roi, self.plan.overlap, active_global,
-                             passes=13 if self.tta else 1)
+                             passes=13 if self.tta else 1, blend_mode=self.blend_mode)
         avg = self.acc.view(torch.float32)
-        self.binaries = torch.empty((o1 - o0, Y, X), dtype=torch.uint8, device=self.dev)
+        with torch.cuda.stream(self.stream):
+            self.binaries = torch.empty((o1 - o0, Y, X), dtype=torch.uint8, device=self.dev)
+            if self.want_sigmoid:        # network_output.npy (inference.py:43,72)
+                self.sigmoid = torch.empty((o1 - o0, Y, X), dtype=torch.float32, device=self.dev)
         self.ctx.op_finalise_slab(avg, self.slab, z1 - z0, z0, self.plan.shape_real, o0, o1, self.binaries,
-                                  threshold=self.threshold, erosion_iters=self.plan.iters, erosion_block_planes=self.ebp)
+                                  threshold=self.threshold, erosion_iters=self.plan.iters, erosion_block_planes=self.ebp,
+                                  sigmoid_out=self.sigmoid)
+        if self.keep_avg:                # averaged logits of the planes this rank owns (inference_output.npy, :246)
+            a0, a1 = self.info["own"]
+            self.avg_own = avg[a0 - z0: a1 - z0]
         self.acc = None
         return self.binaries
-
-    def ccl(self):
-        torch = self.torch
-        self.labels = torch.empty(self.binaries.shape, dtype=torch.int32, device=self.dev)
-        if self.binaries.shape[0] == 0:
-            self.table = None
-            return 0
-        # a slab thicker than one 32-bit label space (cfg4 on 2 or 4 GPUs) is labelled in sub-slabs
-        self.table = ccl_any_size(self.ctx, self.binaries, tuple(self.binaries.shape), labels_out=self.labels)
-        return self.table["n"]
-
-    def first_plane(self):
-        return self.labels[0]
-
-    def last_plane(self):
-        return self.labels[-1]
-
-    def empty_plane(self):
-        Z, Y, X = self.plan.shape_real
-        return self.torch.empty((Y, X), dtype=self.torch.int32, device=self.dev)
-
-    def boundary_pairs(self, lo_plane):
-        return self.ctx.ccl_boundary_pairs(lo_plane, self.labels[0])
-
-    def relabel(self, lut):
-        if self.labels.numel():
-            with self.torch.cuda.stream(self.stream):
-                lut_dev = self.torch.from_numpy(lut.view(np.int32)).to(self.dev)
-            self.ctx.relabel(self.labels, lut_dev)
 
 
 # ------------------------------------------------------------------------------------------- drivers
@@ -387,13 +499,18 @@ def _stream_ctx(worker):
 
 
 def run_distributed(worker, plan, comm):
-    """One rank per process.  Collectives: send/recv of the logit halo and of one label plane, two object all-gathers."""
+    """One rank per process: segmentation stage, then labelling stage.  Collectives: send/recv of the logit halo and
+    of one label plane, padded integer all-gathers of the activity flags, seam pairs and statistics tables."""
     with _stream_ctx(worker):
-        return _run_distributed(worker, plan, comm)
+        distributed_segment(worker, plan, comm)
+        worker.ccl()
+        return distributed_label(worker, comm, plan.shape_real)
 
 
-def _run_distributed(worker, plan, comm):
-    r, world = comm.rank, comm.world
+def distributed_segment(worker, plan, comm):
+    """Exchanges 1 and 2 around the window passes: on return ``worker.binaries`` holds the rank's own planes
+    (what run_inference writes to binaries.npy).  -> global per-window activity flags."""
+    r = comm.rank
     info = plan.rank(r)
     active = worker.accumulate()
     nxt, prv = plan._next_nonempty(r), plan._prev_nonempty(r)
@@ -407,13 +524,23 @@ def _run_distributed(worker, plan, comm):
     if have and info["send"] is not None and nxt is not None:
         g0, g1 = info["send"]
         comm.send(worker.acc_planes(g0, g1), r, nxt, "acc")
-    active_global = np.concatenate(comm.allgather(np.asarray(active, dtype=np.int32)))     # exchange 2
+    active_global = np.concatenate(comm.allgather_array(np.asarray(active, dtype=np.int32)))     # exchange 2
     worker.finalise(active_global)
-    n_local = worker.ccl()
-    nplanes = comm.allgather(int(worker.labels.shape[0]))
+    return active_global
+
+
+def distributed_label(worker, comm, shape_real):
+    """Exchange 3: ``worker`` has labelled its own planes (``worker.ccl()``: local labels 1..N_r, ``worker.table``);
+    on return its labels carry the global numbering and the merged table is returned on every rank.  The slabs are
+    the ranks' plane ranges in rank order (z offsets = running sum of the plane counts)."""
+    r, world = comm.rank, comm.world
+    n_local = 0 if worker.table is None else int(worker.table["n"])
+    meta = comm.allgather_array(np.array([int(worker.labels.shape[0]), n_local], dtype=np.int64))
+    nplanes = [int(m[0]) for m in meta]
+    counts = [int(m[1]) for m in meta]
     src = next((q for q in range(r - 1, -1, -1) if nplanes[q] > 0), None)
     dst = next((q for q in range(r + 1, world) if nplanes[q] > 0), None)
-    pairs = None
+    pairs = np.zeros((0, 2), dtype=np.uint32)
 
     def _send_l():
         if nplanes[r] > 0 and dst is not None:
@@ -423,7 +550,7 @@ def _run_distributed(worker, plan, comm):
         nonlocal pairs
         if nplanes[r] > 0 and src is not None:
             lo = comm.recv(worker.empty_plane(), src, r, "lab")
-            pairs = worker.boundary_pairs(lo)
+            pairs = np.asarray(worker.boundary_pairs(lo), dtype=np.uint32).reshape(-1, 2)
 
     order = [q for q in range(world) if nplanes[q] > 0]
     pos = order.index(r) if r in order else 0
@@ -431,17 +558,68 @@ def _run_distributed(worker, plan, comm):
         _send_l(); _recv_l()
     else:
         _recv_l(); _send_l()
-    gathered = comm.allgather((n_local, pairs, worker.table))                               # exchange 3
-    counts = [g[0] for g in gathered]
-    c2 = [counts[q] for q in order]
-    p2 = [gathered[q][1] for q in order]
-    luts2, n_global = resolve_global_labels(c2, p2)
+    all_pairs = comm.allgather_array(pairs)
+    all_rows = comm.allgather_array(pack_table(worker.table))
+    luts2, n_global = resolve_global_labels([counts[q] for q in order], [all_pairs[q] for q in order])
     luts = [np.zeros(1, np.uint32)] * world
     for i, q in enumerate(order):
         luts[q] = luts2[i]
     worker.relabel(luts[r])
-    zoff = [plan.rank(q)["own_real"][0] for q in range(world)]
-    return merge_tables([g[2] for g in gathered], luts, zoff, n_global, plan.shape_real)
+    zoff = np.concatenate([[0], np.cumsum(nplanes)])[:-1]
+    return merge_tables([unpack_table(rows) for rows in all_rows], luts, zoff, n_global, shape_real)
+
+
+def run_streamed(make_worker, plan, sink=None, label=True):
+    """The virtual slabs of ``plan`` one after the other in ONE process, each released before the next is loaded: the
+    out-of-core mode of a single GPU (the reference streams the volume from memmaps, inference/inference.py:234,
+    244-247).  ``make_worker(r)`` builds slab r's worker (loading its planes); what a slab touches beyond its own
+    planes is kept (a few window depths of int32 sums) and added to the next slab.  ``sink(r, worker)`` is called once
+    slab r's binaries are final (own planes only) - e.g. to copy them into binaries.npy.  With ``label`` the slabs
+    are labelled as they pass and the exact global table is returned (labels themselves are not kept), else None.
+    Bit-identical to the single-slab run (tested)."""
+    world = plan.world
+    pending = None                      # (g0, g1, tensor) sums handed down the chain
+    active = []
+    tables, counts, pairs, nplanes, prev_last = [], [], [], [], None
+    for r in range(world):
+        info = plan.rank(r)
+        have = plan.wrange[r][1] > plan.wrange[r][0]
+        w = make_worker(r)
+        with _stream_ctx(w):
+            act = w.accumulate()
+            active.append(np.asarray(act, dtype=np.int32))
+            if have and info["recv"] is not None and pending is not None:
+                g0, g1, t = pending
+                assert (g0, g1) == tuple(info["recv"])
+                w.add_planes(g0, g1, t)
+                pending = None
+            if have and info["send"] is not None and plan._next_nonempty(r) is not None:
+                g0, g1 = info["send"]
+                pending = (g0, g1, w.acc_planes(g0, g1).clone())
+            # flags of the windows of later slabs are not known yet; they never cover a plane this slab owns
+            nrest = sum(c1 - c0 for c0, c1 in plan.wrange[r + 1:])
+            w.finalise(np.concatenate(active + [np.ones(nrest, dtype=np.int32)]))
+            if sink is not None:
+                sink(r, w)
+            if label:
+                n = w.ccl()
+                nplanes.append(int(w.labels.shape[0]))
+                if nplanes[-1] > 0:
+                    tables.append(w.table); counts.append(n)
+                    pairs.append(w.boundary_pairs(prev_last) if prev_last is not None else None)
+                    prev_last = w.last_plane().clone()
+                else:
+                    tables.append(None)
+        del w
+    if not label:
+        return None
+    keep = [r for r in range(world) if nplanes[r] > 0]
+    luts2, n_global = resolve_global_labels(counts, pairs)
+    luts = [np.zeros(1, np.uint32)] * world
+    for i, r in enumerate(keep):
+        luts[r] = luts2[i]
+    zoff = np.concatenate([[0], np.cumsum(nplanes)])[:-1]
+    return merge_tables(tables, luts, zoff, n_global, plan.shape_real)
 
 
 # ------------------------------------------------------------------------------------------- bench entry (N > 1)
@@ -459,7 +637,7 @@ def balanced_plan(ctx, comm, shape, roi, overlap, planes_fn):
         local[:, 0] -= z0
         act = ctx.windows_active(slab0, local, roi)
         del slab0
-    all_act = np.concatenate([np.asarray(a, dtype=np.int32) for a in comm.allgather(act)])
+    all_act = np.concatenate(comm.allgather_array(np.asarray(act, dtype=np.int32)))
     per_layer = all_act.reshape(len(plan0.sz), -1).sum(axis=1)
     return SlabPlan(shape, roi, overlap, comm.world, window_weights=all_act), per_layer
 
@@ -499,7 +677,7 @@ def bench_main(args, rank, local_rank, world):
     ctx = Context(local_rank)
     ctx.load_weights(sd)
     stream = torch.cuda.ExternalStream(ctx._L.dlv_stream(ctx._h), device=dev)
-    comm = TorchComm()
+    comm = TorchComm(dev)
     PZ, PY, PX = SlabPlan(shape, B.ROI, B.OVERLAP, world).shape_pad
 
     def planes(z0, z1_):

@@ -11,6 +11,7 @@ import torch.multiprocessing as mp
 
 from delivr_cfos_b200 import slabs
 from oracle import ccl_ref, pipeline_ref as P
+from cpu_engine import OracleWorker as _OracleWorker, boundary_pairs_ref
 
 
 def _starts(shape_pad, roi, overlap):
@@ -74,16 +75,7 @@ def _slab_tables(mask, cuts):
     return tabs, labs
 
 
-def _pairs(lo_plane, hi_plane):
-    out = set()
-    Y, X = hi_plane.shape
-    for y, x in zip(*np.nonzero(hi_plane)):
-        for dy in (-1, 0, 1):
-            for dx in (-1, 0, 1):
-                yy, xx = y + dy, x + dx
-                if 0 <= yy < Y and 0 <= xx < X and lo_plane[yy, xx]:
-                    out.add((int(lo_plane[yy, xx]), int(hi_plane[y, x])))
-    return np.array(sorted(out), dtype=np.uint32).reshape(-1, 2)
+_pairs = boundary_pairs_ref
 
 
 @pytest.mark.parametrize("seed,cuts", [(0, [0, 7, 20]), (1, [0, 5, 6, 13, 20]), (2, [0, 10, 11, 12, 20])])
@@ -106,68 +98,11 @@ def test_label_resolution_and_table_merge_exact(seed, cuts):
     assert np.array_equal(table["centroids"], ref["centroids"], equal_nan=True)
 
 
-class OracleWorker:
-    """CPU stand-in for CudaSlabWorker (same interface) built on the oracle: a fake 'network' whose logit is a
-    deterministic function of the voxel value, integer accumulation, oracle erosion / CCL."""
+class OracleWorker(_OracleWorker):
+    """The shared CPU stand-in (tests/cpu_engine.py) fed from a whole in-memory volume."""
 
     def __init__(self, plan, rank, volume):
-        self.plan, self.r = plan, rank
-        self.info = plan.rank(rank)
-        z0, z1 = self.info["slab"]
-        self.slab = volume[z0:z1]
-        self.volume = volume
-
-    def accumulate(self):
-        z0 = self.info["slab"][0]
-        rz, ry, rx = self.plan.roi
-        self.acc = torch.zeros(self.slab.shape, dtype=torch.int32)
-        act = []
-        for (z, y, x) in self.plan.windows_of(self.r):
-            w = self.slab[z - z0:z - z0 + rz, y:y + ry, x:x + rx].astype(np.int64)
-            a = int(w.max() > 0)
-            act.append(a)
-            if a:
-                logit = np.where(w % 9 == 0, 4096, -4096)          # fixed-point logits in 2^-12 units, ~11 % foreground
-                self.acc[z - z0:z - z0 + rz, y:y + ry, x:x + rx] += torch.from_numpy(logit.astype(np.int32))
-        return np.array(act, dtype=np.int32)
-
-    def acc_planes(self, g0, g1):
-        z0 = self.info["slab"][0]
-        return self.acc[g0 - z0:g1 - z0]
-
-    def add_planes(self, g0, g1, t):
-        z0 = self.info["slab"][0]
-        self.acc[g0 - z0:g1 - z0] += t
-
-    def finalise(self, active_global):
-        o0, o1 = self.info["own_real"]
-        Z, Y, X = self.plan.shape_real
-        z0 = self.info["slab"][0]
-        acc = self.acc.numpy()[o0 - z0:o1 - z0, :Y, :X]
-        mask = ccl_ref.erode6((self.volume[:Z, :Y, :X] > 0).astype(np.uint8), self.plan.iters)[o0:o1]   # one global block
-        self.binaries = torch.from_numpy(((acc >= 0) & (mask > 0)).astype(np.uint8))
-        return self.binaries
-
-    def ccl(self):
-        if self.binaries.shape[0] == 0:
-            self.labels, self.table = torch.zeros((0,) + self.binaries.shape[1:], dtype=torch.int32), None
-            return 0
-        lab, n = ccl_ref.connected_components26(self.binaries.numpy())
-        self.table = {"n": n, **ccl_ref.statistics(lab, n)}
-        self.labels = torch.from_numpy(lab.astype(np.int32))
-        return n
-
-    def last_plane(self):
-        return self.labels[-1].contiguous()
-
-    def empty_plane(self):
-        return torch.empty(self.plan.shape_real[1:], dtype=torch.int32)
-
-    def boundary_pairs(self, lo):
-        return _pairs(lo.numpy(), self.labels[0].numpy())
-
-    def relabel(self, lut):
-        self.labels = torch.from_numpy(lut.astype(np.int64)[self.labels.numpy()].astype(np.int32))
+        super().__init__(plan, rank, lambda z0, z1: volume[z0:z1])
 
 
 def _make_volume(shape, roi):
