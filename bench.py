@@ -33,7 +33,7 @@ ROI = (96, 96, 64)
 OVERLAP = 0.5
 CFG3 = dict(shape=(1000, 2048, 2048), seed=1003, name="cfg3 synthetic 1000x2048x2048 binary mask (blob field, 26-connected CC + table)")
 WORKLOADS = {
-    "cfg2": dict(shape=(256, 2048, 2048), seed=1002, name="cfg2 synthetic 256x2048x2048 uint16 slab"),
+    "cfg2": dict(shape=(256, 2048, 2048), seed=1002, name="cfg2 synthetic 256x2048x2048 uint16 slab", active_windows=8891),
     "cfg1": dict(shape=(64, 512, 512), seed=1001, name="cfg1 synthetic 64x512x512 uint16 volume"),
     "small": dict(shape=(96, 288, 256), seed=1005, name="small synthetic 96x288x256 uint16 volume"),
     # BASELINE.json configs[3]: ONE whole-brain-scale volume sharded over the GPUs (strong scaling; --gpus 2/4/8 only)
@@ -91,11 +91,15 @@ def tensor_pipe_pct():
     return json.load(open(p)).get("tensor_pipe")
 
 
+WEIGHTS = os.path.join(ROOT, "baseline", "_ref", "inference_weights.tar")
+
+
 def state_dict():
-    from oracle import unet_ref  # only to synthesise random-init weights of the architecture when no checkpoint
-    w = os.path.join(ROOT, "baseline", "_ref", "inference_weights.tar")
-    if os.path.exists(w):
-        return torch.load(w, map_location="cpu", weights_only=True)["state_dict"], "shipped inference_weights.tar"
+    if os.path.exists(WEIGHTS):
+        return torch.load(WEIGHTS, map_location="cpu", weights_only=True)["state_dict"], "shipped inference_weights.tar"
+    # no checkpoint staged: random-init weights of the same architecture (the only use of oracle/ by the product arm,
+    # outside every timed region)
+    from oracle import unet_ref
     return unet_ref.random_state_dict(0), "random-init weights (checkpoint not staged)"
 
 
@@ -148,35 +152,107 @@ def make_cpu_sample(seed):
     return np.where(v == 0, 1, v).astype(np.uint16)          # all windows active: worst case per voxel
 
 
+SAMPLE_DESC = (f"{CPU_SAMPLE[0]}x{CPU_SAMPLE[1]}x{CPU_SAMPLE[2]} crop-sized volume of the workload (6 windows of 96x96x64, all active), "
+               "1 pass + binarise + CC")
+
+
+class CpuReference:
+    """The reference's CPU implementation of the path, timed on a bounded sample.  kind "reference": the reference's
+    own files (inference/inference.py::run_inference + count_blobs.py::count_blobs, unmodified, staged under
+    baseline/_ref/reference by build(); third-party modules absent from the image are the stand-ins of oracle/shims,
+    cc3d among them).  kind "port": the oracle restatement, only when the files were not staged."""
+
+    def __init__(self, sd):
+        from oracle import ref_runner
+        self.threads = os.cpu_count() or 1
+        torch.set_num_threads(self.threads)
+        self.runner = ref_runner if (ref_runner.reference_root() and os.path.exists(WEIGHTS)) else None
+        self.kind = "reference" if self.runner else "port"
+        if self.runner is None:
+            from oracle import unet_ref
+            self.net = unet_ref.BasicUNet(dropout=0.1)
+            self.net.load_state_dict(unet_ref.strip_module_prefix(sd), strict=True)
+            self.net.eval()
+
+    def step(self, vol):
+        """-> seconds for one pass over the sample volume."""
+        if self.runner is None:
+            return cpu_reference_step(vol, self.net, self.threads)
+        r = self.runner.run(vol, vol.shape, ROI, WEIGHTS, tta=False, sw_batch=2)
+        return r["t_inference"] + r["t_count"]
+
+    def describe(self, vol, t, workload=None):
+        v = vol.size / t / 1e9
+        d = {"value": v, "unit": "Gvoxels/s", "cores": self.threads, "kind": self.kind,
+             "sample": f"{SAMPLE_DESC}, {t:.1f} s per pass"
+                       + ("; unmodified reference run_inference + count_blobs through oracle/shims" if self.kind == "reference" else "; oracle port")}
+        wl = WORKLOADS.get(workload or "", {})
+        if wl.get("active_windows"):
+            # the sample runs 2.0 active patch-voxels per counted voxel, the workload itself more (every voxel is covered
+            # by up to 8 windows): the same CPU rate expressed at the workload's own window density
+            dens_s = 6 * ROI[0] * ROI[1] * ROI[2] / vol.size
+            dens_w = wl["active_windows"] * ROI[0] * ROI[1] * ROI[2] / float(np.prod(wl["shape"]))
+            d["value_at_workload_window_density"] = v * dens_s / dens_w
+            d["window_density"] = {"sample": dens_s, "workload": dens_w}
+        return d
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU path (oracle port; the Python reference itself cannot travel to the
-    GPU box and its third-party deps are absent) on the box's host cores, bounded sample per step."""
+    """--impl reference: the reference's CPU path on the box's host cores, one bounded sample per step (see CpuReference)."""
     if rank != 0:
         return
-    from oracle import unet_ref
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
     sd, wdesc = state_dict()
-    net = unet_ref.BasicUNet(dropout=0.1)
-    net.load_state_dict(unet_ref.strip_module_prefix(sd), strict=True)
-    net.eval()
+    ref = CpuReference(sd)
     wl = WORKLOADS[args.workload]
     vol = make_cpu_sample(wl["seed"])
     for _ in range(args.warmup):
-        cpu_reference_step(vol, net, threads)
-    ts = [cpu_reference_step(vol, net, threads) for _ in range(args.steps)]
+        ref.step(vol)
+    ts = [ref.step(vol) for _ in range(args.steps)]
     t = sum(ts) / len(ts)
-    v = vol.size / t / 1e9
-    sample = f"{CPU_SAMPLE[0]}x{CPU_SAMPLE[1]}x{CPU_SAMPLE[2]} crop-sized volume of the workload (6 windows, all active), 1 pass + binarise + CC"
+    cb = ref.describe(vol, t, args.workload)
+    v = cb["value"]
     emit(({
         "impl": "reference", "metric": "Gvoxels/s seg+CC", "value": v, "unit": "Gvoxels/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": f"synthetic; {wdesc}",
         "config": {"workload": wl["name"], "window": list(ROI), "overlap": OVERLAP, "tta": False,
-                   "note": "oracle port of the reference CPU path (torch fp32 U-Net, C erosion + CCL as cc3d stand-in)"},
-        "cpu_baseline": {"value": v, "unit": "Gvoxels/s", "cores": threads, "kind": "port", "sample": sample},
+                   "note": ("the reference's own inference/inference.py + count_blobs.py, unmodified, on the host CPU (fp32 torch, scipy erosion, "
+                            "cc3d stand-in) over a bounded sample per step" if ref.kind == "reference" else
+                            "oracle port of the reference CPU path (torch fp32 U-Net, C erosion + CCL as cc3d stand-in)")},
+        "cpu_baseline": cb,
         "e2e": {"value": v, "unit": "Gvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def cudnn_baseline(sd, dev, nwin=32, iters=3):
+    """SURVEY.md section 2.3's per-op bar: the same U-Net forward in torch / cuDNN, bf16 channels_last_3d, on the same
+    B200 (the call the library replaces is predictor(window_data), sliding_window_inferer.py:222).  Outside every timed
+    region of the product arm; the network is the oracle's restatement of MONAI BasicUNet.  -> dict or None."""
+    try:
+        from oracle import unet_ref
+        net = unet_ref.BasicUNet(dropout=0.1)
+        net.load_state_dict(unet_ref.strip_module_prefix(sd), strict=True)
+        net = net.eval().to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last_3d)
+        x = (torch.rand((nwin, 1) + ROI, device=dev) * 4000).to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+        with torch.no_grad():
+            for _ in range(2):
+                net(x)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                net(x)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        flop = 2.0 * MAC_PER_PATCH_VOXEL * nwin * ROI[0] * ROI[1] * ROI[2]
+        del net, x
+        torch.cuda.empty_cache()
+        return {"tflops": flop / (ms * 1e-3) / 1e12, "ms_per_batch": ms, "windows": nwin, "windows_per_s": nwin / (ms * 1e-3),
+                "what": "torch 2.11 / cuDNN bf16 channels_last_3d forward of the same U-Net (conv3d + instance_norm + mish + "
+                        "max_pool3d + conv_transpose3d), same B200, whole forward incl. its elementwise passes"}
+    except Exception as e:      # a baseline, never a dependency of the product arm
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
 
 def main():
@@ -189,6 +265,7 @@ def main():
     ap.add_argument("--window-batch", type=int, default=int(os.environ.get("DLV_WINDOW_BATCH", 0)),
                     help="windows per U-Net launch sequence (0: library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cfg4", action="store_true", help="N >= 2: skip the whole-brain (cfg4) leg of the line")
     ap.add_argument("--tta", action="store_true",
                     help="the reference's 13-pass test-time augmentation (config.json default), evaluated as 3 weighted passes")
     args = ap.parse_args()
@@ -300,16 +377,17 @@ def main():
                      "ccl_frac_of_hbm": (9.0 * nvox / (ccl_ms * 1e-3) / 1e9 / hbm_peak) if ccl_ms else None},
     }
     if not args.no_cpu_baseline:
-        from oracle import unet_ref
-        threads = os.cpu_count() or 1
-        torch.set_num_threads(threads)
-        net = unet_ref.BasicUNet(dropout=0.1)
-        net.load_state_dict(unet_ref.strip_module_prefix(sd), strict=True)
-        net.eval()
+        # both baselines run after (outside) the timed regions of the product arm
+        del vol, binaries, labels
+        torch.cuda.empty_cache()
+        cb = cudnn_baseline(sd, dev)
+        if cb and "tflops" in cb:
+            cb["ours_windows_per_s"] = st_t["windows_active"] * evaluated / (st["ms_unet"] * 1e-3)
+            cb["ours_tflops_whole_forward"] = flop / (st["ms_unet"] * 1e-3) / 1e12
+        out["roofline"]["cudnn_baseline"] = cb
+        ref = CpuReference(sd)
         sv = make_cpu_sample(wl["seed"])
-        t = cpu_reference_step(sv, net, threads)
-        out["cpu_baseline"] = {"value": sv.size / t / 1e9, "unit": "Gvoxels/s", "cores": threads, "kind": "port",
-                               "sample": f"{CPU_SAMPLE[0]}x{CPU_SAMPLE[1]}x{CPU_SAMPLE[2]} volume (6 windows, all active), 1 pass + binarise + CC, {t:.1f} s"}
+        out["cpu_baseline"] = ref.describe(sv, ref.step(sv), args.workload)
     emit(out)
 
 

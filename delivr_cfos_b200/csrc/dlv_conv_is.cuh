@@ -46,7 +46,7 @@ constexpr int kIsMaxStages = 4;
 #define DLV_IS_NEWTON_PAIRS 0
 #endif
 #ifndef DLV_IS_COLLECTOR
-#define DLV_IS_COLLECTOR 0
+#define DLV_IS_COLLECTOR 1      // measured on cfg2: 0.478 -> 0.490 Gvoxels/s (profiles/r02_a_variants.txt)
 #endif
 constexpr bool kIsCollector = DLV_IS_COLLECTOR != 0;   // A-operand collector re-use on ring-wrap MMA pairs
 constexpr int kIsNewtonPairs = DLV_IS_NEWTON_PAIRS;   // channel pairs (of 4 per 16 B) whose reciprocal runs on the FMA pipe

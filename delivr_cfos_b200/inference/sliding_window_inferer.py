@@ -106,7 +106,7 @@ def sliding_window_inference(inputs, roi_size, sw_batch_size, predictor, overlap
     if any(image_size[i] < roi[i] for i in range(3)):
         raise NotImplementedError("volumes smaller than the window (the reference's reflect-pad branch, :119-136)")
     print("Inferring...")
-    vol = np.ascontiguousarray(np.asarray(inputs)[0, 0])
+    vol = np.ascontiguousarray(np.asarray(inputs)[0, 0]).astype(np.uint16, copy=False)   # the reference casts per window (:181-195,207)
     avg = np.empty(image_size, dtype=np.float32)
     scratch = np.empty(image_size, dtype=np.uint8)
     predictor.ctx.segment(vol, image_size, image_size, roi, scratch, overlap=overlap, tta=False, flip_dim=flip_dim,

@@ -502,17 +502,23 @@ def run_distributed(worker, plan, comm):
     """One rank per process: segmentation stage, then labelling stage.  Collectives: send/recv of the logit halo and
     of one label plane, padded integer all-gathers of the activity flags, seam pairs and statistics tables."""
     with _stream_ctx(worker):
-        distributed_segment(worker, plan, comm)
+        tr = _Trace(worker, comm.rank)
+        distributed_segment(worker, plan, comm, tr)
         worker.ccl()
-        return distributed_label(worker, comm, plan.shape_real)
+        tr.mark("ccl")
+        table = distributed_label(worker, comm, plan.shape_real, tr)
+        tr.dump()
+        return table
 
 
-def distributed_segment(worker, plan, comm):
+def distributed_segment(worker, plan, comm, tr=None):
     """Exchanges 1 and 2 around the window passes: on return ``worker.binaries`` holds the rank's own planes
     (what run_inference writes to binaries.npy).  -> global per-window activity flags."""
     r = comm.rank
+    tr = tr or _Trace(worker, r)
     info = plan.rank(r)
     active = worker.accumulate()
+    tr.mark("accumulate")
     nxt, prv = plan._next_nonempty(r), plan._prev_nonempty(r)
     have = plan.wrange[r][1] > plan.wrange[r][0]
     # exchange 1: a chain - receive and add first, then send (what is sent may contain what was just received, when
@@ -524,16 +530,20 @@ def distributed_segment(worker, plan, comm):
     if have and info["send"] is not None and nxt is not None:
         g0, g1 = info["send"]
         comm.send(worker.acc_planes(g0, g1), r, nxt, "acc")
+    tr.mark("halo exchange")
     active_global = np.concatenate(comm.allgather_array(np.asarray(active, dtype=np.int32)))     # exchange 2
+    tr.mark("flags all-gather")
     worker.finalise(active_global)
+    tr.mark("finalise")
     return active_global
 
 
-def distributed_label(worker, comm, shape_real):
+def distributed_label(worker, comm, shape_real, tr=None):
     """Exchange 3: ``worker`` has labelled its own planes (``worker.ccl()``: local labels 1..N_r, ``worker.table``);
     on return its labels carry the global numbering and the merged table is returned on every rank.  The slabs are
     the ranks' plane ranges in rank order (z offsets = running sum of the plane counts)."""
     r, world = comm.rank, comm.world
+    tr = tr or _Trace(worker, r)
     n_local = 0 if worker.table is None else int(worker.table["n"])
     meta = comm.allgather_array(np.array([int(worker.labels.shape[0]), n_local], dtype=np.int64))
     nplanes = [int(m[0]) for m in meta]
@@ -558,15 +568,20 @@ def distributed_label(worker, comm, shape_real):
         _send_l(); _recv_l()
     else:
         _recv_l(); _send_l()
+    tr.mark("label plane + pairs")
     all_pairs = comm.allgather_array(pairs)
     all_rows = comm.allgather_array(pack_table(worker.table))
+    tr.mark("pairs / tables all-gather")
     luts2, n_global = resolve_global_labels([counts[q] for q in order], [all_pairs[q] for q in order])
     luts = [np.zeros(1, np.uint32)] * world
     for i, q in enumerate(order):
         luts[q] = luts2[i]
     worker.relabel(luts[r])
+    tr.mark("resolve + relabel")
     zoff = np.concatenate([[0], np.cumsum(nplanes)])[:-1]
-    return merge_tables([unpack_table(rows) for rows in all_rows], luts, zoff, n_global, shape_real)
+    table = merge_tables([unpack_table(rows) for rows in all_rows], luts, zoff, n_global, shape_real)
+    tr.mark("table merge")
+    return table
 
 
 def run_streamed(make_worker, plan, sink=None, label=True):
@@ -653,31 +668,53 @@ def _roofline(B, workload, windows_active, conv_ms_max, world):
             "conv_ms_per_step_max_rank": conv_ms_max}
 
 
-def bench_main(args, rank, local_rank, world):
-    """bench.py --gpus N: weak scaling - N copies of the workload's volume stacked along z (the job at N = 1 is the
-    single-GPU workload itself), window z-layers partitioned over the ranks by active-window count."""
-    import json
+class _Trace:
+    """DLV_TRACE_SLABS=1: per-phase device-synchronised wall times of one step on stderr (rank 0 prints its own and,
+    at the end of a step, nothing else - the phases are bracketed by stream synchronisations, so a traced step is not a
+    timed one)."""
+
+    def __init__(self, worker, rank):
+        import os
+        self.on = os.environ.get("DLV_TRACE_SLABS") == "1"
+        self.w, self.rank = worker, rank
+        self.rows = []
+        if self.on:
+            import time
+            self.time = time
+            self.sync()
+            self.t = time.perf_counter()
+
+    def sync(self):
+        st = getattr(self.w, "stream", None)
+        if st is not None:
+            st.synchronize()
+
+    def mark(self, what):
+        if not self.on:
+            return
+        self.sync()
+        now = self.time.perf_counter()
+        self.rows.append((what, (now - self.t) * 1e3))
+        self.t = now
+
+    def dump(self):
+        if self.on:
+            import sys
+            print(f"[slabs rank {self.rank}] " + " | ".join(f"{k} {v:.1f}" for k, v in self.rows) +
+                  f" | total {sum(v for _, v in self.rows):.1f} ms", file=sys.stderr, flush=True)
+
+
+def _bench_job(B, args, ctx, comm, stream, dev, rank, world, wl, whole, tta, steps, warmup, want_e2e, want_roofline):
+    """One measured configuration of the N-GPU bench: the volume (N stacked copies of the workload, or ONE whole
+    volume) is sharded by balanced_plan and every step is the product path - CudaSlabWorker + run_distributed, what
+    run_inference / count_blobs drive under torchrun.  -> dict of results on rank 0 (None elsewhere)."""
     import torch
     import torch.distributed as dist
-    from . import Context
     from .synth import synth_volume_cuda
-    import bench as B
-
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if not dist.is_initialized():
-        dist.init_process_group("nccl", device_id=dev)
-    wl = B.WORKLOADS[args.workload]
+    from .inference.inference import erosion_block_planes
     z1, Y, X = wl["shape"]
-    tta = bool(getattr(args, "tta", False))
-    evaluated = 3 if tta else 1                # 13 reference passes = 3 distinct ones blended 5 / 4 / 4 times
-    whole = bool(wl.get("whole"))              # one fixed volume sharded over the ranks (strong scaling) instead of N copies
     shape = (z1, Y, X) if whole else (z1 * world, Y, X)
-    sd, wdesc = B.state_dict()
-    ctx = Context(local_rank)
-    ctx.load_weights(sd)
-    stream = torch.cuda.ExternalStream(ctx._L.dlv_stream(ctx._h), device=dev)
-    comm = TorchComm(dev)
+    evaluated = 3 if tta else 1                # 13 reference passes = 3 distinct ones blended 5 / 4 / 4 times
     PZ, PY, PX = SlabPlan(shape, B.ROI, B.OVERLAP, world).shape_pad
 
     def planes(z0, z1_):
@@ -690,17 +727,18 @@ def bench_main(args, rank, local_rank, world):
             full[a - z0: b - z0, :Y, :X] = synth_volume_cuda((z1, Y, X), wl["seed"], device=dev, z_range=(a - k * z1, b - k * z1))
         return full
 
-    from .inference.inference import erosion_block_planes
     ebp = erosion_block_planes(shape)
     with torch.cuda.stream(stream):
         plan, per_layer = balanced_plan(ctx, comm, shape, B.ROI, B.OVERLAP, planes)
         info = plan.rank(rank)
         slab = planes(*info["slab"])
-        # end-to-end leg: the rank's slab starts in pinned host memory, binaries end in pinned host memory
-        hslab = torch.empty(slab.shape, dtype=torch.uint16).pin_memory()
-        hslab.copy_(slab)
         o0, o1 = info["own_real"]
-        hbin = torch.empty((max(o1 - o0, 0), Y, X), dtype=torch.uint8).pin_memory()
+        hslab = hbin = None
+        if want_e2e:
+            # end-to-end leg: the rank's slab starts in pinned host memory, binaries end in pinned host memory
+            hslab = torch.empty(slab.shape, dtype=torch.uint16).pin_memory()
+            hslab.copy_(slab)
+            hbin = torch.empty((max(o1 - o0, 0), Y, X), dtype=torch.uint8).pin_memory()
     torch.cuda.synchronize()
 
     def step(host):
@@ -718,61 +756,131 @@ def bench_main(args, rank, local_rank, world):
             stream.synchronize()
         return table, w
 
-    def timed(host, steps):
+    def timed(host, n):
         dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(steps):
+        for _ in range(n):
             table, w = step(host)
+            del w
         e1.record(stream)
         torch.cuda.synchronize()
         dist.barrier()
         dt = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)      # device time, max over ranks
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        return float(dt.item()) * 1e3 / steps, table
+        return float(dt.item()) * 1e3 / n, table
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step(False)
-    sampler = B.ClockSampler(local_rank) if rank == 0 else None
+    sampler = B.ClockSampler(dev.index) if rank == 0 else None
     l0 = ctx.launches
-    ms, table = timed(False, args.steps)
+    ms, table = timed(False, steps)
     launches = torch.tensor([ctx.launches - l0], device=dev, dtype=torch.int64)
     dist.all_reduce(launches)
     clocks = sampler.stop() if sampler else None
-    step(True)
-    ms_e2e, table_e2e = timed(True, args.steps)
-    io = torch.tensor([hslab.numel() * 2, hbin.numel()], device=dev, dtype=torch.int64)
-    dist.all_reduce(io)
-    # roofline of the tcgen05 convolutions: one extra step with per-launch event timing on every rank; the job's
-    # algorithmic FLOP / the slowest rank's conv time, per GPU
-    ctx.set_conv_timing(True)
-    step(False)
-    conv = torch.tensor([ctx.conv_time_ms()], device=dev, dtype=torch.float64)
-    ctx.set_conv_timing(False)
-    dist.all_reduce(conv, op=dist.ReduceOp.MAX)
+    ms_e2e, io = None, None
+    if want_e2e:
+        step(True)
+        ms_e2e, _ = timed(True, steps)
+        io = torch.tensor([hslab.numel() * 2, hbin.numel()], device=dev, dtype=torch.int64)
+        dist.all_reduce(io)
+    conv_ms = None
+    if want_roofline:
+        # roofline of the tcgen05 convolutions: one extra step with per-launch event timing on every rank; the job's
+        # algorithmic FLOP / the slowest rank's conv time, per GPU
+        ctx.set_conv_timing(True)
+        step(False)
+        conv = torch.tensor([ctx.conv_time_ms()], device=dev, dtype=torch.float64)
+        ctx.set_conv_timing(False)
+        dist.all_reduce(conv, op=dist.ReduceOp.MAX)
+        conv_ms = float(conv.item())
+    del slab, hslab, hbin
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    nvox = int(np.prod(shape))
+    nrow = table["n"] + 1
+    res = {"shape": list(shape), "nvox": nvox, "ms_per_step": ms, "gvoxels_per_s": nvox / (ms * 1e-3) / 1e9, "steps": steps, "warmup": warmup,
+           "tta": tta, "passes_evaluated": evaluated, "components": int(table["n"]), "windows_active": int(per_layer.sum()),
+           "active_windows_per_layer": [int(c) for c in per_layer], "layers_per_rank": plan.layers,
+           "windows_per_rank": [c1 - c0 for c0, c1 in plan.wrange], "launches": int(launches.item()), "clocks": clocks}
+    if want_e2e:
+        res["e2e"] = {"value": nvox / (ms_e2e * 1e-3) / 1e9, "unit": "Gvoxels/s", "h2d_bytes_per_step": int(io[0].item()),
+                      "d2h_bytes_per_step": int(io[1].item()) + nrow * (8 + 24 + 48), "ms_per_step": ms_e2e,
+                      "note": "per-rank pinned host slab in, pinned host binaries + merged table out"}
+    if want_roofline:
+        res["roofline"] = _roofline(B, args.workload, int(per_layer.sum()) * evaluated, conv_ms, world)
+        # strong-scaling view of the same step: what the job would take if only the convolutions ran, perfectly split
+        res["non_conv_share"] = 1.0 - conv_ms / ms if ms > 0 else None
+    return res
+
+
+def bench_main(args, rank, local_rank, world):
+    """bench.py --gpus N.  Headline: weak scaling - N copies of the workload's volume stacked along z (the job at N = 1
+    is the single-GPU workload itself), window z-layers partitioned over the ranks by active-window count.  With the
+    default workload the same line also carries BASELINE.json configs[3] in ``config.cfg4``: ONE whole-brain volume
+    (1500 x 4000 x 4000) sharded over the N GPUs (strong scaling), without and with the reference's default test-time
+    augmentation.  --workload cfg4 makes that volume the headline instead."""
+    import torch
+    import torch.distributed as dist
+    from . import Context
+    import bench as B
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    wl = B.WORKLOADS[args.workload]
+    tta = bool(getattr(args, "tta", False))
+    whole = bool(wl.get("whole"))              # one fixed volume sharded over the ranks (strong scaling) instead of N copies
+    sd, wdesc = B.state_dict()
+    ctx = Context(local_rank)
+    ctx.load_weights(sd)
+    stream = torch.cuda.ExternalStream(ctx._L.dlv_stream(ctx._h), device=dev)
+    comm = TorchComm(dev)
+    head = _bench_job(B, args, ctx, comm, stream, dev, rank, world, wl, whole, tta, args.steps, args.warmup, True, True)
+    cfg4 = None
+    if not whole and args.workload == "cfg2" and not getattr(args, "no_cfg4", False):
+        w4 = B.WORKLOADS["cfg4"]
+        cfg4 = {}
+        for name, t in (("tta_off", False), ("tta_on", True)):
+            # the TTA-on steps are ~3x longer: one timed step where three would take minutes
+            est = (cfg4["tta_off"]["ms_per_step"] * 3e-3) if (t and cfg4.get("tta_off")) else 0.0
+            n = 3 if est < 25.0 else 1
+            r = _bench_job(B, args, ctx, comm, stream, dev, rank, world, w4, True, t, n, 0 if t else 1, world >= 8 and not t, True)
+            if rank == 0:
+                cfg4[name] = {"seconds_per_volume": r["ms_per_step"] * 1e-3, "gvoxels_per_s": r["gvoxels_per_s"], "steps": r["steps"],
+                              "warmup": r["warmup"] if not t else "warm from the tta_off steps", "passes_evaluated": r["passes_evaluated"],
+                              "windows_active": r["windows_active"], "components": r["components"],
+                              "conv_tflops_per_gpu": r["roofline"]["achieved"], "conv_frac": r["roofline"]["frac"],
+                              "non_conv_share": r["non_conv_share"], "windows_per_rank": r["windows_per_rank"],
+                              "ms_per_step": r["ms_per_step"]}
+                if "e2e" in r:
+                    cfg4[name]["seconds_per_volume_e2e"] = r["e2e"]["ms_per_step"] * 1e-3
     if rank == 0:
-        nvox = int(np.prod(shape))
-        v = nvox / (ms * 1e-3) / 1e9
-        nrow = table_e2e["n"] + 1
-        B.emit({
-            "metric": "Gvoxels/s seg+CC", "value": v, "unit": "Gvoxels/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if whole else "weak", "vs_baseline": None,
+        shape = head["shape"]
+        out = {
+            "metric": "Gvoxels/s seg+CC", "value": head["gvoxels_per_s"], "unit": "Gvoxels/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong" if whole else "weak", "vs_baseline": None,
             "dtype": "bf16", "data": f"synthetic; {wdesc}",
             "config": {"workload": (f"{wl['name']}, z-slab sharded over {world} GPUs" if whole else
-                                    f"{world} copies of {wl['name']} stacked along z ({shape[0]}x{Y}x{X}), z-slab sharded"),
-                       "seconds_per_volume": ms * 1e-3, "seconds_per_volume_e2e": ms_e2e * 1e-3,
-                       "window": list(B.ROI), "overlap": B.OVERLAP, "tta": tta, "passes_evaluated": evaluated, "blend": "constant",
-                       "components": table["n"],
-                       "layers_per_rank": plan.layers, "windows_per_rank": [c1 - c0 for c0, c1 in plan.wrange],
-                       "active_windows_per_layer": [int(c) for c in per_layer],
-                       "windows_active": int(per_layer.sum()),
+                                    f"{world} copies of {wl['name']} stacked along z ({shape[0]}x{shape[1]}x{shape[2]}), z-slab sharded"),
+                       "seconds_per_volume": head["ms_per_step"] * 1e-3, "seconds_per_volume_e2e": head["e2e"]["ms_per_step"] * 1e-3,
+                       "window": list(B.ROI), "overlap": B.OVERLAP, "tta": tta, "passes_evaluated": head["passes_evaluated"], "blend": "constant",
+                       "components": head["components"],
+                       "layers_per_rank": head["layers_per_rank"], "windows_per_rank": head["windows_per_rank"],
+                       "active_windows_per_layer": head["active_windows_per_layer"],
+                       "windows_active": head["windows_active"],
                        "timing": "CUDA events on the library stream between barriers, max over ranks",
                        "l2": "inputs larger than L2 (slab + accumulator >> 126 MB)"},
-            "gpu_launches": int(launches.item()), "clocks": clocks,
-            "e2e": {"value": nvox / (ms_e2e * 1e-3) / 1e9, "unit": "Gvoxels/s", "h2d_bytes_per_step": int(io[0].item()),
-                    "d2h_bytes_per_step": int(io[1].item()) + nrow * (8 + 24 + 48),
-                    "note": "per-rank pinned host slab in, pinned host binaries + merged table out"},
-            "roofline": _roofline(B, args.workload, int(per_layer.sum()) * evaluated, float(conv.item()), world),
-        })
+            "gpu_launches": head["launches"], "clocks": head["clocks"],
+            "e2e": {k: v for k, v in head["e2e"].items() if k != "ms_per_step"},
+            "roofline": head["roofline"],
+        }
+        out["roofline"]["non_conv_share_of_step"] = head["non_conv_share"]
+        if cfg4 is not None:
+            out["config"]["cfg4"] = dict(cfg4, workload=f"{B.WORKLOADS['cfg4']['name']}, ONE volume z-slab sharded over {world} GPUs (strong scaling; "
+                                                         "BASELINE.json configs[3], target <= 60 s per volume on 8 GPUs)")
+        B.emit(out)
     dist.destroy_process_group()

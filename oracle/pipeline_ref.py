@@ -122,6 +122,39 @@ def infer_average(volume, roi, overlap, predictor, sw_batch_size, tta=False):
         return (torch.as_tensor(out_sum) / torch.as_tensor(count)).numpy()   # fp16 / uint8 -> fp16
 
 
+# ---------------------------------------------------------------- optional Gaussian blend (not what the reference computes)
+def gaussian_importance_map(roi, sigma_scale=0.125):
+    """MONAI ``compute_importance_map(mode="gaussian")`` as SURVEY.md section 8(c) restates it: separable
+    exp(-x^2 / (2 (sigma_scale n)^2)), x = -(n-1)/2 .. (n-1)/2 per dimension, float32.  The reference itself
+    hard-codes mode='constant' (sliding_window_inferer.py:148), so this pins the library's optional blend_mode = 1 to
+    the restated formula only: PARITY UNPINNED against MONAI (not installed, not exercised by the reference)."""
+    w = None
+    for n in roi:
+        x = np.arange(n, dtype=np.float32) - np.float32((n - 1) / 2.0)
+        g = np.exp(-(x.astype(np.float64) ** 2) / (2.0 * (sigma_scale * n) ** 2)).astype(np.float32)
+        w = g if w is None else w[..., None] * g
+    return w
+
+
+def infer_average_weighted(volume, roi, overlap, predictor, weights):
+    """Importance-weighted blend: sum_w(weight * logit) / sum_w(weight) over the windows covering a voxel, windows whose
+    input is all zero contributing the skip value (per window).  float64 accumulation -> float32 (Zp,Yp,Xp)."""
+    num = np.zeros(volume.shape, dtype=np.float64)
+    den = np.zeros(volume.shape, dtype=np.float64)
+    rz, ry, rx = roi
+    w64 = weights.astype(np.float64)
+    for (z, y, x) in window_list(volume.shape, roi, overlap):
+        data = volume[z:z + rz, y:y + ry, x:x + rx].astype(np.int32)
+        if data.max() <= 0:
+            seg = np.full(data.shape, SKIP_VALUE, dtype=np.float64)
+        else:
+            with torch.no_grad():
+                seg = predictor(torch.as_tensor(data, dtype=torch.float32)[None, None])[0, 0].numpy().astype(np.float64)
+        num[z:z + rz, y:y + ry, x:x + rx] += w64 * seg
+        den[z:z + rz, y:y + ry, x:x + rx] += w64
+    return (num / den).astype(np.float32)
+
+
 # ---------------------------------------------------------------- binarise + eroded mask
 def create_binaries(avg_logits, volume, shape_real, threshold=0.5, return_sigmoid=False):
     """create_nifti_seg (inference.py:31-95): sigmoid >= thr AND erode30(input > 0), per Arrayterator block."""

@@ -18,7 +18,10 @@ def test_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "Gvoxels/s seg+CC" and d["unit"] == "Gvoxels/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # "reference": the reference's own files were found (/root/reference here, baseline/_ref/reference on the GPU box)
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    staged = os.path.exists("/root/reference/inference/inference.py") or os.path.exists(os.path.join(ROOT, "baseline", "_ref", "reference", "inference", "inference.py"))
+    assert (d["cpu_baseline"]["kind"] == "reference") == (staged and os.path.exists(os.path.join(ROOT, "baseline", "_ref", "inference_weights.tar")))
     assert d["e2e"] == {"value": d["value"], "unit": "Gvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
