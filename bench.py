@@ -38,6 +38,8 @@ WORKLOADS = {
     "small": dict(shape=(96, 288, 256), seed=1005, name="small synthetic 96x288x256 uint16 volume"),
     # BASELINE.json configs[3]: ONE whole-brain-scale volume sharded over the GPUs (strong scaling; --gpus 2/4/8 only)
     "cfg4": dict(shape=(1500, 4000, 4000), seed=1004, name="cfg4 synthetic 1500x4000x4000 uint16 volume", whole=True),
+    # BASELINE.json configs[4]: window / overlap sweep; a volume every window size tiles (384 = 2 x 192 = 3 x 128 = 4 x 96 = 6 x 64)
+    "cfg5": dict(shape=(384, 1536, 1536), seed=1005, name="cfg5 sweep volume, synthetic 384x1536x1536 uint16", whole=True),
     "cfg4s": dict(shape=(300, 1000, 1000), seed=1004, name="1/5-scale cfg4 (300x1000x1000) - a quick check of the sharded whole-volume path", whole=True),
 }
 CPU_SAMPLE = (96, 144, 128)           # bounded CPU sample: 1x2x3 = 6 windows of 96x96x64
@@ -265,10 +267,13 @@ def main():
     ap.add_argument("--window-batch", type=int, default=int(os.environ.get("DLV_WINDOW_BATCH", 0)),
                     help="windows per U-Net launch sequence (0: library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep-only", default=None, help="cfg5: comma-separated window:overlap points, e.g. 96:0.5,160:0.25 (default: all 15)")
     ap.add_argument("--no-cfg4", action="store_true", help="N >= 2: skip the whole-brain (cfg4) leg of the line")
     ap.add_argument("--tta", action="store_true",
                     help="the reference's 13-pass test-time augmentation (config.json default), evaluated as 3 weighted passes")
     args = ap.parse_args()
+    if args.sweep_only:
+        args.sweep_only = set(args.sweep_only.split(","))
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -277,8 +282,13 @@ def main():
     if args.impl == "reference":
         return run_reference(args, rank, world)
     protect_stdout()
-    if world > 1 or args.gpus > 1:
+    if world > 1 or args.gpus > 1 or args.workload == "cfg5":
         from delivr_cfos_b200 import slabs
+        if world == 1:          # the sharded driver with a single rank (no torchrun needed)
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29517")
+            os.environ.setdefault("RANK", "0")
+            os.environ.setdefault("WORLD_SIZE", "1")
         return slabs.bench_main(args, rank, local_rank, world)
     if WORKLOADS[args.workload].get("whole"):
         raise SystemExit(f"--workload {args.workload} is the multi-GPU configuration: launch with torchrun and --gpus 2, 4 or 8")

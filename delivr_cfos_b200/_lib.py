@@ -29,6 +29,10 @@ class SegParams(ctypes.Structure):
     ]
 
 
+class BlendGeom(ctypes.Structure):          # include/delivr_b200.h: dlv_blend_geom
+    _fields_ = [("shape_pad", ctypes.c_int64 * 3), ("overlap", ctypes.c_float), ("gz0", ctypes.c_int64)]
+
+
 class SegStats(ctypes.Structure):
     _fields_ = [
         ("windows_total", c_i64), ("windows_active", c_i64), ("passes", c_i64), ("kernel_launches", c_i64),
@@ -48,7 +52,7 @@ class Table(ctypes.Structure):
 # every symbol include/delivr_b200.h declares (tests check the .so exports exactly these)
 EXPORTS = [
     "dlv_abi_version", "dlv_init", "dlv_destroy", "dlv_last_error", "dlv_launch_count", "dlv_stream",
-    "dlv_synchronize", "dlv_set_conv_timing", "dlv_conv_time_ms", "dlv_load_weights", "dlv_segment", "dlv_ccl", "dlv_table_free",
+    "dlv_synchronize", "dlv_set_conv_timing", "dlv_conv_time_ms", "dlv_stage_time_ms", "dlv_load_weights", "dlv_segment", "dlv_ccl", "dlv_table_free",
     "dlv_ccl_last_timing", "dlv_unet_forward", "dlv_op_conv3d", "dlv_op_deconv", "dlv_op_finalise",
     "dlv_window_grid", "dlv_windows_active", "dlv_seg_accumulate", "dlv_seg_average", "dlv_op_finalise_slab",
     "dlv_ccl_boundary_pairs", "dlv_relabel", "dlv_table_merge", "dlv_resolve_labels", "dlv_tiff_info", "dlv_tiff_read_u16", "dlv_tiff_last_error",
@@ -85,6 +89,8 @@ def load_library():
     L.dlv_set_conv_timing.argtypes = [c_vp, ctypes.c_int]
     L.dlv_conv_time_ms.restype = ctypes.c_int
     L.dlv_conv_time_ms.argtypes = [c_vp, P(ctypes.c_double)]
+    L.dlv_stage_time_ms.restype = ctypes.c_int
+    L.dlv_stage_time_ms.argtypes = [c_vp, ctypes.c_int, P(ctypes.c_double)]
     L.dlv_load_weights.restype = ctypes.c_int
     L.dlv_load_weights.argtypes = [c_vp, ctypes.c_int, P(ctypes.c_char_p), P(c_vp), P(c_i64)]
     L.dlv_segment.restype = ctypes.c_int
@@ -108,7 +114,7 @@ def load_library():
     L.dlv_windows_active.restype = ctypes.c_int
     L.dlv_windows_active.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, ctypes.c_int, P(c_i32), c_vp]
     L.dlv_seg_accumulate.restype = ctypes.c_int
-    L.dlv_seg_accumulate.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, ctypes.c_int, P(c_i32), ctypes.c_int, ctypes.c_int, c_vp]
+    L.dlv_seg_accumulate.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, ctypes.c_int, P(c_i32), ctypes.c_int, ctypes.c_int, c_vp, c_vp]
     L.dlv_seg_average.restype = ctypes.c_int
     L.dlv_seg_average.argtypes = [c_vp, c_vp, c_i64, c_i64, P(c_i64), P(c_i32), c_f32, c_vp, ctypes.c_int, ctypes.c_int]
     L.dlv_op_finalise_slab.restype = ctypes.c_int
@@ -140,7 +146,7 @@ def load_library():
                                   c_vp, c_vp, c_vp, c_vp]
     L.dlv_edt.restype = ctypes.c_int
     L.dlv_edt.argtypes = [c_vp, c_vp, P(c_i64), P(ctypes.c_double), c_vp]
-    if L.dlv_abi_version() != 2:
+    if L.dlv_abi_version() != 3:
         raise DlvError("libdelivr_b200.so ABI version mismatch")
     _lib = L
     return L
@@ -226,6 +232,15 @@ class Context:
         ms = ctypes.c_double()
         self._check(self._L.dlv_conv_time_ms(self._h, ctypes.byref(ms)), "dlv_conv_time_ms")
         return ms.value
+
+    def stage_times_ms(self):
+        """Device time per stage of the window loop since timing was enabled (set_conv_timing): conv, blend, norm, gather."""
+        out = {}
+        for i, k in enumerate(("conv", "blend", "norm", "gather")):
+            ms = ctypes.c_double()
+            self._check(self._L.dlv_stage_time_ms(self._h, i, ctypes.byref(ms)), "dlv_stage_time_ms")
+            out[k] = ms.value
+        return out
 
     # ---- weights (inference.py:190-200,217-222)
     def load_weights(self, state_dict):
@@ -333,13 +348,20 @@ class Context:
                                                len(o), r, out.ctypes.data), "dlv_windows_active")
         return out
 
-    def seg_accumulate(self, slab, windows, roi, acc, window_batch=0, blend_mode=0):
-        """windows int32 [n,4] = (oz,oy,ox,flip_dim) local to the slab; acc int32 device tensor shaped like slab."""
+    def seg_accumulate(self, slab, windows, roi, acc, window_batch=0, blend_mode=0, shape_pad=None, overlap=0.5, gz0=0):
+        """windows int32 [n,4] = (oz,oy,ox,flip_dim) local to the slab; acc int32 device tensor shaped like slab.
+        The gaussian blend (blend_mode 1) also needs the window grid: padded shape, overlap, global plane of slab[0]."""
         w = np.ascontiguousarray(windows, dtype=np.int32).reshape(-1, 4)
         self._after_torch(slab, acc)
         r = (c_i32 * 3)(*[int(v) for v in roi])
+        geom = None
+        if blend_mode:
+            geom = BlendGeom()
+            geom.shape_pad[:] = [int(v) for v in shape_pad]
+            geom.overlap, geom.gz0 = float(overlap), int(gz0)
         self._check(self._L.dlv_seg_accumulate(self._h, _ptr(slab), int(slab.shape[1]), int(slab.shape[2]), w.ctypes.data,
-                                               len(w), r, int(window_batch), int(blend_mode), _ptr(acc)), "dlv_seg_accumulate")
+                                               len(w), r, int(window_batch), int(blend_mode),
+                                               ctypes.byref(geom) if geom is not None else None, _ptr(acc)), "dlv_seg_accumulate")
 
     def seg_average(self, acc, nplanes, gz0, shape_pad, roi, overlap, active, passes=1, blend_mode=0):
         sp = (c_i64 * 3)(*[int(v) for v in shape_pad])

@@ -97,7 +97,13 @@ int dlv_synchronize(dlv_ctx* c) {
 int dlv_set_conv_timing(dlv_ctx* c, int enable) {
     if (!c) return DLV_ERR_ARG;
     C(c)->time_convs = enable != 0;
-    if (enable) C(c)->conv_ms = 0.0;
+    if (enable) { C(c)->conv_ms = 0.0; C(c)->stage_ms[0] = C(c)->stage_ms[1] = C(c)->stage_ms[2] = 0.0; }
+    return DLV_OK;
+}
+
+int dlv_stage_time_ms(const dlv_ctx* c, int stage, double* ms_out) {
+    if (!c || !ms_out || stage < 0 || stage > 3) return DLV_ERR_ARG;
+    *ms_out = stage == 0 ? C(c)->conv_ms : C(c)->stage_ms[stage - 1];
     return DLV_OK;
 }
 
@@ -183,8 +189,7 @@ int dlv_unet_forward(dlv_ctx* c, const uint16_t* windows_dev, int nwin, const in
     const int64_t wvox = static_cast<int64_t>(roi[0]) * roi[1] * roi[2];
     for (int off = 0; off < nwin && rc == 0; off += cap) {
         const int n = std::min(cap, nwin - off);
-        rc = dlv::engine_run_batch(ctx, windows_dev, roi[1], roi[2], wd_dev + off, n, nullptr, nullptr, nullptr, nullptr,
-                                   logits_dev + off * wvox);
+        rc = dlv::engine_run_batch(ctx, windows_dev, roi[1], roi[2], wd_dev + off, n, nullptr, dlv::BlendDev(), logits_dev + off * wvox);
     }
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     dlv::dfree(ctx, wd_dev);

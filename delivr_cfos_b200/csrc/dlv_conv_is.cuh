@@ -73,6 +73,11 @@ struct IsArgs {
     int G;                      // planes per statistics group (Zs is a multiple of G)
     uint32_t stage_bytes, w_bytes;
     double inv_count;           // 1 / (Z*Y*X)
+    // FOLD (the uint16 first layer): the volume the windows are cut from and their descriptors - the K = 16 operand
+    // slot (3 kx neighbours x {hi, lo, hi, lo} split terms) is built in shared memory straight from the uint16 voxels
+    const uint16_t* raw_slab;   // uint16 [planes][raw_sy][raw_sx]
+    int64_t raw_sy, raw_sx;
+    const int4* raw_wd;         // [nwin] {oz, oy, ox, flip | (repeat - 1) << 8} (WindowDesc)
     long long* dbg;             // optional [grid][8] cycle counters (DLV_IS_DEBUG)
     int dbg_mode;               // timing experiments (results invalid): 1 skip TMEM loads, 2 skip TMEM zeroing, 4 skip the transform's smem traffic, 8 skip output stores
 };
@@ -106,8 +111,10 @@ __device__ __forceinline__ void st_shared_u4(uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// FOLD: the uint16 first layer.  Its K = 16 slot holds the 3 kx neighbours x 4 split terms of the single input channel
-// (gather_windows_kernel), so only the centre kx tap exists: 3 MMAs per plane and tile instead of 9.
+// FOLD: the uint16 first layer.  Its K = 16 slot holds the 3 kx neighbours x 4 split terms of the single input channel,
+// so only the centre kx tap exists: 3 MMAs per plane and tile instead of 9.  The slot is written by the transform
+// warps from the raw uint16 window (gather + flip + zero padding + bf16 split fused into the operand staging: the
+// window never exists in an expanded form in HBM).
 template <int T, int S, bool FOLD>
 __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) {
     constexpr int KXN = FOLD ? 1 : 3;
@@ -131,7 +138,8 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
 
     if (threadIdx.x == 0) {
         // plain layers: the TMA completes `full` directly; fused layers: TMA -> rawfull -> transform warps -> full
-        const uint32_t full_count = p.xform_chunks > 0 ? static_cast<uint32_t>(kIsXformWarps) : 1u;
+        // (FOLD: one transform warp builds a whole stage and arrives alone)
+        const uint32_t full_count = (!FOLD && p.xform_chunks > 0) ? static_cast<uint32_t>(kIsXformWarps) : 1u;
         for (int s = 0; s < p.nstages; ++s) { mbar_init(&full[s], full_count); mbar_init(&empty[s], 1); mbar_init(&rawfull[s], 1); }
         for (int s = 0; s < S; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
         mbar_init(wfull, 1);
@@ -160,7 +168,7 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
             for (uint32_t off = 0; off < p.w_bytes; off += 27648u)
                 tma_bulk_g2s(wsm + off, reinterpret_cast<const uint8_t*>(p.w) + off, min(27648u, p.w_bytes - off), wfull);
         }
-        {
+        if (!FOLD) {
             // every input chunk of the step arrives by TMA; chunks that hold RAW conv output are normalised in place
             // by the transform warps before the MMA warp sees the stage
             uint64_t* const bars_in = p.xform_chunks > 0 ? rawfull : full;
@@ -412,6 +420,59 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
                         dst[lane * 2 + 1] = cb[lane * 2 + 1] + cb[64 + lane * 2 + 1] + cb[128 + lane * 2 + 1] + cb[192 + lane * 2 + 1];
                     }
                 }
+            }
+        }
+    } else if (FOLD) {
+        // ------------------------------------------------------------ first layer: operand slot from the raw uint16 window.
+        // Replaces the window gather of sliding_window_inferer.py:181-195,207 (and its flips, :218-219).  Step k of the
+        // CTA (the same (item, plane) enumeration as the MMA warp's) is built by transform warp k mod kIsXformWarps:
+        // every warp has kIsXformWarps steps of time for its plane, so the global-load latency needs no software
+        // pipeline.  A uint16 v is split as v = hi + lo (hi = v & 0xFF00, lo = v & 0xFF: both exact in bf16) and paired
+        // with the weights' {Wh, Wh, Wl, Wl} (W = Wh + Wl), which reproduces the fp32 product v * W to ~2^-16 relative.
+        const int tw = warp - kIsWarpXform0;
+        const int ngroups = (p.RL + 31) / 32;
+        int step = 0;
+        for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+            int win, c, za, zb;
+            item_geom(item, win, c, za, zb);
+            const int zi0 = max(za - 1, 1), zi1 = min(zb + 1, p.Z);
+            const int4 wd = p.raw_wd[win];
+            const int flip = wd.w & 0xFF;
+            for (int zi = zi0; zi <= zi1; ++zi, ++step) {
+                if (step % kIsXformWarps != tw) continue;
+                const int stage = step % p.nstages;
+                const uint32_t phase = static_cast<uint32_t>(step / p.nstages) & 1u;
+                const int z = zi - 1, zs = (flip == 1) ? p.Z - 1 - z : z;
+                const uint16_t* plane = p.raw_slab + (static_cast<int64_t>(wd.x + zs) * p.raw_sy + wd.y) * p.raw_sx + wd.z;
+                mbar_wait(&empty[stage], phase ^ 1);
+                const uint32_t base = smem_u32(stages + static_cast<size_t>(stage) * p.stage_bytes) + static_cast<uint32_t>(lane) * 16u;
+#pragma unroll 4
+                for (int g = 0; g < ngroups; ++g) {
+                    const int i = g * 32 + lane;
+                    const int qq = c * R - p.H + i;
+                    uint32_t vm = 0u, v0 = 0u, vp = 0u;
+                    if (i < p.RL && qq >= 0 && qq < p.PL) {
+                        const int yp = qq / p.Xp, xp = qq - yp * p.Xp;
+                        if (yp >= 1 && yp <= p.Y && xp >= 1) {
+                            const int y = yp - 1, x = xp - 1;
+                            const uint16_t* row = plane + static_cast<int64_t>((flip == 2) ? p.Y - 1 - y : y) * p.raw_sx;
+                            const bool fx = flip == 3;
+                            v0 = __ldg(row + (fx ? p.X - 1 - x : x));
+                            if (x > 0) vm = __ldg(row + (fx ? p.X - x : x - 1));
+                            if (x + 1 < p.X) vp = __ldg(row + (fx ? p.X - 2 - x : x + 1));
+                        }
+                    }
+                    if (i < p.RL) {
+                        const uint32_t tm = pack_bf16x2(static_cast<float>(vm & 0xFF00u), static_cast<float>(vm & 0xFFu));
+                        const uint32_t t0 = pack_bf16x2(static_cast<float>(v0 & 0xFF00u), static_cast<float>(v0 & 0xFFu));
+                        const uint32_t tp = pack_bf16x2(static_cast<float>(vp & 0xFF00u), static_cast<float>(vp & 0xFFu));
+                        st_shared_u4(base + static_cast<uint32_t>(g) * 512u, make_uint4(tm, tm, t0, t0));
+                        st_shared_u4(base + static_cast<uint32_t>(p.RL) * 16u + static_cast<uint32_t>(g) * 512u, make_uint4(tp, tp, 0u, 0u));
+                    }
+                }
+                fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core's async proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[stage]);
             }
         }
     } else if (p.xform_chunks > 0) {

@@ -68,6 +68,7 @@ struct Ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double conv_ms = 0.0;       // accumulated device time in conv kernels when timing is enabled
     bool time_convs = false;
+    double stage_ms[3] = {0.0, 0.0, 0.0};   // same for the other U-Net passes: 0 overlap blend, 1 norm / pool passes, 2 window gather
     double ccl_ms = 0.0;
     int64_t ccl_launches = 0;
     bool use_fused = true;      // Cout = 32 layers on the input-stationary fused kernel (DLV_FUSED=0 selects the per-tap kernel)
@@ -84,6 +85,20 @@ void set_error(Ctx* ctx, const char* fmt, ...);
 inline cudaError_t dmalloc(Ctx* ctx, void** p, size_t bytes) { return cudaMallocAsync(p, bytes ? bytes : 1, ctx->stream); }
 template <class T> inline cudaError_t dmalloc(Ctx* ctx, T** p, size_t bytes) { return dmalloc(ctx, reinterpret_cast<void**>(p), bytes); }
 inline void dfree(Ctx* ctx, void* p) { if (p) cudaFreeAsync(p, ctx->stream); }
+
+// Device time of a stage when dlv_set_conv_timing is on (events on the library stream; serialises it - bench only).
+enum { kStageBlend = 0, kStageNorm = 1, kStageGather = 2 };
+struct StageTimer {
+    Ctx* c; int stage;
+    StageTimer(Ctx* ctx, int st) : c(ctx), stage(st) { if (c->time_convs) cudaEventRecord(c->ev0, c->stream); }
+    ~StageTimer() {
+        if (!c->time_convs) return;
+        cudaEventRecord(c->ev1, c->stream);
+        cudaEventSynchronize(c->ev1);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->stage_ms[stage] += ms;
+    }
+};
 
 #define DLV_CUDA_OK(ctx, expr)                                                              \
     do {                                                                                    \
@@ -107,8 +122,16 @@ void engine_free(Ctx* ctx);
 int engine_prepare(Ctx* ctx, const int32_t roi[3], int batch);
 int engine_batch_capacity(Ctx* ctx);
 // gather windows described by wd_dev[0..nwin) from a uint16 slab, run the net, blend into acc (fp32, 2 planes sets)
+// Gaussian importance weights of the optional blend (device pointers; all null = constant blend): wz/wy/wx[roi] the
+// separable window weights, nz/ny/nx the reciprocal of the largest weight any covering window gives a voxel along that
+// axis, indexed by the voxel's slab-local coordinate (nz is pre-offset to the slab's first plane).  Scaling every
+// contribution of a voxel by the same nz*ny*nx cancels in the average and keeps the fixed-point sums well scaled
+// where all covering windows see the voxel at their periphery (raw weights ~1e-5 next to the volume faces).
+struct BlendDev {
+    const float *wz = nullptr, *wy = nullptr, *wx = nullptr, *nz = nullptr, *ny = nullptr, *nx = nullptr;
+};
 int engine_run_batch(Ctx* ctx, const uint16_t* slab, int64_t slabY, int64_t slabX, const WindowDesc* wd_dev, int nwin,
-                     int32_t* acc, const float* wz, const float* wy, const float* wx, float* logits_out);
+                     int32_t* acc, const BlendDev& bw, float* logits_out);
 int windows_active(Ctx* ctx, const uint16_t* slab, int64_t slabY, int64_t slabX, const int32_t* origins_dev, int n,
                    const int32_t roi[3], int32_t* active_dev);
 int op_conv3d(Ctx* ctx, const char* name, const float* x, int n, int D, int H, int W, float* y, double* stats);

@@ -63,7 +63,7 @@ struct AvgArgs {
     const int32_t *sz, *sy, *sx;                              // window starts
     int ny, nx;
     const int32_t* active;     // [nz][ny][nx]
-    const float *wz, *wy, *wx; // gaussian 1-D weights or nullptr
+    BlendDev bw;               // gaussian 1-D weights + per-axis normalisers (nz indexed by GLOBAL z here), or all null
     int passes;
 };
 
@@ -73,12 +73,13 @@ __global__ void average_kernel(const int32_t* __restrict__ acc, float* __restric
     if (x >= a.PX) return;
     const int64_t gz = a.gz0 + z;
     float wsum = 0.f, wskip = 0.f;
+    // the same weight expression as final_blend_kernel: (w_axis * normaliser_axis) per axis, then the product
     for (int iz = a.lo_z[gz]; iz <= a.hi_z[gz]; ++iz) {
-        const float fz = a.wz ? a.wz[gz - a.sz[iz]] : 1.f;
+        const float fz = a.bw.wz ? a.bw.wz[gz - a.sz[iz]] * a.bw.nz[gz] : 1.f;
         for (int iy = a.lo_y[y]; iy <= a.hi_y[y]; ++iy) {
-            const float fy = a.wz ? a.wy[y - a.sy[iy]] : 1.f;
+            const float fy = a.bw.wz ? a.bw.wy[y - a.sy[iy]] * a.bw.ny[y] : 1.f;
             for (int ix = a.lo_x[x]; ix <= a.hi_x[x]; ++ix) {
-                const float w = fz * fy * (a.wz ? a.wx[x - a.sx[ix]] : 1.f);
+                const float w = fz * fy * (a.bw.wz ? a.bw.wx[x - a.sx[ix]] * a.bw.nx[x] : 1.f);
                 wsum += w;
                 if (!a.active[(static_cast<int64_t>(iz) * a.ny + iy) * a.nx + ix]) wskip += w;
             }
@@ -166,17 +167,33 @@ static void cover_tables(const std::vector<int>& starts, int roi, int64_t dim, s
 
 // ------------------------------------------------------------------- reusable stages (also exported per slab)
 struct BlendWeights {
-    DevBuf z, y, x;
-    const float *wz = nullptr, *wy = nullptr, *wx = nullptr;
+    DevBuf z, y, x, nz, ny, nx;
+    BlendDev dev;              // nz indexed by GLOBAL z (callers offset it to their slab)
 };
-static int blend_weights(Ctx* ctx, int blend_mode, const int32_t roi[3], BlendWeights& w) {
+// reciprocal of the largest weight any covering window gives coordinate g (windows start at `starts`, extent roi)
+static std::vector<float> axis_normaliser(const std::vector<int>& starts, int roi, int64_t dim, const std::vector<float>& w) {
+    std::vector<float> r(dim, 1.f);
+    for (int64_t g = 0; g < dim; ++g) {
+        float m = 0.f;
+        for (int s : starts)
+            if (s <= g && g < s + roi) m = std::max(m, w[g - s]);
+        r[g] = m > 0.f ? 1.f / m : 1.f;
+    }
+    return r;
+}
+static int blend_weights(Ctx* ctx, int blend_mode, const int32_t roi[3], const int64_t* shape_pad, float overlap, BlendWeights& w) {
     if (blend_mode == 0) return 0;
     if (blend_mode != 1) { set_error(ctx, "blend_mode must be 0 (constant) or 1 (gaussian)"); return DLV_ERR_ARG; }
+    if (!shape_pad) { set_error(ctx, "the gaussian blend needs the window grid (padded shape, overlap, first plane of the slab)"); return DLV_ERR_ARG; }
     int rc;
-    if ((rc = dev_upload(ctx, w.z, gaussian_1d(roi[0])))) return rc;
-    if ((rc = dev_upload(ctx, w.y, gaussian_1d(roi[1])))) return rc;
-    if ((rc = dev_upload(ctx, w.x, gaussian_1d(roi[2])))) return rc;
-    w.wz = w.z.as<float>(); w.wy = w.y.as<float>(); w.wx = w.x.as<float>();
+    const std::vector<float> gz = gaussian_1d(roi[0]), gy = gaussian_1d(roi[1]), gx = gaussian_1d(roi[2]);
+    if ((rc = dev_upload(ctx, w.z, gz)) || (rc = dev_upload(ctx, w.y, gy)) || (rc = dev_upload(ctx, w.x, gx))) return rc;
+    if ((rc = dev_upload(ctx, w.nz, axis_normaliser(window_starts(shape_pad[0], roi[0], overlap), roi[0], shape_pad[0], gz))) ||
+        (rc = dev_upload(ctx, w.ny, axis_normaliser(window_starts(shape_pad[1], roi[1], overlap), roi[1], shape_pad[1], gy))) ||
+        (rc = dev_upload(ctx, w.nx, axis_normaliser(window_starts(shape_pad[2], roi[2], overlap), roi[2], shape_pad[2], gx))))
+        return rc;
+    w.dev.wz = w.z.as<float>(); w.dev.wy = w.y.as<float>(); w.dev.wx = w.x.as<float>();
+    w.dev.nz = w.nz.as<float>(); w.dev.ny = w.ny.as<float>(); w.dev.nx = w.nx.as<float>();
     return 0;
 }
 
@@ -197,7 +214,7 @@ static int default_window_batch(const int32_t roi[3]) {
 
 // run the scheduled windows (origins local to `slab`) and blend them into acc (int32, same extent as slab)
 int seg_accumulate(Ctx* ctx, const uint16_t* slab, int64_t SY, int64_t SX, const std::vector<WindowDesc>& sched,
-                   const int32_t roi[3], int batch, int blend_mode, int32_t* acc) {
+                   const int32_t roi[3], int batch, int blend_mode, int32_t* acc, const dlv_blend_geom* geom) {
     if (!ctx->net.loaded) { set_error(ctx, "call dlv_load_weights first"); return DLV_ERR_STATE; }
     if (sched.empty()) return 0;
     batch = batch > 0 ? batch : default_window_batch(roi);
@@ -205,12 +222,18 @@ int seg_accumulate(Ctx* ctx, const uint16_t* slab, int64_t SY, int64_t SX, const
     if (rc) return rc;
     batch = engine_batch_capacity(ctx);
     BlendWeights bw;
-    if ((rc = blend_weights(ctx, blend_mode, roi, bw))) return rc;
+    if ((rc = blend_weights(ctx, blend_mode, roi, geom ? geom->shape_pad : nullptr, geom ? geom->overlap : 0.f, bw))) return rc;
+    if (blend_mode && (geom->gz0 < 0 || geom->gz0 >= geom->shape_pad[0] || SY != geom->shape_pad[1] || SX != geom->shape_pad[2])) {
+        set_error(ctx, "gaussian blend: slab origin / in-plane extent inconsistent with the padded shape");
+        return DLV_ERR_ARG;
+    }
+    BlendDev bdev = bw.dev;
+    if (blend_mode) bdev.nz += geom->gz0;          // slab-local z indexing inside the window loop
     DevBuf d_sched;
     if ((rc = dev_upload(ctx, d_sched, sched))) return rc;
     for (size_t off = 0; off < sched.size() && rc == 0; off += batch) {
         const int n = static_cast<int>(std::min<size_t>(batch, sched.size() - off));
-        rc = engine_run_batch(ctx, slab, SY, SX, d_sched.as<WindowDesc>() + off, n, acc, bw.wz, bw.wy, bw.wx, nullptr);
+        rc = engine_run_batch(ctx, slab, SY, SX, d_sched.as<WindowDesc>() + off, n, acc, bdev, nullptr);
     }
     cudaError_t e = cudaStreamSynchronize(ctx->stream);   // d_sched / weights are freed on return
     if (rc == 0 && e != cudaSuccess) { set_error(ctx, "accumulate: %s", cudaGetErrorString(e)); rc = DLV_ERR_CUDA; }
@@ -228,7 +251,7 @@ int seg_average(Ctx* ctx, int32_t* acc, int64_t nplanes, int64_t gz0, const int6
     const int64_t nwin = static_cast<int64_t>(sz.size()) * sy.size() * sx.size();
     BlendWeights bw;
     int rc;
-    if ((rc = blend_weights(ctx, blend_mode, roi, bw))) return rc;
+    if ((rc = blend_weights(ctx, blend_mode, roi, shape_pad, overlap, bw))) return rc;
     DevBuf t_loz, t_hiz, t_loy, t_hiy, t_lox, t_hix, t_sz, t_sy, t_sx, d_active;
     std::vector<int32_t> lo, hi;
     cover_tables(sz, roi[0], PZ, lo, hi);
@@ -292,7 +315,7 @@ int seg_average(Ctx* ctx, int32_t* acc, int64_t nplanes, int64_t gz0, const int6
     a.lo_x = t_lox.as<int32_t>(); a.hi_x = t_hix.as<int32_t>();
     a.sz = t_sz.as<int32_t>(); a.sy = t_sy.as<int32_t>(); a.sx = t_sx.as<int32_t>();
     a.ny = static_cast<int>(sy.size()); a.nx = static_cast<int>(sx.size()); a.active = d_active.as<int32_t>();
-    a.wz = bw.wz; a.wy = bw.wy; a.wx = bw.wx; a.passes = passes;
+    a.bw = bw.dev; a.passes = passes;
     dim3 grid(static_cast<unsigned>((PX + 255) / 256), static_cast<unsigned>(PY), static_cast<unsigned>(nplanes));
     average_kernel<<<grid, 256, 0, ctx->stream>>>(acc, reinterpret_cast<float*>(acc), a);
     ctx->launches++;
@@ -401,7 +424,9 @@ int segment_run(Ctx* ctx, const void* volume_any, const dlv_seg_params* P, void*
     const int64_t launches0 = ctx->launches;
     ctx->conv_ms = 0.0;
     cudaEventRecord(e0, ctx->stream);
-    rc = seg_accumulate(ctx, slab, PY, PX, sched, P->roi, batch, P->blend_mode, d_acc.as<int32_t>());
+    dlv_blend_geom geom;
+    geom.shape_pad[0] = PZ; geom.shape_pad[1] = PY; geom.shape_pad[2] = PX; geom.overlap = P->overlap; geom.gz0 = 0;
+    rc = seg_accumulate(ctx, slab, PY, PX, sched, P->roi, batch, P->blend_mode, d_acc.as<int32_t>(), &geom);
     cudaEventRecord(e1, ctx->stream);
     mark("u-net passes");
 

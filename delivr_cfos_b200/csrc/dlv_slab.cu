@@ -11,7 +11,7 @@ namespace dlv {
 
 std::vector<int> window_starts(int64_t image, int roi, float overlap);
 int seg_accumulate(Ctx* ctx, const uint16_t* slab, int64_t SY, int64_t SX, const std::vector<WindowDesc>& sched,
-                   const int32_t roi[3], int batch, int blend_mode, int32_t* acc);
+                   const int32_t roi[3], int batch, int blend_mode, int32_t* acc, const dlv_blend_geom* geom);
 int seg_average(Ctx* ctx, int32_t* acc, int64_t nplanes, int64_t gz0, const int64_t shape_pad[3], const int32_t roi[3],
                 float overlap, const int32_t* active_host, int passes, int blend_mode);
 
@@ -98,7 +98,7 @@ int dlv_windows_active(dlv_ctx* c, const uint16_t* slab_dev, int64_t SY, int64_t
 }
 
 int dlv_seg_accumulate(dlv_ctx* c, const uint16_t* slab_dev, int64_t SY, int64_t SX, const int32_t* windows_host, int n,
-                       const int32_t roi[3], int window_batch, int blend_mode, int32_t* acc_dev) {
+                       const int32_t roi[3], int window_batch, int blend_mode, const dlv_blend_geom* geom_or_null, int32_t* acc_dev) {
     Ctx* ctx = C(c);
     if (!ctx) return DLV_ERR_ARG;
     if (!slab_dev || !roi || !acc_dev || (n > 0 && !windows_host)) { dlv::set_error(ctx, "dlv_seg_accumulate: null argument"); return DLV_ERR_ARG; }
@@ -112,7 +112,8 @@ int dlv_seg_accumulate(dlv_ctx* c, const uint16_t* slab_dev, int64_t SY, int64_t
         }
         sched[i] = dlv::WindowDesc{windows_host[4 * i], windows_host[4 * i + 1], windows_host[4 * i + 2], (f ? f - 1 : 0) | (rep1 << 8)};
     }
-    return dlv::seg_accumulate(ctx, slab_dev, SY, SX, sched, roi, window_batch, blend_mode, acc_dev);
+    if (blend_mode != 0 && !geom_or_null) { dlv::set_error(ctx, "dlv_seg_accumulate: the gaussian blend needs dlv_blend_geom"); return DLV_ERR_ARG; }
+    return dlv::seg_accumulate(ctx, slab_dev, SY, SX, sched, roi, window_batch, blend_mode, acc_dev, geom_or_null);
 }
 
 int dlv_seg_average(dlv_ctx* c, int32_t* acc_dev_inout, int64_t nplanes, int64_t gz0, const int64_t shape_pad[3],

@@ -178,8 +178,7 @@ __global__ void norm_mish_kernel(const __nv_bfloat16* __restrict__ raw, LevelDev
 __global__ void final_blend_kernel(const __nv_bfloat16* __restrict__ raw, LevelDev L, const double* __restrict__ stats,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    const float* __restrict__ fw, float fb, const WindowDesc* __restrict__ wd,
-                                   int32_t* __restrict__ acc, int64_t slabY, int64_t slabX,
-                                   const float* __restrict__ wz, const float* __restrict__ wy, const float* __restrict__ wx,
+                                   int32_t* __restrict__ acc, int64_t slabY, int64_t slabX, const BlendDev bw,
                                    float* __restrict__ logits_out) {
     __shared__ f32x2 sa[16], sb[16], sw[16];
     const int win = blockIdx.y;
@@ -224,7 +223,7 @@ __global__ void final_blend_kernel(const __nv_bfloat16* __restrict__ raw, LevelD
     const int zo = (flip == 1) ? L.Z - 1 - z : z;
     const int yo = (flip == 2) ? L.Y - 1 - y : y;
     const int xo = (flip == 3) ? L.X - 1 - x : x;
-    const float wgt = wz ? wz[zo] * wy[yo] * wx[xo] : 1.f;
+    const float wgt = bw.wz ? (bw.wz[zo] * bw.nz[w.oz + zo]) * (bw.wy[yo] * bw.ny[w.oy + yo]) * (bw.wx[xo] * bw.nx[w.ox + xo]) : 1.f;
     // fixed-point accumulation (2^-12 logit units): integer adds are associative, so the blended sum is
     // bit-identical for any window order, batch composition or slab partition across GPUs.  `repeat` identical
     // passes (test-time augmentation evaluates the same flip several times) are one pass added `repeat` times.
@@ -535,10 +534,10 @@ static int run_conv(Ctx* ctx, const ConvLayer& Ly, const Level& L, int nwin, con
 
 // ------------------------------------------------------------------- input-stationary fused conv launcher (Cout = 32)
 static const int kIsStatGroup = 8;      // output planes per InstanceNorm partial record of the fused conv
-// partial records per window of a level: (Z / G) groups x at most ceil(PL / 256) columns (T = 2)
+// partial records per window of a level: (Z / G) groups x at most ceil(PL / 128) columns (T = 1)
 static int is_max_parts(const Level& L) {
     const int G = (L.Z % kIsStatGroup == 0) ? kIsStatGroup : L.Z;
-    return (L.Z / G) * ((L.YpXp + 255) / 256);
+    return (L.Z / G) * ((L.YpXp + 127) / 128);      // columns of one tile (T = 1) at most
 }
 
 struct IsPlan {
@@ -555,7 +554,7 @@ static bool plan_conv_is(const Ctx* ctx, const ConvLayer& Ly, const Level& L, in
     auto fits = [&](int T, int& nst, int& RL, uint32_t& sb) {
         RL = ((128 * T + 2 * P.H + 7) / 8) * 8;
         sb = static_cast<uint32_t>(nchunks) * RL * 16;
-        const uint32_t fixed = P.w_bytes + kIsXformWarps * 32 * 4 + 512 * 8 + 256;
+        const uint32_t fixed = P.w_bytes + 512 * 8 + 512;      // weights + statistics combine buffer + barriers
         nst = 0;
         for (int n = kIsMaxStages; n >= 2; --n)
             if (fixed + static_cast<uint64_t>(n) * sb <= kSmemLimit) { nst = n; break; }
@@ -574,6 +573,13 @@ static bool plan_conv_is(const Ctx* ctx, const ConvLayer& Ly, const Level& L, in
         const double cost = mma * (static_cast<double>(NC) * R / PL);
         if (cost < best) { best = cost; bestT = T; }
     }
+    // wide windows (a row halo of 2 (X + 2) positions per column): one tile per column, 16 plane slots - the stages
+    // of the two-tile column no longer fit next to the weights (X > ~100 for the 64 -> 32 layers)
+    if (!bestT && (!ctx->is_tiles || ctx->is_tiles == 1)) {
+        int nst, RL; uint32_t sb;
+        if (fits(1, nst, RL, sb)) bestT = 1;
+    }
+    if (ctx->is_tiles == 1) { int nst, RL; uint32_t sb; if (fits(1, nst, RL, sb)) bestT = 1; }
     if (!bestT) return false;
     P.T = bestT; P.S = 16 / bestT;
     fits(P.T, P.nstages, P.RL, P.stage_bytes);
@@ -615,8 +621,15 @@ static int launch_conv_is_t(Ctx* ctx, const IsArgs& a, int grid, uint32_t smem) 
 
 // One Cout = 32 conv layer over nwin windows.  `xform`: the leading 4 chunks of in0 hold the RAW output of `prod`
 // (statistics in prod_stats) and get InstanceNorm + Mish applied while being staged.
+struct RawWindows {            // the first layer's input: uint16 volume + window descriptors (instead of a gathered tensor)
+    const uint16_t* slab = nullptr;
+    int64_t sy = 0, sx = 0;
+    const WindowDesc* wd = nullptr;
+};
+
 static int run_conv_is(Ctx* ctx, const ConvLayer& Ly, const Level& L, int nwin, const bf16* in0, int nch0, const bf16* in1,
-                       const ConvLayer* prod, const double* prod_stats, bf16* out, double* part, double* stats) {
+                       const ConvLayer* prod, const double* prod_stats, bf16* out, double* part, double* stats,
+                       const RawWindows* raw = nullptr) {
     IsPlan P;
     if (!plan_conv_is(ctx, Ly, L, nwin, P) || P.nparts > is_max_parts(L)) {
         set_error(ctx, "conv %s: level %dx%dx%d does not fit the input-stationary kernel", Ly.name.c_str(), L.Z, L.Y, L.X);
@@ -638,14 +651,23 @@ static int run_conv_is(Ctx* ctx, const ConvLayer& Ly, const Level& L, int nwin, 
     a.RL = P.RL; a.H = P.H; a.nstages = P.nstages;
     a.stage_bytes = P.stage_bytes; a.w_bytes = P.w_bytes;
     a.inv_count = 1.0 / (static_cast<double>(L.Z) * L.Y * L.X);
+    if (Ly.cin == 1) {
+        if (!raw || !raw->slab || !raw->wd) { set_error(ctx, "conv %s: the first layer reads the uint16 windows directly", Ly.name.c_str()); return DLV_ERR_ARG; }
+        a.raw_slab = raw->slab; a.raw_sy = raw->sy; a.raw_sx = raw->sx;
+        a.raw_wd = reinterpret_cast<const int4*>(raw->wd);
+    }
     const int grid = std::min(ctx->num_sms, a.nitems);
     static const bool dbg = getenv("DLV_IS_DEBUG") != nullptr;
     if (const char* e = getenv("DLV_IS_MODE")) a.dbg_mode = atoi(e);
     if (dbg) { cudaMalloc(reinterpret_cast<void**>(&a.dbg), grid * 64); cudaMemset(a.dbg, 0, grid * 64); }
     if (ctx->time_convs) cudaEventRecord(ctx->ev0, ctx->stream);
     int rc;
-    if (Ly.cin == 1) rc = (P.T == 4) ? launch_conv_is_t<4, 4, true>(ctx, a, grid, P.smem) : launch_conv_is_t<2, 8, true>(ctx, a, grid, P.smem);
-    else rc = (P.T == 4) ? launch_conv_is_t<4, 4, false>(ctx, a, grid, P.smem) : launch_conv_is_t<2, 8, false>(ctx, a, grid, P.smem);
+    if (Ly.cin == 1)
+        rc = (P.T == 4) ? launch_conv_is_t<4, 4, true>(ctx, a, grid, P.smem) : (P.T == 2) ? launch_conv_is_t<2, 8, true>(ctx, a, grid, P.smem)
+                                                                                         : launch_conv_is_t<1, 16, true>(ctx, a, grid, P.smem);
+    else
+        rc = (P.T == 4) ? launch_conv_is_t<4, 4, false>(ctx, a, grid, P.smem) : (P.T == 2) ? launch_conv_is_t<2, 8, false>(ctx, a, grid, P.smem)
+                                                                                          : launch_conv_is_t<1, 16, false>(ctx, a, grid, P.smem);
     if (ctx->time_convs && rc == 0) {
         cudaEventRecord(ctx->ev1, ctx->stream);
         cudaEventSynchronize(ctx->ev1);
@@ -742,6 +764,7 @@ static int run_norm(Ctx* ctx, const ConvLayer& Ly, const Level& L, int nwin, con
                     const Level* Lp, const double* stats) {
     const int nchunk = Ly.cout / 8;
     const LevelDev Ld = to_dev(L);
+    StageTimer timer(ctx, kStageNorm);
     if (pooled) {
         const int n = (L.Z / 2) * (L.Y / 2) * (L.X / 2);
         dim3 grid((n + 127) / 128, nwin * nchunk);
@@ -776,12 +799,12 @@ static int deconv_block(Ctx* ctx, Engine* e, const char* name, int lvl_in, int n
 // Fused path: the eight Cout = 32 layers (levels 0 and 1) run on the input-stationary kernel, which normalises its
 // input while staging it; only pooled / deconv-input tensors still need an elementwise pass.
 static int fused_block(Ctx* ctx, Engine* e, int layer_idx, const char* name, int lvl, int nwin, const bf16* in0, int nch0,
-                       const bf16* in1, const char* prod_name, int prod_idx, bf16* out) {
+                       const bf16* in1, const char* prod_name, int prod_idx, bf16* out, const RawWindows* raw = nullptr) {
     const ConvLayer& Ly = ctx->net.conv.at(name);
     const ConvLayer* prod = prod_name ? &ctx->net.conv.at(prod_name) : nullptr;
     const double* pst = prod_name ? e->stats + static_cast<size_t>(prod_idx) * e->batch * kStatsPerLayer : nullptr;
     double* st = e->stats + static_cast<size_t>(layer_idx) * e->batch * kStatsPerLayer;
-    return run_conv_is(ctx, Ly, e->L[lvl], nwin, in0, nch0, in1, prod, pst, out, e->part, st);
+    return run_conv_is(ctx, Ly, e->L[lvl], nwin, in0, nch0, in1, prod, pst, out, e->part, st, raw);
 }
 static int norm_block(Ctx* ctx, Engine* e, int layer_idx, const char* name, int lvl, int nwin, const bf16* raw, bf16* out, bf16* pooled) {
     const ConvLayer& Ly = ctx->net.conv.at(name);
@@ -789,20 +812,27 @@ static int norm_block(Ctx* ctx, Engine* e, int layer_idx, const char* name, int 
     return run_norm(ctx, Ly, e->L[lvl], nwin, raw, out, pooled, pooled ? &e->L[lvl + 1] : nullptr, st);
 }
 
-// everything after the gather: 18 convs, 4 deconvs, norms, final blend
-static int forward_from_in0(Ctx* ctx, int nwin, const WindowDesc* wd_dev, int32_t* acc, int64_t slabY,
-                            int64_t slabX, const float* wz, const float* wy, const float* wx, float* logits_out) {
+// Cout = 32 layers on the fused input-stationary kernel?  (window levels 0 and 1 must fit its shared-memory stages)
+static bool fused_path(Ctx* ctx, int nwin) {
+    Engine* e = ctx->eng;
+    IsPlan probe;
+    return ctx->use_fused && plan_conv_is(ctx, ctx->net.conv.at("upcat_1.convs.conv_0"), e->L[0], nwin, probe) &&
+           plan_conv_is(ctx, ctx->net.conv.at("upcat_2.convs.conv_0"), e->L[1], nwin, probe) &&
+           plan_conv_is(ctx, ctx->net.conv.at("conv_0.conv_0"), e->L[0], nwin, probe);
+}
+
+// 18 convs, 4 deconvs, norms, final blend.  Fused path: the first layer reads the uint16 windows itself (no gather);
+// per-tap path: from the gathered tensor in0.
+static int forward_windows(Ctx* ctx, int nwin, bool fused, const RawWindows& rawin, const WindowDesc* wd_dev, int32_t* acc, int64_t slabY,
+                           int64_t slabX, const BlendDev& bw, float* logits_out) {
     Engine* e = ctx->eng;
     int rc;
     DLV_CUDA_OK(ctx, cudaMemsetAsync(e->stats, 0, sizeof(double) * 18 * e->batch * kStatsPerLayer, ctx->stream));
 #define CB(i, name, lvl, a, na, b, out, pool) if ((rc = conv_block(ctx, e, i, name, lvl, nwin, a, na, b, out, pool))) return rc;
-    IsPlan probe;
-    const bool fused = ctx->use_fused && plan_conv_is(ctx, ctx->net.conv.at("upcat_1.convs.conv_0"), e->L[0], nwin, probe) &&
-                       plan_conv_is(ctx, ctx->net.conv.at("upcat_2.convs.conv_0"), e->L[1], nwin, probe);
     const bf16* last_raw = e->raw[0];
     if (fused) {
 #define FB(i, name, lvl, a, na, b, prod, pi, out) if ((rc = fused_block(ctx, e, i, name, lvl, nwin, a, na, b, prod, pi, out))) return rc;
-        FB(0, "conv_0.conv_0", 0, e->in0, 2, nullptr, nullptr, 0, e->c0a)
+        if ((rc = fused_block(ctx, e, 0, "conv_0.conv_0", 0, nwin, nullptr, 2, nullptr, nullptr, 0, e->c0a, &rawin))) return rc;
         FB(1, "conv_0.conv_1", 0, e->c0a, 4, nullptr, "conv_0.conv_0", 0, e->x0)
         if ((rc = norm_block(ctx, e, 1, "conv_0.conv_1", 0, nwin, e->x0, nullptr, e->p1))) return rc;
         FB(2, "down_1.convs.conv_0", 1, e->p1, 4, nullptr, nullptr, 0, e->d1a)
@@ -847,26 +877,33 @@ static int forward_from_in0(Ctx* ctx, int nwin, const WindowDesc* wd_dev, int32_
     const Level& L0 = e->L[0];
     const int n = L0.Z * L0.Y * L0.X;
     dim3 grid((n + 255) / 256, nwin);
+    StageTimer timer(ctx, kStageBlend);
     final_blend_kernel<<<grid, 256, 0, ctx->stream>>>(last_raw, to_dev(L0), e->stats + static_cast<size_t>(17) * e->batch * kStatsPerLayer,
                                                       last.gamma, last.beta, ctx->net.final_w, ctx->net.final_b, wd_dev, acc,
-                                                      slabY, slabX, wz, wy, wx, logits_out);
+                                                      slabY, slabX, bw, logits_out);
     ctx->launches++;
     DLV_CUDA_OK(ctx, cudaGetLastError());
     return 0;
 }
 
 int engine_run_batch(Ctx* ctx, const uint16_t* slab, int64_t slabY, int64_t slabX, const WindowDesc* wd_dev, int nwin,
-                     int32_t* acc, const float* wz, const float* wy, const float* wx, float* logits_out) {
+                     int32_t* acc, const BlendDev& bw, float* logits_out) {
     Engine* e = ctx->eng;
     if (!e || !ctx->net.loaded) { set_error(ctx, "engine_run_batch: weights/engine not ready"); return DLV_ERR_STATE; }
     if (nwin < 1 || nwin > e->batch) { set_error(ctx, "engine_run_batch: nwin %d outside [1,%d]", nwin, e->batch); return DLV_ERR_ARG; }
     const Level& L0 = e->L[0];
-    const int n = L0.Z * L0.Y * L0.X;
-    dim3 grid((n + 255) / 256, nwin);
-    gather_windows_kernel<<<grid, 256, 0, ctx->stream>>>(slab, slabY, slabX, wd_dev, to_dev(L0), e->in0);
-    ctx->launches++;
-    DLV_CUDA_OK(ctx, cudaGetLastError());
-    return forward_from_in0(ctx, nwin, wd_dev, acc, slabY, slabX, wz, wy, wx, logits_out);
+    const bool fused = fused_path(ctx, nwin);
+    RawWindows rawin;
+    rawin.slab = slab; rawin.sy = slabY; rawin.sx = slabX; rawin.wd = wd_dev;
+    if (!fused) {
+        const int n = L0.Z * L0.Y * L0.X;
+        dim3 grid((n + 255) / 256, nwin);
+        StageTimer timer(ctx, kStageGather);
+        gather_windows_kernel<<<grid, 256, 0, ctx->stream>>>(slab, slabY, slabX, wd_dev, to_dev(L0), e->in0);
+        ctx->launches++;
+        DLV_CUDA_OK(ctx, cudaGetLastError());
+    }
+    return forward_windows(ctx, nwin, fused, rawin, wd_dev, acc, slabY, slabX, bw, logits_out);
 }
 
 int windows_active(Ctx* ctx, const uint16_t* slab, int64_t slabY, int64_t slabX, const int32_t* origins_dev, int n,

@@ -391,7 +391,8 @@ class CudaSlabWorker(_CudaLabelOps):
             if len(sel) else np.zeros((0, 4), dtype=np.int32)
         with torch.cuda.stream(self.stream):
             self.acc = torch.zeros(self.slab.shape, dtype=torch.int32, device=self.dev)
-        self.ctx.seg_accumulate(self.slab, sched, self.plan.roi, self.acc, window_batch=self.window_batch, blend_mode=self.blend_mode)
+        self.ctx.seg_accumulate(self.slab, sched, self.plan.roi, self.acc, window_batch=self.window_batch, blend_mode=self.blend_mode,
+                                shape_pad=self.plan.shape_pad, overlap=self.plan.overlap, gz0=z0)
         return active
 
     def acc_planes(self, g0, g1):
@@ -657,15 +658,88 @@ def balanced_plan(ctx, comm, shape, roi, overlap, planes_fn):
     return SlabPlan(shape, roi, overlap, comm.world, window_weights=all_act), per_layer
 
 
-def _roofline(B, workload, windows_active, conv_ms_max, world):
+def _roofline(B, workload, windows_active, conv_ms_max, world, roi=None):
     tf_peak, _, peak_kind = B.peaks()
-    flop = 2.0 * B.MAC_PER_PATCH_VOXEL * windows_active * B.ROI[0] * B.ROI[1] * B.ROI[2]
+    roi = tuple(roi or B.ROI)
+    flop = 2.0 * B.MAC_PER_PATCH_VOXEL * windows_active * roi[0] * roi[1] * roi[2]
     achieved = flop / (conv_ms_max * 1e-3) / 1e12 / world if conv_ms_max > 0 else 0.0
-    traffic, src = B.conv_traffic(workload, windows_active)
+    traffic, src = B.conv_traffic(workload, windows_active) if roi == tuple(B.ROI) else (None, None)
     return {"bound": "tensor", "kernel": "conv_is_kernel / conv_tc_kernel (all conv/deconv launches of one step)",
             "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s per GPU", "frac": achieved / tf_peak,
             "traffic": traffic, "traffic_source": src, "peak_kind": f"bf16_tflops_sustained, {peak_kind}",
             "conv_ms_per_step_max_rank": conv_ms_max}
+
+
+class _TimedWorker(CudaSlabWorker):
+    """Bench only: device-synchronised wall time of the finalise and labelling stages of one (untimed) step."""
+    t_finalise = t_ccl = 0.0
+
+    def _timed(self, fn, *a):
+        import time
+        self.stream.synchronize()
+        t0 = time.perf_counter()
+        out = fn(*a)
+        self.stream.synchronize()
+        return out, (time.perf_counter() - t0) * 1e3
+
+    def finalise(self, active_global):
+        out, self.t_finalise = self._timed(super().finalise, active_global)
+        return out
+
+    def ccl(self):
+        out, self.t_ccl = self._timed(super().ccl)
+        return out
+
+
+CFG5_WINDOWS = (64, 96, 128, 160, 192)
+CFG5_OVERLAPS = (0.25, 0.5, 0.75)
+
+
+def bench_cfg5(B, args, ctx, comm, stream, dev, rank, world, wdesc):
+    """BASELINE.json configs[4]: sliding-window patch-size / overlap sweep (64^3 - 192^3, overlap 0.25 - 0.75) on one
+    volume sharded over the N GPUs; per point the throughput, the tensor roofline fraction of the convolutions and the
+    HBM roofline fractions of the blend, finalise and labelling stages (algorithmic bytes of SURVEY.md section 8d)."""
+    wl = B.WORKLOADS["cfg5"]
+    _, hbm_peak, _ = B.peaks()
+    pts = []
+    only = getattr(args, "sweep_only", None)
+    for win in CFG5_WINDOWS:
+        for ov in CFG5_OVERLAPS:
+            if only and f"{win}:{ov}" not in only:
+                continue
+            roi = (win, win, win)
+            r = _bench_job(B, args, ctx, comm, stream, dev, rank, world, wl, True, False, args.steps, min(args.warmup, 1), False, True,
+                           roi=roi, overlap=ov, want_stages=True)
+            if rank != 0:
+                continue
+            nv, pv = r["nvox"], float(r["windows_active"]) * win ** 3
+            sm = r["stage_ms_max_rank"]
+            gbs = lambda nbytes, ms: (nbytes / world / (ms * 1e-3) / 1e9) if ms > 0 else None
+            blend, fin, ccl = gbs(10.0 * pv, sm["blend"]), gbs(7.0 * nv, sm["finalise"]), gbs(9.0 * nv, sm["ccl"])
+            pts.append({"window": win, "overlap": ov, "gvoxels_per_s": r["gvoxels_per_s"], "ms_per_step": r["ms_per_step"],
+                        "windows_active": r["windows_active"], "conv_tflops_per_gpu": r["roofline"]["achieved"],
+                        "conv_frac_of_bf16_peak": r["roofline"]["frac"], "non_conv_share": r["non_conv_share"],
+                        "blend_gbs_per_gpu": blend, "blend_frac_of_hbm": blend / hbm_peak if blend else None,
+                        "finalise_gbs_per_gpu": fin, "finalise_frac_of_hbm": fin / hbm_peak if fin else None,
+                        "ccl_gbs_per_gpu": ccl, "ccl_frac_of_hbm": ccl / hbm_peak if ccl else None,
+                        "stage_ms_max_rank": sm, "clocks": r["clocks"], "launches": r["launches"]})
+    if rank != 0:
+        return
+    head = next((p for p in pts if p["window"] == 96 and p["overlap"] == 0.5), pts[0])
+    shape = wl["shape"]
+    B.emit({"metric": "Gvoxels/s seg+CC", "value": head["gvoxels_per_s"], "unit": "Gvoxels/s", "n_gpus": world, "steps": args.steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16", "data": f"synthetic; {wdesc}",
+            "config": {"workload": f"{wl['name']}, z-slab sharded over {world} GPUs; headline = window {head['window']}^3, overlap {head['overlap']}",
+                       "sweep": pts, "tta": False, "blend": "constant",
+                       "fused_path": "windows whose x extent keeps the fused input-stationary conv's stages in shared memory (x <= ~150) run it; "
+                                     "192^3 runs the per-tap tcgen05 kernel + separate norm passes",
+                       "algorithmic_bytes": {"blend_per_active_patch_voxel": 10, "finalise_per_voxel": 7, "ccl_per_voxel": 9},
+                       "timing": "CUDA events on the library stream between barriers, max over ranks; stage times from one extra, serialised step",
+                       "l2": "inputs larger than L2"},
+            "gpu_launches": sum(p["launches"] for p in pts), "clocks": head["clocks"],
+            "roofline": {"bound": "tensor", "kernel": "conv_is_kernel / conv_tc_kernel", "achieved": head["conv_tflops_per_gpu"],
+                         "peak": B.peaks()[0], "unit": "TFLOP/s per GPU", "frac": head["conv_frac_of_bf16_peak"], "traffic": None}})
 
 
 class _Trace:
@@ -704,7 +778,8 @@ class _Trace:
                   f" | total {sum(v for _, v in self.rows):.1f} ms", file=sys.stderr, flush=True)
 
 
-def _bench_job(B, args, ctx, comm, stream, dev, rank, world, wl, whole, tta, steps, warmup, want_e2e, want_roofline):
+def _bench_job(B, args, ctx, comm, stream, dev, rank, world, wl, whole, tta, steps, warmup, want_e2e, want_roofline,
+               roi=None, overlap=None, want_stages=False):
     """One measured configuration of the N-GPU bench: the volume (N stacked copies of the workload, or ONE whole
     volume) is sharded by balanced_plan and every step is the product path - CudaSlabWorker + run_distributed, what
     run_inference / count_blobs drive under torchrun.  -> dict of results on rank 0 (None elsewhere)."""
@@ -713,9 +788,11 @@ def _bench_job(B, args, ctx, comm, stream, dev, rank, world, wl, whole, tta, ste
     from .synth import synth_volume_cuda
     from .inference.inference import erosion_block_planes
     z1, Y, X = wl["shape"]
+    roi = tuple(roi or B.ROI)
+    overlap = B.OVERLAP if overlap is None else float(overlap)
     shape = (z1, Y, X) if whole else (z1 * world, Y, X)
     evaluated = 3 if tta else 1                # 13 reference passes = 3 distinct ones blended 5 / 4 / 4 times
-    PZ, PY, PX = SlabPlan(shape, B.ROI, B.OVERLAP, world).shape_pad
+    PZ, PY, PX = SlabPlan(shape, roi, overlap, world).shape_pad
 
     def planes(z0, z1_):
         full = torch.zeros((z1_ - z0, PY, PX), dtype=torch.uint16, device=dev)
@@ -729,7 +806,7 @@ def _bench_job(B, args, ctx, comm, stream, dev, rank, world, wl, whole, tta, ste
 
     ebp = erosion_block_planes(shape)
     with torch.cuda.stream(stream):
-        plan, per_layer = balanced_plan(ctx, comm, shape, B.ROI, B.OVERLAP, planes)
+        plan, per_layer = balanced_plan(ctx, comm, shape, roi, overlap, planes)
         info = plan.rank(rank)
         slab = planes(*info["slab"])
         o0, o1 = info["own_real"]
@@ -748,13 +825,17 @@ def _bench_job(B, args, ctx, comm, stream, dev, rank, world, wl, whole, tta, ste
             d = torch.empty(slab.shape, dtype=torch.uint16, device=dev)
             d.copy_(hslab, non_blocking=True)
             return d
-        w = CudaSlabWorker(ctx, plan, rank, load, erosion_block_planes=ebp, tta=tta)
+        w = (_TimedWorker if timing["on"] else CudaSlabWorker)(ctx, plan, rank, load, erosion_block_planes=ebp, tta=tta)
         table = run_distributed(w, plan, comm)
+        if timing["on"]:
+            timing.update(finalise=w.t_finalise, ccl=w.t_ccl)
         if host:
             with torch.cuda.stream(stream):
                 hbin.copy_(w.binaries, non_blocking=True)
             stream.synchronize()
         return table, w
+
+    timing = {"on": False}
 
     def timed(host, n):
         dist.barrier()
@@ -790,11 +871,16 @@ def _bench_job(B, args, ctx, comm, stream, dev, rank, world, wl, whole, tta, ste
         # roofline of the tcgen05 convolutions: one extra step with per-launch event timing on every rank; the job's
         # algorithmic FLOP / the slowest rank's conv time, per GPU
         ctx.set_conv_timing(True)
+        timing["on"] = bool(want_stages)
         step(False)
-        conv = torch.tensor([ctx.conv_time_ms()], device=dev, dtype=torch.float64)
+        timing["on"] = False
+        st = ctx.stage_times_ms()
+        conv = torch.tensor([st["conv"], st["blend"], st["norm"], st["gather"], timing.get("finalise", 0.0), timing.get("ccl", 0.0)],
+                            device=dev, dtype=torch.float64)
         ctx.set_conv_timing(False)
         dist.all_reduce(conv, op=dist.ReduceOp.MAX)
-        conv_ms = float(conv.item())
+        conv_ms = float(conv[0].item())
+        stage_ms = {k: float(conv[i].item()) for i, k in enumerate(("conv", "blend", "norm", "gather", "finalise", "ccl"))}
     del slab, hslab, hbin
     torch.cuda.empty_cache()
     if rank != 0:
@@ -810,7 +896,8 @@ def _bench_job(B, args, ctx, comm, stream, dev, rank, world, wl, whole, tta, ste
                       "d2h_bytes_per_step": int(io[1].item()) + nrow * (8 + 24 + 48), "ms_per_step": ms_e2e,
                       "note": "per-rank pinned host slab in, pinned host binaries + merged table out"}
     if want_roofline:
-        res["roofline"] = _roofline(B, args.workload, int(per_layer.sum()) * evaluated, conv_ms, world)
+        res["roofline"] = _roofline(B, args.workload, int(per_layer.sum()) * evaluated, conv_ms, world, roi)
+        res["stage_ms_max_rank"] = stage_ms
         # strong-scaling view of the same step: what the job would take if only the convolutions ran, perfectly split
         res["non_conv_share"] = 1.0 - conv_ms / ms if ms > 0 else None
     return res
@@ -839,6 +926,10 @@ def bench_main(args, rank, local_rank, world):
     ctx.load_weights(sd)
     stream = torch.cuda.ExternalStream(ctx._L.dlv_stream(ctx._h), device=dev)
     comm = TorchComm(dev)
+    if args.workload == "cfg5":
+        bench_cfg5(B, args, ctx, comm, stream, dev, rank, world, wdesc)
+        dist.destroy_process_group()
+        return
     head = _bench_job(B, args, ctx, comm, stream, dev, rank, world, wl, whole, tta, args.steps, args.warmup, True, True)
     cfg4 = None
     if not whole and args.workload == "cfg2" and not getattr(args, "no_cfg4", False):

@@ -35,7 +35,7 @@ typedef struct dlv_ctx dlv_ctx;
 #define DLV_ERR_STATE (-3)
 #define DLV_ERR_UNSUPPORTED (-4)
 
-#define DLV_ABI_VERSION 2
+#define DLV_ABI_VERSION 3
 
 /* ---- lifecycle -------------------------------------------------------- */
 int dlv_abi_version(void);
@@ -54,6 +54,10 @@ int dlv_set_conv_timing(dlv_ctx* ctx, int enable);
 /* Device time accumulated in the convolution kernels since timing was last enabled / the last dlv_segment started
  * (the slab-level entry points do not reset it). */
 int dlv_conv_time_ms(const dlv_ctx* ctx, double* ms_out);
+/* Same accounting per stage of the window loop while timing is enabled: stage 0 = tcgen05 convolutions (what
+ * dlv_conv_time_ms returns), 1 = final 1x1 conv + overlap blend (sliding_window_inferer.py:232-251), 2 = InstanceNorm /
+ * Mish / MaxPool passes that are not fused into a convolution, 3 = uint16 window gather (sliding_window_inferer.py:181-195). */
+int dlv_stage_time_ms(const dlv_ctx* ctx, int stage, double* ms_out);
 
 /* ---- network weights --------------------------------------------------
  * Replaces BasicUNet(...) + load_state_dict(checkpoint["state_dict"])
@@ -171,8 +175,15 @@ int dlv_windows_active(dlv_ctx* ctx, const uint16_t* slab_dev, int64_t SY, int64
  * origins local to the slab; the window's logits are added `repeat` times (identical noise-free TTA passes,
  * inference.py:269-279, are evaluated once); acc_dev: int32, same extent as the slab, fixed point 2^-12 logit units
  * (+=, order independent). */
+/* Where the slab sits in the window grid - needed by the gaussian blend only (blend_mode 1), whose per-voxel weight
+ * normalisation depends on the windows that cover a plane globally; NULL for the constant blend. */
+typedef struct dlv_blend_geom {
+    int64_t shape_pad[3];   /* padded volume (Zp,Yp,Xp) */
+    float overlap;
+    int64_t gz0;            /* global plane of the slab's first plane */
+} dlv_blend_geom;
 int dlv_seg_accumulate(dlv_ctx* ctx, const uint16_t* slab_dev, int64_t SY, int64_t SX, const int32_t* windows_host, int n,
-                       const int32_t roi[3], int window_batch, int blend_mode, int32_t* acc_dev);
+                       const int32_t roi[3], int window_batch, int blend_mode, const dlv_blend_geom* geom_or_null, int32_t* acc_dev);
 /* In-place int32 sums -> float32 averaged logits for planes [gz0, gz0+nplanes) of the padded volume
  * (inference.py:285-299); active_host is the whole window grid [nz][ny][nx] (skipped windows contribute -1000). */
 int dlv_seg_average(dlv_ctx* ctx, int32_t* acc_dev_inout, int64_t nplanes, int64_t gz0, const int64_t shape_pad[3],

@@ -9,9 +9,10 @@ from oracle import pipeline_ref as P, unet_ref
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("shape,roi,world,tta", [((100, 80, 70), (32, 32, 32), 3, False), ((70, 64, 64), (32, 48, 32), 2, False),
-                                                 ((150, 60, 50), (32, 32, 32), 4, True), ((40, 64, 64), (32, 32, 32), 5, False)])
-def test_virtual_slabs_equal_single_gpu(shape, roi, world, tta):
+@pytest.mark.parametrize("shape,roi,world,tta,blend", [((100, 80, 70), (32, 32, 32), 3, False, 0), ((70, 64, 64), (32, 48, 32), 2, False, 0),
+                                                       ((150, 60, 50), (32, 32, 32), 4, True, 0), ((40, 64, 64), (32, 32, 32), 5, False, 0),
+                                                       ((100, 80, 70), (32, 32, 32), 3, False, 1), ((120, 60, 50), (32, 48, 32), 4, True, 1)])
+def test_virtual_slabs_equal_single_gpu(shape, roi, world, tta, blend):
     from delivr_cfos_b200 import Context
     from delivr_cfos_b200 import slabs
     from delivr_cfos_b200.synth import synth_volume_cuda
@@ -26,14 +27,14 @@ def test_virtual_slabs_equal_single_gpu(shape, roi, world, tta):
     shape_pad = tuple(vol.shape)
     # single slab
     b1 = torch.empty(shape, dtype=torch.uint8, device="cuda")
-    ctx.segment(vol, shape_pad, shape, roi, b1, tta=tta, erosion_block_planes=17)
+    ctx.segment(vol, shape_pad, shape, roi, b1, tta=tta, erosion_block_planes=17, blend_mode=blend)
     l1 = torch.empty(shape, dtype=torch.int32, device="cuda")
     t1 = ctx.ccl(b1, shape, labels_out=l1)
     assert t1["n"] > 3 and int(b1.sum()) > 0
     # N virtual slabs
     plan = slabs.SlabPlan(shape, roi, 0.5, world)
     assert plan.shape_pad == shape_pad
-    workers = [slabs.CudaSlabWorker(ctx, plan, r, lambda a, b: vol[a:b].contiguous(), tta=tta, erosion_block_planes=17)
+    workers = [slabs.CudaSlabWorker(ctx, plan, r, lambda a, b: vol[a:b].contiguous(), tta=tta, erosion_block_planes=17, blend_mode=blend)
                for r in range(world)]
     table = slabs.run_virtual(workers, plan)
     bN = torch.cat([w.binaries for w in workers])
