@@ -24,15 +24,17 @@ from .count_blobs import _context, load_cached_stats
 from .slabs import ccl_any_size
 
 
-def blob_depths(stats, distances, settings):
-    """blob_depthmap.py:184-197: centroid -> down-sampled voxel -> distance value, rows 0..N."""
+def blob_depths(stats, distances, settings, n=None):
+    """blob_depthmap.py:184-207: centroid -> down-sampled voxel -> distance value, for the rows the painting loop
+    reads (0..N-1: the reference never touches the last component).  The background row's centroid may be NaN (no
+    background voxel): such rows read voxel (0, 0, 0) instead of a garbage index; indices are clipped to the stack."""
     ds = settings["mask_detection"]["downsample_steps"]
-    coordinates = np.array(stats["centroids"], dtype=np.float64).copy()
+    coordinates = np.array(stats["centroids"], dtype=np.float64)[:n].copy()
+    coordinates[~np.isfinite(coordinates).all(axis=1)] = 0.0
     coordinates[:, 0] = coordinates[:, 0] / (ds["downsample_um_z"] / ds["original_um_z"])
     coordinates[:, 1] = coordinates[:, 1] / (ds["downsample_um_y"] / ds["original_um_y"])
     coordinates[:, 2] = coordinates[:, 2] / (ds["downsample_um_x"] / ds["original_um_x"])
-    with np.errstate(invalid="ignore"):
-        coordinates = coordinates.astype(int)
+    coordinates = np.clip(coordinates.astype(int), 0, np.array(distances.shape) - 1)
     return distances[coordinates[:, 0], coordinates[:, 1], coordinates[:, 2]]
 
 
@@ -73,7 +75,7 @@ def depth_map_blobs(settings, brain, stack_shape, device=0):
     distances = distances.astype(np.uint16)
 
     print(f"{datetime.datetime.now()} : generating depth-coded blob map")
-    depths = blob_depths(stats, distances, settings)
+    depths = blob_depths(stats, distances, settings, n=N)
     ids = np.arange(N)
     boxes = padded_boxes(stats, ids, stack_shape)
     depthmap = np.empty(shape, dtype=np.uint16)

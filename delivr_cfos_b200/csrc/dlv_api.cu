@@ -58,6 +58,7 @@ int dlv_init(int device, dlv_ctx** out) {
     if (const char* e = getenv("DLV_IS_T")) ctx->is_tiles = atoi(e);
     DLV_CUDA_OK(ctx, cudaSetDevice(device));
     DLV_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    DLV_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     {   // keep freed transient buffers in the pool (they are re-used by the next call instead of returned to the driver)
         cudaMemPool_t pool;
         DLV_CUDA_OK(ctx, cudaDeviceGetDefaultMemPool(&pool, device));
@@ -79,6 +80,7 @@ void dlv_destroy(dlv_ctx* c) {
     if (ctx->paint_owner) cudaFree(ctx->paint_owner);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -141,7 +143,8 @@ int dlv_ccl(dlv_ctx* c, const void* mask_any, const int64_t shape[3], int connec
     void *mask_own = nullptr, *lab_own = nullptr;
     if (!dlv::dev_ptr(mask_any)) {
         DLV_CUDA_OK(ctx, dlv::dmalloc(ctx, &mask_own, n));
-        DLV_CUDA_OK(ctx, cudaMemcpyAsync(mask_own, mask_any, n, cudaMemcpyHostToDevice, ctx->stream));
+        cudaError_t e = cudaMemcpyAsync(mask_own, mask_any, n, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) { dlv::dfree(ctx, mask_own); dlv::set_error(ctx, "dlv_ccl: mask upload: %s", cudaGetErrorString(e)); return DLV_ERR_CUDA; }
         mask = static_cast<const uint8_t*>(mask_own);
     }
     uint32_t* labels = static_cast<uint32_t*>(labels_out_any);

@@ -61,6 +61,7 @@ struct Ctx {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // host -> device volume chunks of dlv_segment, overlapped with the window passes
     char err[1024] = {0};
     int64_t launches = 0;
     Net net;

@@ -364,69 +364,122 @@ int segment_run(Ctx* ctx, const void* volume_any, const dlv_seg_params* P, void*
     const size_t nvox_pad = static_cast<size_t>(PZ) * PY * PX;
     const size_t nvox = static_cast<size_t>(Z) * Y * X;
 
-    // ---- input slab on the device
-    DevBuf slab_own;
-    const uint16_t* slab = static_cast<const uint16_t*>(volume_any);
-    if (!is_device_ptr(volume_any)) {
-        if ((rc = dev_alloc(ctx, slab_own, nvox_pad * 2))) return rc;
-        DLV_CUDA_OK(ctx, cudaMemcpyAsync(slab_own.p, volume_any, nvox_pad * 2, cudaMemcpyHostToDevice, ctx->stream));
-        slab = slab_own.as<uint16_t>();
-    }
-
-    mark("volume on device");
     // ---- window grid, z-major / x fastest like dense_patch_slices
     const std::vector<int> sz = window_starts(PZ, P->roi[0], P->overlap), sy = window_starts(PY, P->roi[1], P->overlap),
                            sx = window_starts(PX, P->roi[2], P->overlap);
     const int nz = sz.size(), ny = sy.size(), nx = sx.size();
-    const int64_t nwin = static_cast<int64_t>(nz) * ny * nx;
+    const int64_t nwin = static_cast<int64_t>(nz) * ny * nx, per_layer = static_cast<int64_t>(ny) * nx;
     std::vector<int32_t> origins(nwin * 3);
     for (int iz = 0, w = 0; iz < nz; ++iz)
         for (int iy = 0; iy < ny; ++iy)
             for (int ix = 0; ix < nx; ++ix, ++w) { origins[3 * w] = sz[iz]; origins[3 * w + 1] = sy[iy]; origins[3 * w + 2] = sx[ix]; }
-    DevBuf d_orig, d_active;
-    if ((rc = dev_upload(ctx, d_orig, origins))) return rc;
-    if ((rc = dev_alloc(ctx, d_active, nwin * sizeof(int32_t)))) return rc;
-    std::vector<int32_t> active(nwin, 1);
-    if (P->skip_empty) {
-        if ((rc = windows_active(ctx, slab, PY, PX, d_orig.as<int32_t>(), static_cast<int>(nwin), P->roi, d_active.as<int32_t>()))) return rc;
-        DLV_CUDA_OK(ctx, cudaMemcpyAsync(active.data(), d_active.p, nwin * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        DLV_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-    } else {
-        DLV_CUDA_OK(ctx, cudaMemcpyAsync(d_active.p, active.data(), nwin * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    }
-
-    mark("skip-rule scan");
-    // ---- schedule: passes x active windows
     const int passes = P->tta ? 13 : 1;
     int single_flip = 0;
     if (!P->tta && P->flip_dim) {
         if (P->flip_dim < 2 || P->flip_dim > 4) { set_error(ctx, "flip_dim must be 0, 2 (z), 3 (y) or 4 (x)"); return DLV_ERR_ARG; }
         single_flip = P->flip_dim - 1;
     }
-    std::vector<WindowDesc> sched;
-    int64_t nactive = 0;
-    for (int64_t w = 0; w < nwin; ++w) nactive += active[w] != 0;
     const int distinct = P->tta ? 3 : 1;
-    sched.reserve(nactive * distinct);
-    for (int ps = 0; ps < distinct; ++ps)
-        for (int64_t w = 0; w < nwin; ++w)
-            if (active[w])
-                sched.push_back(WindowDesc{origins[3 * w], origins[3 * w + 1], origins[3 * w + 2],
-                                           P->tta ? (kTtaFlips[ps] | ((kTtaRepeat[ps] - 1) << 8)) : single_flip});
+    auto push_window = [&](std::vector<WindowDesc>& out, int64_t w, int ps) {
+        out.push_back(WindowDesc{origins[3 * w], origins[3 * w + 1], origins[3 * w + 2],
+                                 P->tta ? (kTtaFlips[ps] | ((kTtaRepeat[ps] - 1) << 8)) : single_flip});
+    };
 
-    // ---- accumulate
-    DevBuf d_acc;
+    // ---- input slab on the device.  A host volume is uploaded in z chunks on a second stream - chunk k ends where
+    // window z-layer k ends - and layer k's skip scan and window batches start as soon as their chunk has landed, so
+    // everything but the first chunk of the upload hides behind the network (pinned host memory; a pageable volume
+    // is staged by the driver and overlaps only with batches that are already enqueued).
+    DevBuf slab_own, d_orig, d_active, d_acc;
+    const uint16_t* slab = static_cast<const uint16_t*>(volume_any);
+    const bool host_volume = !is_device_ptr(volume_any);
+    if ((rc = dev_upload(ctx, d_orig, origins))) return rc;
+    if ((rc = dev_alloc(ctx, d_active, nwin * sizeof(int32_t)))) return rc;
+    std::vector<int32_t> active(nwin, 1);
     if ((rc = dev_alloc(ctx, d_acc, nvox_pad * 4))) return rc;
     DLV_CUDA_OK(ctx, cudaMemsetAsync(d_acc.p, 0, nvox_pad * 4, ctx->stream));
-    mark("schedule + acc memset");
-    cudaEvent_t e0, e1, e2;
-    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
-    const int64_t launches0 = ctx->launches;
-    ctx->conv_ms = 0.0;
-    cudaEventRecord(e0, ctx->stream);
+    struct Events {           // destroyed on every return path
+        std::vector<cudaEvent_t> e;
+        explicit Events(int n) : e(n, nullptr) { for (auto& x : e) cudaEventCreateWithFlags(&x, cudaEventDisableTiming); }
+        ~Events() { for (auto& x : e) if (x) cudaEventDestroy(x); }
+    };
+    struct TimingEvents {
+        cudaEvent_t e[3] = {nullptr, nullptr, nullptr};
+        TimingEvents() { for (auto& x : e) cudaEventCreate(&x); }
+        ~TimingEvents() { for (auto& x : e) if (x) cudaEventDestroy(x); }
+    } tev;
+    cudaEvent_t e0 = tev.e[0], e1 = tev.e[1], e2 = tev.e[2];
     dlv_blend_geom geom;
     geom.shape_pad[0] = PZ; geom.shape_pad[1] = PY; geom.shape_pad[2] = PX; geom.overlap = P->overlap; geom.gz0 = 0;
-    rc = seg_accumulate(ctx, slab, PY, PX, sched, P->roi, batch, P->blend_mode, d_acc.as<int32_t>(), &geom);
+    const int64_t launches0 = ctx->launches;
+    ctx->conv_ms = 0.0;
+    int64_t nactive = 0;
+    cudaEventRecord(e0, ctx->stream);
+    if (!host_volume) {
+        if (P->skip_empty) {
+            if ((rc = windows_active(ctx, slab, PY, PX, d_orig.as<int32_t>(), static_cast<int>(nwin), P->roi, d_active.as<int32_t>()))) return rc;
+            DLV_CUDA_OK(ctx, cudaMemcpyAsync(active.data(), d_active.p, nwin * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            DLV_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        mark("skip-rule scan");
+        // ---- schedule: passes x active windows
+        std::vector<WindowDesc> sched;
+        for (int64_t w = 0; w < nwin; ++w) nactive += active[w] != 0;
+        sched.reserve(nactive * distinct);
+        for (int ps = 0; ps < distinct; ++ps)
+            for (int64_t w = 0; w < nwin; ++w)
+                if (active[w]) push_window(sched, w, ps);
+        rc = seg_accumulate(ctx, slab, PY, PX, sched, P->roi, batch, P->blend_mode, d_acc.as<int32_t>(), &geom);
+    } else {
+        if ((rc = dev_alloc(ctx, slab_own, nvox_pad * 2))) return rc;
+        slab = slab_own.as<uint16_t>();
+        Events landed(nz);
+        // the allocation (stream-ordered on ctx->stream) must precede the first copy on the copy stream
+        cudaEvent_t alloc_done = nullptr;
+        cudaEventCreateWithFlags(&alloc_done, cudaEventDisableTiming);
+        cudaEventRecord(alloc_done, ctx->stream);
+        cudaStreamWaitEvent(ctx->copy_stream, alloc_done, 0);
+        cudaEventDestroy(alloc_done);
+        const size_t plane_bytes = static_cast<size_t>(PY) * PX * 2;
+        int64_t copied = 0;                                     // planes already enqueued
+        auto upload_layer = [&](int k) -> int {                 // chunk k: up to the end of window layer k (the last one takes the rest)
+            const int64_t end = (k == nz - 1) ? PZ : std::min<int64_t>(PZ, static_cast<int64_t>(sz[k]) + P->roi[0]);
+            if (end > copied) {
+                DLV_CUDA_OK(ctx, cudaMemcpyAsync(slab_own.as<uint8_t>() + copied * plane_bytes, static_cast<const uint8_t*>(volume_any) + copied * plane_bytes,
+                                                 static_cast<size_t>(end - copied) * plane_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+                copied = end;
+            }
+            DLV_CUDA_OK(ctx, cudaEventRecord(landed.e[k], ctx->copy_stream));
+            return 0;
+        };
+        if ((rc = upload_layer(0))) return rc;
+        std::vector<WindowDesc> pending;                        // active windows whose planes have landed, not yet run
+        const size_t bcap = static_cast<size_t>(engine_batch_capacity(ctx));
+        for (int k = 0; k < nz && rc == 0; ++k) {
+            if (k + 1 < nz && (rc = upload_layer(k + 1))) return rc;
+            DLV_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, landed.e[k], 0));
+            const int64_t w0 = static_cast<int64_t>(k) * per_layer;
+            if (P->skip_empty) {
+                if ((rc = windows_active(ctx, slab, PY, PX, d_orig.as<int32_t>() + 3 * w0, static_cast<int>(per_layer), P->roi,
+                                         d_active.as<int32_t>() + w0))) return rc;
+                DLV_CUDA_OK(ctx, cudaMemcpyAsync(active.data() + w0, d_active.as<int32_t>() + w0, per_layer * sizeof(int32_t),
+                                                 cudaMemcpyDeviceToHost, ctx->stream));
+                DLV_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+            }
+            for (int ps = 0; ps < distinct; ++ps)
+                for (int64_t w = w0; w < w0 + per_layer; ++w)
+                    if (active[w]) { push_window(pending, w, ps); nactive += ps == 0; }
+            // whole batches now; what is left over joins the next layer's windows (window order does not matter:
+            // the blend is an integer sum)
+            const size_t run = (k == nz - 1) ? pending.size() : (bcap ? pending.size() / bcap * bcap : pending.size());
+            if (run) {
+                std::vector<WindowDesc> now(pending.begin(), pending.begin() + run);
+                pending.erase(pending.begin(), pending.begin() + run);
+                rc = seg_accumulate(ctx, slab, PY, PX, now, P->roi, batch, P->blend_mode, d_acc.as<int32_t>(), &geom);
+            }
+        }
+        cudaStreamSynchronize(ctx->copy_stream);
+        mark("upload + skip-rule scan");
+    }
     cudaEventRecord(e1, ctx->stream);
     mark("u-net passes");
 
@@ -466,7 +519,6 @@ int segment_run(Ctx* ctx, const void* volume_any, const dlv_seg_params* P, void*
         cudaEventElapsedTime(&ms, e1, e2); st_out->ms_finalise = ms;
         st_out->ms_conv = ctx->conv_ms;
     }
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     return rc;
 }
 

@@ -305,6 +305,66 @@ def unpack_table(rows):
             "sums": np.ascontiguousarray(rows[:, 1:4]).view(np.uint64), "bounding_boxes": np.ascontiguousarray(rows[:, 4:10])}
 
 
+# ------------------------------------------------------------------------------------------- overlapped slab upload
+class StreamedSlab:
+    """A device slab whose planes are still arriving.  ``feed(copy_chunk)`` runs in a background thread:
+    ``copy_chunk(a, b)`` must enqueue the upload of planes [a, b) on ``self.side`` (a second CUDA stream); after each
+    chunk an event is recorded.  The consumer iterates ``chunks()`` -> (planes landed so far, is_last) and calls
+    ``wait(stream)`` to order its stream after the chunk just yielded."""
+
+    def __init__(self, tensor, bounds, side_stream, torch):
+        import queue
+        import threading
+        self.tensor, self.bounds, self.side, self.torch = tensor, list(bounds), side_stream, torch
+        self._q = queue.Queue()
+        self._threading = threading
+        self._event = None
+        self._thread = None
+        self._error = None
+
+    def feed(self, copy_chunk, after=None):
+        def work():
+            try:
+                with self.torch.cuda.stream(self.side):
+                    if after is not None:
+                        self.side.wait_event(after)
+                    a = 0
+                    for b in self.bounds:
+                        copy_chunk(a, b)
+                        ev = self.torch.cuda.Event()
+                        ev.record(self.side)
+                        self._q.put((b, ev))
+                        a = b
+            except BaseException as e:      # surfaced in the consumer
+                self._error = e
+                self._q.put((None, None))
+        self._thread = self._threading.Thread(target=work, daemon=True)
+        self._thread.start()
+        return self
+
+    def chunks(self):
+        for i in range(len(self.bounds)):
+            b, ev = self._q.get()
+            if b is None:
+                raise self._error
+            self._event = ev
+            yield b, i == len(self.bounds) - 1
+        self._thread.join()
+
+    def wait(self, stream):
+        stream.wait_event(self._event)
+
+
+def layer_bounds(plan, rank):
+    """Upload chunk ends (slab-local planes) for rank's slab: where each of its window z-layers ends, then the rest."""
+    info = plan.rank(rank)
+    z0, z1 = info["slab"]
+    rz = plan.roi[0]
+    ends = sorted({min(z1, plan.sz[l] + rz) - z0 for l in range(info["layers"][0], info["layers"][1])})
+    ends = [e for e in ends if 0 < e < z1 - z0]
+    return ends + [z1 - z0]
+
+
 # ------------------------------------------------------------------------------------------- CUDA workers
 class _CudaLabelOps:
     """Labelling stage of a slab of device-resident binaries (``self.binaries``): local labels + table, the seam
@@ -370,9 +430,26 @@ class CudaSlabWorker(_CudaLabelOps):
         self.blend_mode, self.want_sigmoid, self.keep_avg = blend_mode, want_sigmoid, keep_avg
         self.sigmoid = self.avg_own = None
         z0, z1 = self.info["slab"]
+        self.loading = None
         with torch.cuda.stream(self.stream):
-            self.slab = planes_fn(z0, z1) if z1 > z0 else None        # uint16 (z1-z0, PY, PX) on the device
+            got = planes_fn(z0, z1) if z1 > z0 else None              # uint16 (z1-z0, PY, PX) on the device
+        if isinstance(got, StreamedSlab):                             # planes still arriving: see accumulate()
+            self.loading, got = got, got.tensor
+        self.slab = got
         self.acc = None
+
+    def _schedule(self, sel):
+        # inference.py:265-279: 13 passes = 5 x plain, 4 x flip z (dim 2), 4 x flip y (dim 3); identical passes are
+        # evaluated once and blended `repeat` times (flip_dim | (repeat - 1) << 8, see dlv_seg_accumulate)
+        flips = [0 | (4 << 8), 2 | (3 << 8), 3 | (3 << 8)] if self.tta else [0]
+        if not len(sel):
+            return np.zeros((0, 4), dtype=np.int32)
+        return np.concatenate([np.concatenate([sel, np.full((len(sel), 1), f, dtype=np.int32)], axis=1) for f in flips])
+
+    def _run(self, sched):
+        if len(sched):
+            self.ctx.seg_accumulate(self.slab, sched, self.plan.roi, self.acc, window_batch=self.window_batch, blend_mode=self.blend_mode,
+                                    shape_pad=self.plan.shape_pad, overlap=self.plan.overlap, gz0=self.info["slab"][0])
 
     def accumulate(self):
         torch = self.torch
@@ -382,17 +459,34 @@ class CudaSlabWorker(_CudaLabelOps):
         wins = self.plan.windows_of(self.r)
         local = wins.copy()
         local[:, 0] -= z0
-        active = self.ctx.windows_active(self.slab, local, self.plan.roi)
-        sel = local[active != 0]
-        # inference.py:265-279: 13 passes = 5 x plain, 4 x flip z (dim 2), 4 x flip y (dim 3); identical passes are
-        # evaluated once and blended `repeat` times (flip_dim | (repeat - 1) << 8, see dlv_seg_accumulate)
-        flips = [0 | (4 << 8), 2 | (3 << 8), 3 | (3 << 8)] if self.tta else [0]
-        sched = np.concatenate([np.concatenate([sel, np.full((len(sel), 1), f, dtype=np.int32)], axis=1) for f in flips]) \
-            if len(sel) else np.zeros((0, 4), dtype=np.int32)
         with torch.cuda.stream(self.stream):
             self.acc = torch.zeros(self.slab.shape, dtype=torch.int32, device=self.dev)
-        self.ctx.seg_accumulate(self.slab, sched, self.plan.roi, self.acc, window_batch=self.window_batch, blend_mode=self.blend_mode,
-                                shape_pad=self.plan.shape_pad, overlap=self.plan.overlap, gz0=z0)
+        if self.loading is None:
+            active = self.ctx.windows_active(self.slab, local, self.plan.roi)
+            self._run(self._schedule(local[active != 0]))
+            return active
+        # the slab is still being uploaded (file read -> pinned staging -> device on a second stream): windows run as
+        # soon as the chunk that holds their last plane has landed, whole batches at a time, the upload of the next
+        # chunk overlapping them.  The blend is an integer sum: any order gives the same accumulator.
+        active = np.zeros(len(local), dtype=np.int32)
+        done, pending = 0, np.zeros((0, 3), dtype=np.int32)
+        batch = max(1, self.window_batch or 128)
+        rz = self.plan.roi[0]
+        for z_end, last in self.loading.chunks():
+            self.loading.wait(self.stream)                            # planes [0, z_end) of the slab are on the device
+            n = done
+            while n < len(local) and local[n, 0] + rz <= z_end:      # windows are z-major: eligible ones are a prefix
+                n += 1
+            if n > done:
+                active[done:n] = self.ctx.windows_active(self.slab, local[done:n], self.plan.roi)
+                pending = np.concatenate([pending, local[done:n][active[done:n] != 0]])
+                done = n
+            run = len(pending) if last else len(pending) // batch * batch
+            if run:
+                self._run(self._schedule(pending[:run]))
+                pending = pending[run:]
+        assert done == len(local) and len(pending) == 0
+        self.loading = None
         return active
 
     def acc_planes(self, g0, g1):

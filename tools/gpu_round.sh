@@ -17,4 +17,5 @@ K='regex:conv_tc|conv_is|is_reduce|norm_mish|final_blend|gather_windows|window_a
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" --launch-skip 60 -c 120 --csv --log-file gpurun_out/launches_cfg2_${tag}.csv python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_list_cfg2_${tag}.log 2>&1; echo "ncu list exit $?"
 timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:conv_ --launch-skip 22 -c 22 --csv --log-file gpurun_out/conv_traffic_${tag}.csv python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_traffic_${tag}.log 2>&1; echo "ncu traffic exit $?"
 timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k 'regex:ccl_|scan_|bbox_|paint_' -c 14 --csv --log-file gpurun_out/ccl_traffic_${tag}.csv python bench.py --workload cfg3 --steps 1 --warmup 0 > gpurun_out/ncu_ccl_${tag}.log 2>&1; echo "ncu ccl exit $?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_is --launch-skip 8 -c 4 -o gpurun_out/prof_is_${tag} python bench.py --workload small --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_is_${tag}.log 2>&1; echo "ncu is exit $?"
+# one ncu --set full capture of the dominant kernel on the HEADLINE workload (cfg2): the 8 conv_is launches of the second batch
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:conv_is --launch-skip 8 -c 8 -o gpurun_out/prof_is_${tag} python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_is_${tag}.log 2>&1; echo "ncu is exit $?"
