@@ -56,6 +56,7 @@ int dlv_init(int device, dlv_ctx** out) {
     ctx->num_sms = prop.multiProcessorCount;
     if (const char* e = getenv("DLV_FUSED")) ctx->use_fused = atoi(e) != 0;
     if (const char* e = getenv("DLV_IS_T")) ctx->is_tiles = atoi(e);
+    if (const char* e = getenv("DLV_IS_TX")) ctx->is_tiles_xf = atoi(e);
     DLV_CUDA_OK(ctx, cudaSetDevice(device));
     DLV_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     DLV_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));

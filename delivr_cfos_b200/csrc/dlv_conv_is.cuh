@@ -41,13 +41,17 @@ constexpr int kIsWarpMma = kIsXformWarps + 5;           // sub-partition 1
 #else
 constexpr int kIsWarpProducer = 0, kIsWarpMma = 1, kIsWarpEpi0 = 2, kIsWarpXform0 = 6;
 #endif
-constexpr int kIsMaxStages = 4;
+constexpr int kIsMaxStages = 8;      // barrier slots; plain / fused layers use at most 4, the uint16 first layer up to 8
 #ifndef DLV_IS_NEWTON_PAIRS
 #define DLV_IS_NEWTON_PAIRS 0
 #endif
 #ifndef DLV_IS_COLLECTOR
 #define DLV_IS_COLLECTOR 1      // measured on cfg2: 0.478 -> 0.490 Gvoxels/s (profiles/r02_a_variants.txt)
 #endif
+#ifndef DLV_IS_XF_EXP
+#define DLV_IS_XF_EXP 0         // timing experiments on the transform role (results invalid): 1 = copy only (shared-memory
+#endif                          // traffic without arithmetic), 2 = arithmetic only (no shared-memory loads / stores)
+constexpr int kIsXfExp = DLV_IS_XF_EXP;
 constexpr bool kIsCollector = DLV_IS_COLLECTOR != 0;   // A-operand collector re-use on ring-wrap MMA pairs
 constexpr int kIsNewtonPairs = DLV_IS_NEWTON_PAIRS;   // channel pairs (of 4 per 16 B) whose reciprocal runs on the FMA pipe
 
@@ -109,6 +113,21 @@ __device__ __forceinline__ uint4 ld_shared_u4(uint32_t addr) {
 }
 __device__ __forceinline__ void st_shared_u4(uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// transform-role experiment hooks (identity in production builds)
+__device__ __forceinline__ uint4 xf_load(uint32_t addr) {
+    if (kIsXfExp == 2) return make_uint4(addr, addr * 3u, addr ^ 0x3c003c00u, 0x3c003c00u);
+    return ld_shared_u4(addr);
+}
+template <int NRP>
+__device__ __forceinline__ uint4 xf_math(const uint4 u, const f32x2 (&a)[4], const f32x2 (&b)[4]) {
+    if (kIsXfExp == 1) return u;
+    return norm_mish8<NRP>(u, a, b);
+}
+__device__ __forceinline__ void xf_store(uint32_t addr, const uint4& v) {
+    if (kIsXfExp == 2) { if (v.x == 0x12345678u && v.w == 0x9abcdef0u) st_shared_u4(addr, v); return; }
+    st_shared_u4(addr, v);
 }
 
 // FOLD: the uint16 first layer.  Its K = 16 slot holds the 3 kx neighbours x 4 split terms of the single input channel,
@@ -425,22 +444,23 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
     } else if (FOLD) {
         // ------------------------------------------------------------ first layer: operand slot from the raw uint16 window.
         // Replaces the window gather of sliding_window_inferer.py:181-195,207 (and its flips, :218-219).  Step k of the
-        // CTA (the same (item, plane) enumeration as the MMA warp's) is built by transform warp k mod kIsXformWarps:
-        // every warp has kIsXformWarps steps of time for its plane, so the global-load latency needs no software
-        // pipeline.  A uint16 v is split as v = hi + lo (hi = v & 0xFF00, lo = v & 0xFF: both exact in bf16) and paired
+        // CTA (the same (item, plane) enumeration as the MMA warp's) is built by transform warp k mod nstages
+        // (nstages <= kIsXformWarps): warp w owns stage w, so its consecutive uses of that stage are consecutive
+        // phases of the stage's barriers (a parity wait cannot tell phases two apart), and every warp has nstages
+        // steps of time for its plane, so the global-load latency needs no software pipeline.  A uint16 v is split as v = hi + lo (hi = v & 0xFF00, lo = v & 0xFF: both exact in bf16) and paired
         // with the weights' {Wh, Wh, Wl, Wl} (W = Wh + Wl), which reproduces the fp32 product v * W to ~2^-16 relative.
         const int tw = warp - kIsWarpXform0;
         const int ngroups = (p.RL + 31) / 32;
         int step = 0;
-        for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+        for (int item = blockIdx.x; tw < p.nstages && item < p.nitems; item += gridDim.x) {
             int win, c, za, zb;
             item_geom(item, win, c, za, zb);
             const int zi0 = max(za - 1, 1), zi1 = min(zb + 1, p.Z);
             const int4 wd = p.raw_wd[win];
             const int flip = wd.w & 0xFF;
             for (int zi = zi0; zi <= zi1; ++zi, ++step) {
-                if (step % kIsXformWarps != tw) continue;
-                const int stage = step % p.nstages;
+                if (step % p.nstages != tw) continue;
+                const int stage = tw;
                 const uint32_t phase = static_cast<uint32_t>(step / p.nstages) & 1u;
                 const int z = zi - 1, zs = (flip == 1) ? p.Z - 1 - z : z;
                 const uint16_t* plane = p.raw_slab + (static_cast<int64_t>(wd.x + zs) * p.raw_sy + wd.y) * p.raw_sx + wd.z;
@@ -533,28 +553,28 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
                 // load latency was the largest single stall of this role)
                 int k = (p.dbg_mode & 4) ? nmine : 0;
                 uint4 n0 = make_uint4(0u, 0u, 0u, 0u), n1 = n0;
-                if (k < nmine && ((okbits >> k) & 1u)) n0 = ld_shared_u4(base + static_cast<uint32_t>(sub + NW * k) * 512u);
-                if (k + 1 < nmine && ((okbits >> (k + 1)) & 1u)) n1 = ld_shared_u4(base + static_cast<uint32_t>(sub + NW * (k + 1)) * 512u);
+                if (k < nmine && ((okbits >> k) & 1u)) n0 = xf_load(base + static_cast<uint32_t>(sub + NW * k) * 512u);
+                if (k + 1 < nmine && ((okbits >> (k + 1)) & 1u)) n1 = xf_load(base + static_cast<uint32_t>(sub + NW * (k + 1)) * 512u);
 #pragma unroll 1
                 for (; k + 1 < nmine; k += 2) {
                     const uint32_t ad0 = base + static_cast<uint32_t>(sub + NW * k) * 512u;
                     const uint32_t ad1 = ad0 + NW * 512u;
                     const bool ok1 = (okbits >> (k + 1)) & 1u;        // only the last group can be partial
                     const uint4 u0 = n0, u1 = n1;
-                    if ((okbits >> (k + 2)) & 1u) n0 = ld_shared_u4(ad0 + 2 * NW * 512u);      // okbits is 0 beyond nmine
-                    if ((okbits >> (k + 3)) & 1u) n1 = ld_shared_u4(ad1 + 2 * NW * 512u);
-                    uint4 o0 = norm_mish8<kIsNewtonPairs>(u0, a, b), o1 = norm_mish8<kIsNewtonPairs>(u1, a, b);
+                    if ((okbits >> (k + 2)) & 1u) n0 = xf_load(ad0 + 2 * NW * 512u);      // okbits is 0 beyond nmine
+                    if ((okbits >> (k + 3)) & 1u) n1 = xf_load(ad1 + 2 * NW * 512u);
+                    uint4 o0 = xf_math<kIsNewtonPairs>(u0, a, b), o1 = xf_math<kIsNewtonPairs>(u1, a, b);
                     const bool in0 = (inbits >> k) & 1u, in1 = (inbits >> (k + 1)) & 1u;
                     if (!in0) o0 = make_uint4(0u, 0u, 0u, 0u);          // halo positions stay exactly zero
                     if (!in1) o1 = make_uint4(0u, 0u, 0u, 0u);
-                    st_shared_u4(ad0, o0);
-                    if (ok1) st_shared_u4(ad1, o1);
+                    xf_store(ad0, o0);
+                    if (ok1) xf_store(ad1, o1);
                 }
                 if (k < nmine && ((okbits >> k) & 1u)) {
                     const uint32_t ad0 = base + static_cast<uint32_t>(sub + NW * k) * 512u;
-                    uint4 o0 = norm_mish8<kIsNewtonPairs>(n0, a, b);
+                    uint4 o0 = xf_math<kIsNewtonPairs>(n0, a, b);
                     if (!((inbits >> k) & 1u)) o0 = make_uint4(0u, 0u, 0u, 0u);
-                    st_shared_u4(ad0, o0);
+                    xf_store(ad0, o0);
                 }
                 fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core's async proxy
                 __syncwarp();

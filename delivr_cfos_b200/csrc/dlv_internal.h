@@ -74,6 +74,7 @@ struct Ctx {
     int64_t ccl_launches = 0;
     bool use_fused = true;      // Cout = 32 layers on the input-stationary fused kernel (DLV_FUSED=0 selects the per-tap kernel)
     int is_tiles = 0;           // 0 = heuristic; 2 / 4 force the tile count per column (DLV_IS_T)
+    int is_tiles_xf = 0;        // same for the 32 -> 32 layers that normalise while staging (DLV_IS_TX)
     uint32_t* paint_owner = nullptr;   // painter scratch (dlv_paint.cu), all-zero between calls when paint_owner_clean
     size_t paint_owner_cap = 0;        // voxels
     bool paint_owner_clean = false;

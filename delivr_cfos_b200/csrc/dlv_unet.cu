@@ -545,8 +545,10 @@ struct IsPlan {
     uint32_t stage_bytes, w_bytes, smem;
 };
 
-static bool plan_conv_is(const Ctx* ctx, const ConvLayer& Ly, const Level& L, int nwin, IsPlan& P) {
+static bool plan_conv_is(const Ctx* ctx, const ConvLayer& Ly, const Level& L, int nwin, IsPlan& P, bool xform = false) {
     if (Ly.cout != 32 || Ly.ntaps != 27 || !Ly.w_is) return false;
+    // tile-count override: DLV_IS_T for every layer, DLV_IS_TX for the layers that normalise while staging (32 -> 32)
+    const int force_t = (xform && Ly.KB == 2 && ctx->is_tiles_xf) ? ctx->is_tiles_xf : ctx->is_tiles;
     const int PL = L.YpXp;
     P.H = L.Xp + 1;
     P.w_bytes = static_cast<uint32_t>(Ly.KB) * (Ly.cin == 1 ? 3 : 9) * 3072;
@@ -556,7 +558,8 @@ static bool plan_conv_is(const Ctx* ctx, const ConvLayer& Ly, const Level& L, in
         sb = static_cast<uint32_t>(nchunks) * RL * 16;
         const uint32_t fixed = P.w_bytes + 512 * 8 + 512;      // weights + statistics combine buffer + barriers
         nst = 0;
-        for (int n = kIsMaxStages; n >= 2; --n)
+        // plain / fused layers: up to 4 stages; the uint16 first layer: one stage per building warp, up to 8
+        for (int n = (Ly.cin == 1 ? std::min(kIsMaxStages, kIsXformWarps) : 4); n >= 2; --n)
             if (fixed + static_cast<uint64_t>(n) * sb <= kSmemLimit) { nst = n; break; }
         return nst >= 2 && RL <= 1024;      // 32 mask words per transform warp
     };
@@ -564,7 +567,7 @@ static bool plan_conv_is(const Ctx* ctx, const ConvLayer& Ly, const Level& L, in
     // times the column quantisation of the plane
     int bestT = 0; double best = 1e30;
     for (int T : {4, 2}) {
-        if (ctx->is_tiles && ctx->is_tiles != T) continue;
+        if (force_t && force_t != T) continue;
         int nst, RL; uint32_t sb;
         if (!fits(T, nst, RL, sb)) continue;
         const int S = 16 / T, R = 128 * T;
@@ -575,11 +578,17 @@ static bool plan_conv_is(const Ctx* ctx, const ConvLayer& Ly, const Level& L, in
     }
     // wide windows (a row halo of 2 (X + 2) positions per column): one tile per column, 16 plane slots - the stages
     // of the two-tile column no longer fit next to the weights (X > ~100 for the 64 -> 32 layers)
-    if (!bestT && (!ctx->is_tiles || ctx->is_tiles == 1)) {
-        int nst, RL; uint32_t sb;
-        if (fits(1, nst, RL, sb)) bestT = 1;
+    if (!bestT && force_t > 1) {          // the forced tile count does not fit this layer: fall back to the model's choice
+        for (int T : {4, 2}) {
+            int nst, RL; uint32_t sb;
+            if (!fits(T, nst, RL, sb)) continue;
+            const int S = 16 / T, R = 128 * T;
+            const int NC = (PL + R - 1) / R;
+            const double cost = 9.0 * ((S - 2) * 56.0 + 2 * 88.0) / S * (static_cast<double>(NC) * R / PL);
+            if (cost < best) { best = cost; bestT = T; }
+        }
     }
-    if (ctx->is_tiles == 1) { int nst, RL; uint32_t sb; if (fits(1, nst, RL, sb)) bestT = 1; }
+    if (!bestT || force_t == 1) { int nst, RL; uint32_t sb; if (fits(1, nst, RL, sb)) bestT = 1; }
     if (!bestT) return false;
     P.T = bestT; P.S = 16 / bestT;
     fits(P.T, P.nstages, P.RL, P.stage_bytes);
@@ -631,7 +640,7 @@ static int run_conv_is(Ctx* ctx, const ConvLayer& Ly, const Level& L, int nwin, 
                        const ConvLayer* prod, const double* prod_stats, bf16* out, double* part, double* stats,
                        const RawWindows* raw = nullptr) {
     IsPlan P;
-    if (!plan_conv_is(ctx, Ly, L, nwin, P) || P.nparts > is_max_parts(L)) {
+    if (!plan_conv_is(ctx, Ly, L, nwin, P, prod != nullptr) || P.nparts > is_max_parts(L)) {
         set_error(ctx, "conv %s: level %dx%dx%d does not fit the input-stationary kernel", Ly.name.c_str(), L.Z, L.Y, L.X);
         return DLV_ERR_UNSUPPORTED;
     }
