@@ -57,6 +57,7 @@ int dlv_init(int device, dlv_ctx** out) {
     if (const char* e = getenv("DLV_FUSED")) ctx->use_fused = atoi(e) != 0;
     if (const char* e = getenv("DLV_IS_T")) ctx->is_tiles = atoi(e);
     if (const char* e = getenv("DLV_IS_TX")) ctx->is_tiles_xf = atoi(e);
+    if (const char* e = getenv("DLV_IS_NSUB")) ctx->is_nsub = atoi(e);
     DLV_CUDA_OK(ctx, cudaSetDevice(device));
     DLV_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     DLV_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -79,6 +80,7 @@ void dlv_destroy(dlv_ctx* c) {
     dlv::engine_free(ctx);
     dlv::net_free(ctx);
     if (ctx->paint_owner) cudaFree(ctx->paint_owner);
+    for (void* p : ctx->scratch) if (p) cudaFree(p);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);

@@ -74,6 +74,8 @@ struct IsArgs {
     int nparts;
     int Z, Y, X, Xp, PL, Vp;
     int KB, NC, NZS, Zs, nitems, RL, H, nstages;
+    int nsub;                   // sub-steps per input plane: the plane's 2 * KB chunks are staged (and multiplied) in nsub
+                                // groups of 2 * KB / nsub chunks, each group one pipeline stage (64 -> 32 layers: 2)
     int G;                      // planes per statistics group (Zs is a multiple of G)
     uint32_t stage_bytes, w_bytes;
     double inv_count;           // 1 / (Z*Y*X)
@@ -191,25 +193,28 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
             // every input chunk of the step arrives by TMA; chunks that hold RAW conv output are normalised in place
             // by the transform warps before the MMA warp sees the stage
             uint64_t* const bars_in = p.xform_chunks > 0 ? rawfull : full;
+            const int cps = p.nchunks / p.nsub;                  // chunks per sub-step
             int stage = 0; uint32_t phase = 0;
             for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
                 int win, c, za, zb;
                 item_geom(item, win, c, za, zb);
                 const int zi0 = max(za - 1, 1), zi1 = min(zb + 1, p.Z);
                 for (int zi = zi0; zi <= zi1; ++zi) {
-                    mbar_wait(&empty[stage], phase ^ 1);
-                    if (lane == 0) mbar_arrive_expect_tx(&bars_in[stage], static_cast<uint32_t>(p.nchunks) * p.RL * 16);
-                    __syncwarp();
                     const int64_t pos = static_cast<int64_t>(p.in_guard) + static_cast<int64_t>(win) * p.Vp +
                                         static_cast<int64_t>(zi) * p.PL + c * R - p.H;
-                    if (lane < p.nchunks) {
-                        const int chunk = lane;
-                        const __nv_bfloat16* base = (chunk < p.nch0) ? p.in0 + static_cast<int64_t>(chunk) * p.inS * 8
-                                                                     : p.in1 + static_cast<int64_t>(chunk - p.nch0) * p.inS * 8;
-                        tma_bulk_g2s(stages + static_cast<size_t>(stage) * p.stage_bytes + static_cast<size_t>(chunk) * p.RL * 16,
-                                     base + pos * 8, p.RL * 16, &bars_in[stage]);
+                    for (int sub = 0; sub < p.nsub; ++sub) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        if (lane == 0) mbar_arrive_expect_tx(&bars_in[stage], static_cast<uint32_t>(cps) * p.RL * 16);
+                        __syncwarp();
+                        if (lane < cps) {
+                            const int chunk = sub * cps + lane;
+                            const __nv_bfloat16* base = (chunk < p.nch0) ? p.in0 + static_cast<int64_t>(chunk) * p.inS * 8
+                                                                         : p.in1 + static_cast<int64_t>(chunk - p.nch0) * p.inS * 8;
+                            tma_bulk_g2s(stages + static_cast<size_t>(stage) * p.stage_bytes + static_cast<size_t>(lane) * p.RL * 16,
+                                         base + pos * 8, p.RL * 16, &bars_in[stage]);
+                        }
+                        if (++stage == p.nstages) { stage = 0; phase ^= 1; }
                     }
-                    if (++stage == p.nstages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -219,7 +224,7 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
         // thread spends outside the MMA stream is a bubble.  The loop is therefore software-pipelined: the next
         // step's parameters are computed and its barriers probed (non-blocking) in the middle of the current burst.
         if (elect_one_sync()) {
-            long long c_wait = 0, c_steps = 0;
+            long long c_wait = 0, c_wait_slot = 0, c_steps = 0;
             const long long c_begin = clock64();
             mbar_wait(wfull, 0);
             const uint32_t dhi = (128u >> 4) | (1u << 14);      // constant upper descriptor word (SBO 128 B, version 1)
@@ -233,8 +238,10 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
                 uint32_t par0, par1, full_par;
             };
             // iterator over (item, input plane)
-            int item = blockIdx.x, win = 0, c = 0, za = 0, zb = 0, zi0 = 0, zi1 = 0, zi = 0;
+            int item = blockIdx.x, win = 0, c = 0, za = 0, zb = 0, zi0 = 0, zi1 = 0, zi = 0, sub = 0;
             int stage = 0; uint32_t phase = 0, slot_par = 0;
+            const int kbs = p.KB / p.nsub;                               // k-blocks per sub-step
+            const uint32_t b_sub = static_cast<uint32_t>(kbs) * 9u * 192u;   // weight block of one sub-step in 16 B units (nsub > 1: never the first layer)
             bool have = item < p.nitems;
             if (have) { item_geom(item, win, c, za, zb); zi0 = max(za - 1, 1); zi1 = min(zb + 1, p.Z); zi = zi0; }
             auto make_step = [&](Step& st) {
@@ -244,7 +251,7 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
                 const int n0 = min(cnt, S - (lo & (S - 1)));
                 st.n1 = cnt - n0;
                 st.a_lo0 = a_stage0 + static_cast<uint32_t>(stage) * a_stage_step;
-                st.b_lo0 = b_base + static_cast<uint32_t>((lo - (zi - 1)) * 32);
+                st.b_lo0 = b_base + static_cast<uint32_t>((lo - (zi - 1)) * 32) + static_cast<uint32_t>(sub) * b_sub;
                 st.b_lo1 = st.b_lo0 + static_cast<uint32_t>(n0 * 32);
                 st.c0 = tmem_base + (lo & (S - 1)) * 32;
                 st.i0 = umma_idesc_bf16_m128(32) + (static_cast<uint32_t>((n0 - 1) * 4) << 17);
@@ -252,30 +259,38 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
                 st.stage = stage;
                 st.full_par = phase;
                 st.acq0 = st.acq1 = -1; st.par0 = st.par1 = 0;
-                if (new_lo <= hi) { st.acq0 = new_lo & (S - 1); st.par0 = (slot_par >> st.acq0) & 1u; slot_par ^= 1u << st.acq0; }
-                if (new_lo + 1 <= hi) { st.acq1 = (new_lo + 1) & (S - 1); st.par1 = (slot_par >> st.acq1) & 1u; slot_par ^= 1u << st.acq1; }
+                // accumulator slots are acquired by the plane's first sub-step and handed over by its last
+                if (sub == 0 && new_lo <= hi) { st.acq0 = new_lo & (S - 1); st.par0 = (slot_par >> st.acq0) & 1u; slot_par ^= 1u << st.acq0; }
+                if (sub == 0 && new_lo + 1 <= hi) { st.acq1 = (new_lo + 1) & (S - 1); st.par1 = (slot_par >> st.acq1) & 1u; slot_par ^= 1u << st.acq1; }
                 // output planes whose last contributing input plane is this one
-                st.done0 = (zi - 1 >= lo) ? ((zi - 1) & (S - 1)) : -1;
-                st.done1 = (zi == zi1 && zi <= zb) ? (zi & (S - 1)) : -1;
+                const bool last_sub = sub == p.nsub - 1;
+                st.done0 = (last_sub && zi - 1 >= lo) ? ((zi - 1) & (S - 1)) : -1;
+                st.done1 = (last_sub && zi == zi1 && zi <= zb) ? (zi & (S - 1)) : -1;
                 // advance the iterator
                 if (++stage == p.nstages) { stage = 0; phase ^= 1; }
-                if (zi < zi1) {
-                    ++zi;
+                if (!last_sub) {
+                    ++sub;
                 } else {
-                    item += gridDim.x;
-                    have = item < p.nitems;
-                    if (have) { item_geom(item, win, c, za, zb); zi0 = max(za - 1, 1); zi1 = min(zb + 1, p.Z); zi = zi0; }
+                    sub = 0;
+                    if (zi < zi1) {
+                        ++zi;
+                    } else {
+                        item += gridDim.x;
+                        have = item < p.nitems;
+                        if (have) { item_geom(item, win, c, za, zb); zi0 = max(za - 1, 1); zi1 = min(zb + 1, p.Z); zi = zi0; }
+                    }
                 }
             };
             auto wait_step = [&](const Step& st, bool ok_full, bool ok0, bool ok1) {
                 const long long w0 = p.dbg ? clock64() : 0;
                 if (!ok0 && st.acq0 >= 0) mbar_wait(&tempty[st.acq0], st.par0);
                 if (!ok1 && st.acq1 >= 0) mbar_wait(&tempty[st.acq1], st.par1);
+                const long long w1 = p.dbg ? clock64() : 0;
                 if (!ok_full) mbar_wait(&full[st.stage], st.full_par);
                 tc_fence_after();
-                if (p.dbg) c_wait += clock64() - w0;
+                if (p.dbg) { c_wait += clock64() - w0; c_wait_slot += w1 - w0; }
             };
-            const int nrows = 3 * p.KB;                                  // (kb, ky) rows of 3 taps
+            const int nrows = 3 * kbs;                                   // (kb, ky) rows of 3 taps of one sub-step
             const uint32_t xp = static_cast<uint32_t>(p.Xp);
             const uint32_t a_kb_adj = static_cast<uint32_t>(2 * p.RL) - 3u * xp;   // row 2 of kb -> row 0 of kb + 1
             const uint32_t a_tap0 = static_cast<uint32_t>(p.H - p.Xp - (FOLD ? 0 : 1));
@@ -328,7 +343,7 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
             }
             if (p.dbg) {
                 long long* d = p.dbg + blockIdx.x * 8;
-                d[0] = clock64() - c_begin; d[1] = c_wait; d[2] = 0; d[3] = 0; d[4] = c_steps;
+                d[0] = clock64() - c_begin; d[1] = c_wait; d[2] = c_wait_slot; d[3] = c_wait - c_wait_slot; d[4] = c_steps;
             }
         }
         __syncwarp();
@@ -447,8 +462,9 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
         // CTA (the same (item, plane) enumeration as the MMA warp's) is built by transform warp k mod nstages
         // (nstages <= kIsXformWarps): warp w owns stage w, so its consecutive uses of that stage are consecutive
         // phases of the stage's barriers (a parity wait cannot tell phases two apart), and every warp has nstages
-        // steps of time for its plane, so the global-load latency needs no software pipeline.  A uint16 v is split as v = hi + lo (hi = v & 0xFF00, lo = v & 0xFF: both exact in bf16) and paired
-        // with the weights' {Wh, Wh, Wl, Wl} (W = Wh + Wl), which reproduces the fp32 product v * W to ~2^-16 relative.
+        // steps of time for its plane.  A uint16 v is split as v = hi + lo (hi = v & 0xFF00, lo = v & 0xFF: both exact in
+        // bf16) and paired with the weights' {Wh, Wh, Wl, Wl} (W = Wh + Wl), which reproduces the fp32 product v * W to
+        // ~2^-16 relative.
         const int tw = warp - kIsWarpXform0;
         const int ngroups = (p.RL + 31) / 32;
         int step = 0;
@@ -464,30 +480,44 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
                 const uint32_t phase = static_cast<uint32_t>(step / p.nstages) & 1u;
                 const int z = zi - 1, zs = (flip == 1) ? p.Z - 1 - z : z;
                 const uint16_t* plane = p.raw_slab + (static_cast<int64_t>(wd.x + zs) * p.raw_sy + wd.y) * p.raw_sx + wd.z;
+                // value of in-plane position c * R - H + i of this (flipped) window plane; 0 in the halo and outside the plane.
+                // The kx neighbours of a position are the positions before and after it (a row ends in a halo column),
+                // so every lane loads ONE voxel and takes its neighbours from the adjacent lanes.
+                auto ld_pos = [&](int i) -> uint32_t {
+                    const int qq = c * R - p.H + i;
+                    if (qq < 0 || qq >= p.PL) return 0u;
+                    const int yp = qq / p.Xp, xp = qq - yp * p.Xp;
+                    if (yp < 1 || yp > p.Y || xp < 1) return 0u;
+                    const int y = yp - 1, x = xp - 1;
+                    return __ldg(plane + static_cast<int64_t>((flip == 2) ? p.Y - 1 - y : y) * p.raw_sx + ((flip == 3) ? p.X - 1 - x : x));
+                };
+                constexpr int GB = 8;               // groups of 32 positions per batch: GB + 1 independent loads in flight per lane
+                uint32_t prev = (lane == 31) ? ld_pos(-1) : 0u;     // "group -1": only its lane 31 (position -1) is ever read
                 mbar_wait(&empty[stage], phase ^ 1);
                 const uint32_t base = smem_u32(stages + static_cast<size_t>(stage) * p.stage_bytes) + static_cast<uint32_t>(lane) * 16u;
-#pragma unroll 4
-                for (int g = 0; g < ngroups; ++g) {
-                    const int i = g * 32 + lane;
-                    const int qq = c * R - p.H + i;
-                    uint32_t vm = 0u, v0 = 0u, vp = 0u;
-                    if (i < p.RL && qq >= 0 && qq < p.PL) {
-                        const int yp = qq / p.Xp, xp = qq - yp * p.Xp;
-                        if (yp >= 1 && yp <= p.Y && xp >= 1) {
-                            const int y = yp - 1, x = xp - 1;
-                            const uint16_t* row = plane + static_cast<int64_t>((flip == 2) ? p.Y - 1 - y : y) * p.raw_sx;
-                            const bool fx = flip == 3;
-                            v0 = __ldg(row + (fx ? p.X - 1 - x : x));
-                            if (x > 0) vm = __ldg(row + (fx ? p.X - x : x - 1));
-                            if (x + 1 < p.X) vp = __ldg(row + (fx ? p.X - 2 - x : x + 1));
+                for (int g0 = 0; g0 < ngroups; g0 += GB) {
+                    uint32_t v[GB + 1];
+#pragma unroll
+                    for (int j = 0; j <= GB; ++j)       // group j of the batch; of the group after the last one only lane 0 is read
+                        v[j] = (j < GB && g0 + j < ngroups) || (lane == 0 && g0 + j <= ngroups) ? ld_pos((g0 + j) * 32 + lane) : 0u;
+#pragma unroll
+                    for (int j = 0; j < GB; ++j) {
+                        if (g0 + j < ngroups) {         // warp-uniform
+                            const uint32_t before = __shfl_sync(0xffffffffu, prev, 31), after = __shfl_sync(0xffffffffu, v[j + 1], 0);
+                            uint32_t vm = __shfl_up_sync(0xffffffffu, v[j], 1), vp = __shfl_down_sync(0xffffffffu, v[j], 1);
+                            if (lane == 0) vm = before;
+                            if (lane == 31) vp = after;
+                            const uint32_t v0 = v[j];
+                            prev = v0;
+                            const int g = g0 + j;
+                            if (g * 32 + lane < p.RL) {
+                                const uint32_t tm = pack_bf16x2(static_cast<float>(vm & 0xFF00u), static_cast<float>(vm & 0xFFu));
+                                const uint32_t t0 = pack_bf16x2(static_cast<float>(v0 & 0xFF00u), static_cast<float>(v0 & 0xFFu));
+                                const uint32_t tp = pack_bf16x2(static_cast<float>(vp & 0xFF00u), static_cast<float>(vp & 0xFFu));
+                                st_shared_u4(base + static_cast<uint32_t>(g) * 512u, make_uint4(tm, tm, t0, t0));
+                                st_shared_u4(base + static_cast<uint32_t>(p.RL) * 16u + static_cast<uint32_t>(g) * 512u, make_uint4(tp, tp, 0u, 0u));
+                            }
                         }
-                    }
-                    if (i < p.RL) {
-                        const uint32_t tm = pack_bf16x2(static_cast<float>(vm & 0xFF00u), static_cast<float>(vm & 0xFFu));
-                        const uint32_t t0 = pack_bf16x2(static_cast<float>(v0 & 0xFF00u), static_cast<float>(v0 & 0xFFu));
-                        const uint32_t tp = pack_bf16x2(static_cast<float>(vp & 0xFF00u), static_cast<float>(vp & 0xFFu));
-                        st_shared_u4(base + static_cast<uint32_t>(g) * 512u, make_uint4(tm, tm, t0, t0));
-                        st_shared_u4(base + static_cast<uint32_t>(p.RL) * 16u + static_cast<uint32_t>(g) * 512u, make_uint4(tp, tp, 0u, 0u));
                     }
                 }
                 fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core's async proxy
@@ -505,6 +535,7 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
         const int chunk = tw & 3, sub = tw >> 2;
         const int ngroups = (p.RL + 31) / 32;                    // 32-position groups of the run
         const int nmine = (ngroups - sub + NW - 1) / NW;         // groups sub, sub + NW, ... handled by this warp
+        const int cps = p.nchunks / p.nsub;                      // chunks per stage (4: one per group of NW warps)
         const uint32_t chunk_off = static_cast<uint32_t>(chunk) * p.RL * 16 + static_cast<uint32_t>(lane) * 16;
         int stage = 0; uint32_t phase = 0;
         long long x_wait = 0, x_work = 0;
@@ -543,15 +574,18 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
                     b[i] = pk2(__shfl_sync(0xffffffffu, mb, 2 * i), __shfl_sync(0xffffffffu, mb, 2 * i + 1));
                 }
             }
-            for (int zi = zi0; zi <= zi1; ++zi) {
+            for (int zs = (zi1 - zi0 + 1) * p.nsub, ss = 0; zs > 0; --zs, ss = (ss + 1 == p.nsub) ? 0 : ss + 1) {
                 const long long x0 = p.dbg ? clock64() : 0;
                 mbar_wait(&rawfull[stage], phase);
                 const long long x1 = p.dbg ? clock64() : 0;
+                // sub-steps whose chunks are already activations (the up-sampled half of a concatenation) only pass the
+                // stage on: full[] counts one arrival per transform warp whatever the stage holds
+                const bool raw_stage = ss * cps < p.xform_chunks;
                 const uint32_t base = smem_u32(stages + static_cast<size_t>(stage) * p.stage_bytes) + chunk_off;
                 // two groups (16 elements per lane) per iteration: enough independent MUFU chains to keep the pipe busy;
                 // the NEXT iteration's raw values are loaded before this iteration's arithmetic (the shared-memory
                 // load latency was the largest single stall of this role)
-                int k = (p.dbg_mode & 4) ? nmine : 0;
+                int k = ((p.dbg_mode & 4) || !raw_stage) ? nmine : 0;
                 uint4 n0 = make_uint4(0u, 0u, 0u, 0u), n1 = n0;
                 if (k < nmine && ((okbits >> k) & 1u)) n0 = xf_load(base + static_cast<uint32_t>(sub + NW * k) * 512u);
                 if (k + 1 < nmine && ((okbits >> (k + 1)) & 1u)) n1 = xf_load(base + static_cast<uint32_t>(sub + NW * (k + 1)) * 512u);

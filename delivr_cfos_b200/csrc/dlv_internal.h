@@ -74,7 +74,16 @@ struct Ctx {
     int64_t ccl_launches = 0;
     bool use_fused = true;      // Cout = 32 layers on the input-stationary fused kernel (DLV_FUSED=0 selects the per-tap kernel)
     int is_tiles = 0;           // 0 = heuristic; 2 / 4 force the tile count per column (DLV_IS_T)
-    int is_tiles_xf = 0;        // same for the 32 -> 32 layers that normalise while staging (DLV_IS_TX)
+    int is_nsub = 1;            // 64 -> 32 layers: planes staged whole (1) or in two half-plane stages (2, DLV_IS_NSUB)
+    int is_tiles_xf = 4;        // same for the 32 -> 32 layers that normalise while staging (DLV_IS_TX): four-tile columns
+                                // re-transform less halo (RL / R = 1.26 instead of 1.53 at X = 64), which is what bounds them;
+                                // measured on cfg2: 3 316 -> 2 747 clk per 256 positions, 0.482 -> 0.492 Gvoxels/s
+    // Grow-only buffers for the per-call gigabyte temporaries of dlv_segment / the finalise stage (blend sums, erosion
+    // distances, the uploaded volume, device-side binaries).  They used to come from the stream-ordered pool on every
+    // call; when small allocations split a cached block the pool grew again mid-step (observed: +0.2-0.4 s in the
+    // finalise stage of every step on one box).  Freed by dlv_destroy, or all at once when one of them cannot grow.
+    void* scratch[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_cap[4] = {0, 0, 0, 0};
     uint32_t* paint_owner = nullptr;   // painter scratch (dlv_paint.cu), all-zero between calls when paint_owner_clean
     size_t paint_owner_cap = 0;        // voxels
     bool paint_owner_clean = false;
@@ -87,6 +96,26 @@ void set_error(Ctx* ctx, const char* fmt, ...);
 inline cudaError_t dmalloc(Ctx* ctx, void** p, size_t bytes) { return cudaMallocAsync(p, bytes ? bytes : 1, ctx->stream); }
 template <class T> inline cudaError_t dmalloc(Ctx* ctx, T** p, size_t bytes) { return dmalloc(ctx, reinterpret_cast<void**>(p), bytes); }
 inline void dfree(Ctx* ctx, void* p) { if (p) cudaFreeAsync(p, ctx->stream); }
+
+enum { kScratchAcc = 0, kScratchDist = 1, kScratchSlab = 2, kScratchBin = 3 };
+// -> device pointer of at least `bytes` (contents undefined), valid until the next request for the same slot.  The
+// caller orders its use on ctx->stream; growing synchronises the device (cudaFree / cudaMalloc).
+inline cudaError_t scratch_get(Ctx* ctx, int slot, size_t bytes, void** out) {
+    if (ctx->scratch_cap[slot] < bytes) {
+        if (ctx->scratch[slot]) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->scratch[slot]); ctx->scratch[slot] = nullptr; ctx->scratch_cap[slot] = 0; }
+        cudaError_t e = cudaMalloc(&ctx->scratch[slot], bytes);
+        if (e != cudaSuccess) {            // make room: drop the other slots and try once more
+            cudaGetLastError();
+            cudaStreamSynchronize(ctx->stream);
+            for (int i = 0; i < 4; ++i) { if (ctx->scratch[i]) cudaFree(ctx->scratch[i]); ctx->scratch[i] = nullptr; ctx->scratch_cap[i] = 0; }
+            e = cudaMalloc(&ctx->scratch[slot], bytes);
+            if (e != cudaSuccess) { ctx->scratch[slot] = nullptr; return e; }
+        }
+        ctx->scratch_cap[slot] = bytes;
+    }
+    *out = ctx->scratch[slot];
+    return cudaSuccess;
+}
 
 // Device time of a stage when dlv_set_conv_timing is on (events on the library stream; serialises it - bench only).
 enum { kStageBlend = 0, kStageNorm = 1, kStageGather = 2 };

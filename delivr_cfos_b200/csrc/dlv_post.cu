@@ -181,7 +181,7 @@ int post_finalise_slab(Ctx* ctx, const float* avg, const uint16_t* vol, int64_t 
     g.SY = SY; g.SX = SX; g.Y = sr[1]; g.X = sr[2]; g.nplanes = nplanes; g.cap = iters + 1;
     if (nplanes <= 0 || g.Y <= 0 || g.X <= 0) return 0;
     uint8_t* dist = nullptr;
-    DLV_CUDA_OK(ctx, dmalloc(ctx, &dist, static_cast<size_t>(nplanes) * g.Y * g.X));
+    DLV_CUDA_OK(ctx, scratch_get(ctx, kScratchDist, static_cast<size_t>(nplanes) * g.Y * g.X, reinterpret_cast<void**>(&dist)));
     const int nwords = static_cast<int>((g.X + 31) / 32);
     const int wpb = 8;
     const size_t smem = static_cast<size_t>(wpb) * nwords * 4;
@@ -199,7 +199,6 @@ int post_finalise_slab(Ctx* ctx, const float* avg, const uint16_t* vol, int64_t 
     erode_z_final_kernel<<<grid, 128, 0, ctx->stream>>>(dist, g, avg, gz0, Zreal, bp, first_block, oz0, oz1, thr, iters, bin, sig);
     ctx->launches += 3;
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    dfree(ctx, dist);
     if (e != cudaSuccess) { set_error(ctx, "finalise kernels failed: %s", cudaGetErrorString(e)); return DLV_ERR_CUDA; }
     return 0;
 }

@@ -136,6 +136,10 @@ struct DevBuf {
     ~DevBuf() { if (p) cudaFreeAsync(p, s); }
     template <class T> T* as() { return static_cast<T*>(p); }
 };
+struct Borrowed {              // context-owned grow-only scratch (scratch_get): same accessors as DevBuf, nothing to free
+    void* p = nullptr;
+    template <class T> T* as() { return static_cast<T*>(p); }
+};
 static int dev_alloc(Ctx* ctx, DevBuf& b, size_t bytes) {
     b.s = ctx->stream;
     DLV_CUDA_OK(ctx, dmalloc(ctx, &b.p, bytes));
@@ -389,13 +393,14 @@ int segment_run(Ctx* ctx, const void* volume_any, const dlv_seg_params* P, void*
     // window z-layer k ends - and layer k's skip scan and window batches start as soon as their chunk has landed, so
     // everything but the first chunk of the upload hides behind the network (pinned host memory; a pageable volume
     // is staged by the driver and overlaps only with batches that are already enqueued).
-    DevBuf slab_own, d_orig, d_active, d_acc;
+    DevBuf d_orig, d_active;
+    Borrowed slab_own, d_acc, bin_own;
     const uint16_t* slab = static_cast<const uint16_t*>(volume_any);
     const bool host_volume = !is_device_ptr(volume_any);
     if ((rc = dev_upload(ctx, d_orig, origins))) return rc;
     if ((rc = dev_alloc(ctx, d_active, nwin * sizeof(int32_t)))) return rc;
     std::vector<int32_t> active(nwin, 1);
-    if ((rc = dev_alloc(ctx, d_acc, nvox_pad * 4))) return rc;
+    DLV_CUDA_OK(ctx, scratch_get(ctx, kScratchAcc, nvox_pad * 4, &d_acc.p));
     DLV_CUDA_OK(ctx, cudaMemsetAsync(d_acc.p, 0, nvox_pad * 4, ctx->stream));
     struct Events {           // destroyed on every return path
         std::vector<cudaEvent_t> e;
@@ -430,7 +435,7 @@ int segment_run(Ctx* ctx, const void* volume_any, const dlv_seg_params* P, void*
                 if (active[w]) push_window(sched, w, ps);
         rc = seg_accumulate(ctx, slab, PY, PX, sched, P->roi, batch, P->blend_mode, d_acc.as<int32_t>(), &geom);
     } else {
-        if ((rc = dev_alloc(ctx, slab_own, nvox_pad * 2))) return rc;
+        DLV_CUDA_OK(ctx, scratch_get(ctx, kScratchSlab, nvox_pad * 2, &slab_own.p));
         slab = slab_own.as<uint16_t>();
         Events landed(nz);
         // the allocation (stream-ordered on ctx->stream) must precede the first copy on the copy stream
@@ -488,12 +493,12 @@ int segment_run(Ctx* ctx, const void* volume_any, const dlv_seg_params* P, void*
 
     mark("average");
     // ---- binarise + eroded-mask gate
-    DevBuf bin_own, sig_own;
+    DevBuf sig_own;
     uint8_t* bin = static_cast<uint8_t*>(binaries_any);
     float* sig = static_cast<float*>(sig_any);
     const bool bin_host = !is_device_ptr(binaries_any);
     const bool sig_host = sig_any && !is_device_ptr(sig_any);
-    if (rc == 0 && bin_host) { if ((rc = dev_alloc(ctx, bin_own, nvox))) return rc; bin = bin_own.as<uint8_t>(); }
+    if (rc == 0 && bin_host) { DLV_CUDA_OK(ctx, scratch_get(ctx, kScratchBin, nvox, &bin_own.p)); bin = bin_own.as<uint8_t>(); }
     if (rc == 0 && sig_host) { if ((rc = dev_alloc(ctx, sig_own, nvox * 4))) return rc; sig = sig_own.as<float>(); }
     if (rc == 0)
         rc = post_finalise(ctx, d_acc.as<float>(), slab, P->shape_pad, P->shape_real, P->threshold, P->erosion_iters,

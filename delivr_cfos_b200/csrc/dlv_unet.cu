@@ -541,7 +541,7 @@ static int is_max_parts(const Level& L) {
 }
 
 struct IsPlan {
-    int T, S, RL, H, NC, NZS, Zs, nstages, nparts, G;
+    int T, S, RL, H, NC, NZS, Zs, nstages, nparts, G, nsub;
     uint32_t stage_bytes, w_bytes, smem;
 };
 
@@ -552,7 +552,12 @@ static bool plan_conv_is(const Ctx* ctx, const ConvLayer& Ly, const Level& L, in
     const int PL = L.YpXp;
     P.H = L.Xp + 1;
     P.w_bytes = static_cast<uint32_t>(Ly.KB) * (Ly.cin == 1 ? 3 : 9) * 3072;
-    const int nchunks = 2 * Ly.KB;
+    // 64 -> 32 layers can stage (and multiply) a plane in two halves of 4 chunks - the skip tensor's raw half, which the
+    // transform warps normalise, and the up-sampled half, which is ready as it lands: four half-plane stages fit beside
+    // the weights where only two whole-plane stages do.  Measured slower (DLV_IS_NSUB=2: 5 704 instead of 5 387 clk
+    // per plane on cfg2 - transform and MMA stream then overlap fully and slow each other), so it is off by default.
+    P.nsub = (Ly.KB == 4 && ctx->is_nsub == 2) ? 2 : 1;
+    const int nchunks = 2 * Ly.KB / P.nsub;      // chunks per stage
     auto fits = [&](int T, int& nst, int& RL, uint32_t& sb) {
         RL = ((128 * T + 2 * P.H + 7) / 8) * 8;
         sb = static_cast<uint32_t>(nchunks) * RL * 16;
@@ -657,7 +662,7 @@ static int run_conv_is(Ctx* ctx, const ConvLayer& Ly, const Level& L, int nwin, 
     a.Z = L.Z; a.Y = L.Y; a.X = L.X; a.Xp = L.Xp; a.PL = L.YpXp; a.Vp = L.Vp;
     a.KB = Ly.KB; a.NC = P.NC; a.NZS = P.NZS; a.Zs = P.Zs; a.G = P.G;
     a.nitems = nwin * P.NC * P.NZS;
-    a.RL = P.RL; a.H = P.H; a.nstages = P.nstages;
+    a.RL = P.RL; a.H = P.H; a.nstages = P.nstages; a.nsub = P.nsub;
     a.stage_bytes = P.stage_bytes; a.w_bytes = P.w_bytes;
     a.inv_count = 1.0 / (static_cast<double>(L.Z) * L.Y * L.X);
     if (Ly.cin == 1) {
@@ -691,8 +696,8 @@ static int run_conv_is(Ctx* ctx, const ConvLayer& Ly, const Level& L, int nwin, 
         cudaFree(a.dbg);
         double t[7] = {0, 0, 0, 0, 0, 0, 0};
         for (int b = 0; b < grid; ++b) for (int k = 0; k < 7; ++k) t[k] += h[b * 8 + k];
-        const double st = t[4] > 0 ? t[4] : 1;
-        fprintf(stderr, "[is] %-22s nwin %d T %d NZS %d nst %d KB %d xf %d: cycles/CTA %.0f | per step: total %.0f mma-thread waits %.0f (%.0f %.0f) | xform raw-wait %.0f work %.0f\n",
+        const double st = (t[4] > 0 ? t[4] : 1) / P.nsub;      // input planes (the kernel counts sub-steps)
+        fprintf(stderr, "[is] %-22s nwin %d T %d NZS %d nst %d KB %d xf %d: cycles/CTA %.0f | per step: total %.0f mma-thread waits %.0f (slots %.0f, stage %.0f) | xform raw-wait %.0f work %.0f\n",
                 Ly.name.c_str(), nwin, P.T, P.NZS, P.nstages, Ly.KB, a.xform_chunks, t[0] / grid, t[0] / st, t[1] / st, t[2] / st, t[3] / st, t[5] / st, t[6] / st);
     }
     if (rc) return rc;
