@@ -58,6 +58,7 @@ int dlv_init(int device, dlv_ctx** out) {
     if (const char* e = getenv("DLV_IS_T")) ctx->is_tiles = atoi(e);
     if (const char* e = getenv("DLV_IS_TX")) ctx->is_tiles_xf = atoi(e);
     if (const char* e = getenv("DLV_IS_NSUB")) ctx->is_nsub = atoi(e);
+    if (const char* e = getenv("DLV_IS_TF")) ctx->is_tiles_fold = atoi(e);
     DLV_CUDA_OK(ctx, cudaSetDevice(device));
     DLV_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     DLV_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));

@@ -73,6 +73,7 @@ struct IsArgs {
     double* part;               // [nwin][nparts][32][2] partial sums of this layer's output, nparts = (Z / G) * NC
     int nparts;
     int Z, Y, X, Xp, PL, Vp;
+    uint32_t xp_magic;          // ceil(2^32 / Xp): q / Xp == umulhi(q, xp_magic) for 0 <= q < 2^32 / Xp (in-plane positions are < 2^20)
     int KB, NC, NZS, Zs, nitems, RL, H, nstages;
     int nsub;                   // sub-steps per input plane: the plane's 2 * KB chunks are staged (and multiplied) in nsub
                                 // groups of 2 * KB / nsub chunks, each group one pipeline stage (64 -> 32 layers: 2)
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
 #pragma unroll
             for (int t = 0; t < T; ++t) {
                 const int qq = c * R + t * 128 + q * 32 + lane;
-                const int yp = qq / p.Xp, xp = qq - yp * p.Xp;
+                const int yp = static_cast<int>(__umulhi(static_cast<uint32_t>(qq), p.xp_magic)), xp = qq - yp * p.Xp;
                 valid[t] = qq < p.PL && yp >= 1 && yp <= p.Y && xp >= 1;
                 poff[t] = static_cast<int64_t>(p.out_guard) + static_cast<int64_t>(win) * p.Vp + qq;
                 anyvalid |= valid[t];
@@ -486,7 +487,7 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
                 auto ld_pos = [&](int i) -> uint32_t {
                     const int qq = c * R - p.H + i;
                     if (qq < 0 || qq >= p.PL) return 0u;
-                    const int yp = qq / p.Xp, xp = qq - yp * p.Xp;
+                    const int yp = static_cast<int>(__umulhi(static_cast<uint32_t>(qq), p.xp_magic)), xp = qq - yp * p.Xp;
                     if (yp < 1 || yp > p.Y || xp < 1) return 0u;
                     const int y = yp - 1, x = xp - 1;
                     return __ldg(plane + static_cast<int64_t>((flip == 2) ? p.Y - 1 - y : y) * p.raw_sx + ((flip == 3) ? p.X - 1 - x : x));
@@ -548,7 +549,7 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
             for (int k = 0; k < nmine; ++k) {
                 const int i = (sub + NW * k) * 32 + lane;
                 const int qq = c * R - p.H + i;
-                const int yp = qq / p.Xp, xp = qq - yp * p.Xp;
+                const int yp = static_cast<int>(__umulhi(static_cast<uint32_t>(max(qq, 0)), p.xp_magic)), xp = qq - yp * p.Xp;
                 const bool ok = i < p.RL;
                 const bool in = ok && qq >= 0 && qq < p.PL && yp >= 1 && yp <= p.Y && xp >= 1;
                 inbits |= (in ? 1u : 0u) << k;

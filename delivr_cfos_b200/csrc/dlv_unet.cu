@@ -548,7 +548,9 @@ struct IsPlan {
 static bool plan_conv_is(const Ctx* ctx, const ConvLayer& Ly, const Level& L, int nwin, IsPlan& P, bool xform = false) {
     if (Ly.cout != 32 || Ly.ntaps != 27 || !Ly.w_is) return false;
     // tile-count override: DLV_IS_T for every layer, DLV_IS_TX for the layers that normalise while staging (32 -> 32)
-    const int force_t = (xform && Ly.KB == 2 && ctx->is_tiles_xf) ? ctx->is_tiles_xf : ctx->is_tiles;
+    // and DLV_IS_TF for the uint16 first layer (3 MMAs per tile and plane: the issuing thread's per-plane bookkeeping, not
+    // the tensor pipe, bounds it, so more tiles per plane step is what helps)
+    const int force_t = (xform && Ly.KB == 2 && ctx->is_tiles_xf) ? ctx->is_tiles_xf : (Ly.cin == 1 && ctx->is_tiles_fold) ? ctx->is_tiles_fold : ctx->is_tiles;
     const int PL = L.YpXp;
     P.H = L.Xp + 1;
     P.w_bytes = static_cast<uint32_t>(Ly.KB) * (Ly.cin == 1 ? 3 : 9) * 3072;
@@ -660,6 +662,7 @@ static int run_conv_is(Ctx* ctx, const ConvLayer& Ly, const Level& L, int nwin, 
     a.w = Ly.w_is; a.out = out; a.outS = L.S; a.out_guard = L.guard;
     a.part = part; a.nparts = P.nparts;
     a.Z = L.Z; a.Y = L.Y; a.X = L.X; a.Xp = L.Xp; a.PL = L.YpXp; a.Vp = L.Vp;
+    a.xp_magic = static_cast<uint32_t>(((1ull << 32) + L.Xp - 1) / L.Xp);
     a.KB = Ly.KB; a.NC = P.NC; a.NZS = P.NZS; a.Zs = P.Zs; a.G = P.G;
     a.nitems = nwin * P.NC * P.NZS;
     a.RL = P.RL; a.H = P.H; a.nstages = P.nstages; a.nsub = P.nsub;
