@@ -48,6 +48,11 @@ constexpr int kIsMaxStages = 8;      // barrier slots; plain / fused layers use 
 #ifndef DLV_IS_COLLECTOR
 #define DLV_IS_COLLECTOR 1      // measured on cfg2: 0.478 -> 0.490 Gvoxels/s (profiles/r02_a_variants.txt)
 #endif
+#ifndef DLV_IS_FOLD_SETS
+#define DLV_IS_FOLD_SETS 1      // epilogue warp sets of the first layer (2: four of the eight staging warps drain tiles too -
+                                // measured no better: 4 building warps then starve the MMA thread, profiles/r02_m_first_layer.txt)
+#endif
+constexpr int kIsFoldSets = DLV_IS_FOLD_SETS;
 #ifndef DLV_IS_XF_EXP
 #define DLV_IS_XF_EXP 0         // timing experiments on the transform role (results invalid): 1 = copy only (shared-memory
 #endif                          // traffic without arithmetic), 2 = arithmetic only (no shared-memory loads / stores)
@@ -140,13 +145,17 @@ __device__ __forceinline__ void xf_store(uint32_t addr, const uint4& v) {
 template <int T, int S, bool FOLD>
 __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) {
     constexpr int KXN = FOLD ? 1 : 3;
+    // epilogue warp sets: the first layer is bounded by its epilogue (3 MMAs per tile and plane against the same TMEM
+    // drain, stores and statistics as every other layer), so there half of the staging warps drain tiles too
+    constexpr int NE = (FOLD && kIsFoldSets == 2 && kIsXformWarps >= 8 && T >= 2) ? 2 : 1;
+    constexpr int kFoldBuilders = kIsXformWarps - (NE - 1) * 4;      // first layer: warps that build operand stages
     static_assert(T * S * 32 <= 512, "accumulator ring exceeds TMEM");
     constexpr int R = 128 * T;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* wsm = smem;
     uint8_t* stages = smem + p.w_bytes;
-    double* comb = reinterpret_cast<double*>(stages + static_cast<size_t>(p.nstages) * p.stage_bytes);   // [2][4][64]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(comb + 512);
+    double* comb = reinterpret_cast<double*>(stages + static_cast<size_t>(p.nstages) * p.stage_bytes);   // [2][4 * NE][64]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(comb + 1024);
     uint64_t* full = bars;                          // [stages]
     uint64_t* empty = bars + kIsMaxStages;          // [stages]
     uint64_t* tfull = bars + 2 * kIsMaxStages;      // [S]
@@ -163,7 +172,7 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
         // (FOLD: one transform warp builds a whole stage and arrives alone)
         const uint32_t full_count = (!FOLD && p.xform_chunks > 0) ? static_cast<uint32_t>(kIsXformWarps) : 1u;
         for (int s = 0; s < p.nstages; ++s) { mbar_init(&full[s], full_count); mbar_init(&empty[s], 1); mbar_init(&rawfull[s], 1); }
-        for (int s = 0; s < S; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        for (int s = 0; s < S; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4 * NE); }
         mbar_init(wfull, 1);
         fence_mbar_init();
     }
@@ -348,12 +357,16 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
             }
         }
         __syncwarp();
-    } else if (warp >= kIsWarpEpi0 && warp < kIsWarpEpi0 + 4) {
-        // ------------------------------------------------------------ epilogue (4 warps = 4 TMEM lane quadrants)
+    } else if ((warp >= kIsWarpEpi0 && warp < kIsWarpEpi0 + 4) ||
+               (NE == 2 && warp >= kIsWarpXform0 + kFoldBuilders && warp < kIsWarpXform0 + kIsXformWarps)) {
+        // ------------------------------------------------------------ epilogue (4 warps = 4 TMEM lane quadrants; first
+        // layer: two such sets, set e drains the tiles t with t % 2 == e)
         const int q = warp & 3;
+        const int eset = (warp >= kIsWarpEpi0) ? 0 : 1;
         uint32_t slot_par = 0, flush = 0;
         // all accumulators start at zero (every MMA accumulates); then hand every slot to the MMA warp
-        for (int col = 0; col < 512; col += 32) tmem_zero32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + col);
+        if (eset == 0)
+            for (int col = 0; col < 512; col += 32) tmem_zero32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + col);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
@@ -393,6 +406,7 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
                 tc_fence_after();
 #pragma unroll
                 for (int t = 0; t < T; ++t) {
+                    if (NE == 2 && (t & 1) != eset) continue;       // the other epilogue set's tile
                     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * (S * 32) + s * 32;
                     if (anyw && vw[t] != 0) {      // warp-uniform
                         float v[32];
@@ -443,16 +457,20 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
 #pragma unroll
                         for (int i = 0; i < 16; ++i) { acc_s[i] = 0ull; acc_q[i] = 0ull; }
                     }
-                    double* cb = comb + (flush & 1u) * 256;
+                    double* cb = comb + (flush & 1u) * (256 * NE);
                     ++flush;
-                    cb[q * 64 + lane * 2] = run_s;
-                    cb[q * 64 + lane * 2 + 1] = run_q;
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    if (q == 2) {
+                    cb[(eset * 4 + q) * 64 + lane * 2] = run_s;
+                    cb[(eset * 4 + q) * 64 + lane * 2 + 1] = run_q;
+                    if (NE == 2) asm volatile("bar.sync 1, 256;" ::: "memory");
+                    else asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (q == 2 && eset == 0) {
                         const int grp = (zo - 1) / p.G;
                         double* dst = p.part + (static_cast<int64_t>(win) * p.nparts + grp * p.NC + c) * 64;
-                        dst[lane * 2] = cb[lane * 2] + cb[64 + lane * 2] + cb[128 + lane * 2] + cb[192 + lane * 2];
-                        dst[lane * 2 + 1] = cb[lane * 2 + 1] + cb[64 + lane * 2 + 1] + cb[128 + lane * 2 + 1] + cb[192 + lane * 2 + 1];
+                        double ts = 0.0, tq = 0.0;
+#pragma unroll
+                        for (int w = 0; w < 4 * NE; ++w) { ts += cb[w * 64 + lane * 2]; tq += cb[w * 64 + lane * 2 + 1]; }   // fixed order
+                        dst[lane * 2] = ts;
+                        dst[lane * 2 + 1] = tq;
                     }
                 }
             }
@@ -469,7 +487,7 @@ __global__ void __launch_bounds__(kIsThreads, 1) conv_is_kernel(const IsArgs p) 
         const int tw = warp - kIsWarpXform0;
         const int ngroups = (p.RL + 31) / 32;
         int step = 0;
-        for (int item = blockIdx.x; tw < p.nstages && item < p.nitems; item += gridDim.x) {
+        for (int item = blockIdx.x; tw < p.nstages && item < p.nitems; item += gridDim.x) {      // nstages <= kFoldBuilders (host)
             int win, c, za, zb;
             item_geom(item, win, c, za, zb);
             const int zi0 = max(za - 1, 1), zi1 = min(zb + 1, p.Z);

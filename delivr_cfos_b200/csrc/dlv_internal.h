@@ -74,7 +74,9 @@ struct Ctx {
     int64_t ccl_launches = 0;
     bool use_fused = true;      // Cout = 32 layers on the input-stationary fused kernel (DLV_FUSED=0 selects the per-tap kernel)
     int is_tiles = 0;           // 0 = heuristic; 2 / 4 force the tile count per column (DLV_IS_T)
-    int is_tiles_fold = 4;      // tile count of the uint16 first layer (DLV_IS_TF)
+    int is_tiles_fold = 0;      // tile count of the uint16 first layer (DLV_IS_TF; 0 = the cost model's choice, two tiles on cfg2:
+                                // four measured the same throughput, the layer is bounded by the issuing thread's per-plane
+                                // bookkeeping and the four epilogue warps, profiles/r02_m_first_layer.txt)
     int is_nsub = 1;            // 64 -> 32 layers: planes staged whole (1) or in two half-plane stages (2, DLV_IS_NSUB)
     int is_tiles_xf = 4;        // same for the 32 -> 32 layers that normalise while staging (DLV_IS_TX): four-tile columns
                                 // re-transform less halo (RL / R = 1.26 instead of 1.53 at X = 64), which is what bounds them;

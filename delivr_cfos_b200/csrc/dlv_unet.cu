@@ -563,10 +563,12 @@ static bool plan_conv_is(const Ctx* ctx, const ConvLayer& Ly, const Level& L, in
     auto fits = [&](int T, int& nst, int& RL, uint32_t& sb) {
         RL = ((128 * T + 2 * P.H + 7) / 8) * 8;
         sb = static_cast<uint32_t>(nchunks) * RL * 16;
-        const uint32_t fixed = P.w_bytes + 512 * 8 + 512;      // weights + statistics combine buffer + barriers
+        const uint32_t fixed = P.w_bytes + 1024 * 8 + 512;     // weights + statistics combine buffer + barriers
         nst = 0;
-        // plain / fused layers: up to 4 stages; the uint16 first layer: one stage per building warp, up to 8
-        for (int n = (Ly.cin == 1 ? std::min(kIsMaxStages, kIsXformWarps) : 4); n >= 2; --n)
+        // plain / fused layers: up to 4 stages; the uint16 first layer: one stage per building warp - 4 of the staging
+        // warps when the other 4 serve as a second epilogue set (T >= 2), all 8 otherwise
+        const int max_st = (Ly.cin != 1) ? 4 : (T >= 2 && kIsXformWarps >= 8 && kIsFoldSets == 2) ? kIsXformWarps - 4 : std::min(kIsMaxStages, kIsXformWarps);
+        for (int n = max_st; n >= 2; --n)
             if (fixed + static_cast<uint64_t>(n) * sb <= kSmemLimit) { nst = n; break; }
         return nst >= 2 && RL <= 1024;      // 32 mask words per transform warp
     };

@@ -238,6 +238,8 @@ class TorchComm:
         self.torch, self.dist = torch, dist
         self.world = dist.get_world_size()
         self.rank = dist.get_rank()
+        if device is None and dist.get_backend() == "nccl":       # NCCL moves device tensors only
+            device = torch.device("cuda", torch.cuda.current_device())
         self.device = device
 
     def _p2p(self, op, tensor, peer):
@@ -1011,7 +1013,9 @@ def bench_main(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if not dist.is_initialized():
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a rank that fails must surface as an abort within minutes, not after NCCL's 10-minute default
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
     wl = B.WORKLOADS[args.workload]
     tta = bool(getattr(args, "tta", False))
     whole = bool(wl.get("whole"))              # one fixed volume sharded over the ranks (strong scaling) instead of N copies
@@ -1024,15 +1028,18 @@ def bench_main(args, rank, local_rank, world):
         bench_cfg5(B, args, ctx, comm, stream, dev, rank, world, wdesc)
         dist.destroy_process_group()
         return
-    head = _bench_job(B, args, ctx, comm, stream, dev, rank, world, wl, whole, tta, args.steps, args.warmup, True, True)
+    # the end-to-end leg keeps a second device copy of the slab while it uploads: a whole brain on fewer than 8 GPUs has no room for it
+    head = _bench_job(B, args, ctx, comm, stream, dev, rank, world, wl, whole, tta, args.steps, args.warmup, (not whole) or world >= 8, True)
     cfg4 = None
     if not whole and args.workload == "cfg2" and not getattr(args, "no_cfg4", False):
         w4 = B.WORKLOADS["cfg4"]
         cfg4 = {}
         for name, t in (("tta_off", False), ("tta_on", True)):
-            # the TTA-on steps are ~3x longer: one timed step where three would take minutes
-            est = (cfg4["tta_off"]["ms_per_step"] * 3e-3) if (t and cfg4.get("tta_off")) else 0.0
-            n = 3 if est < 25.0 else 1
+            # the TTA-on steps are ~3x longer: one timed step where three would take minutes.  Every rank must take the
+            # same decision (the timing lives on rank 0 only)
+            est = torch.tensor([(cfg4["tta_off"]["ms_per_step"] * 3e-3) if (t and cfg4.get("tta_off")) else 0.0], device=dev, dtype=torch.float64)
+            dist.broadcast(est, 0)
+            n = 3 if float(est.item()) < 25.0 else 1
             r = _bench_job(B, args, ctx, comm, stream, dev, rank, world, w4, True, t, n, 0 if t else 1, world >= 8 and not t, True)
             if rank == 0:
                 cfg4[name] = {"seconds_per_volume": r["ms_per_step"] * 1e-3, "gvoxels_per_s": r["gvoxels_per_s"], "steps": r["steps"],
@@ -1051,7 +1058,8 @@ def bench_main(args, rank, local_rank, world):
             "dtype": "bf16", "data": f"synthetic; {wdesc}",
             "config": {"workload": (f"{wl['name']}, z-slab sharded over {world} GPUs" if whole else
                                     f"{world} copies of {wl['name']} stacked along z ({shape[0]}x{shape[1]}x{shape[2]}), z-slab sharded"),
-                       "seconds_per_volume": head["ms_per_step"] * 1e-3, "seconds_per_volume_e2e": head["e2e"]["ms_per_step"] * 1e-3,
+                       "seconds_per_volume": head["ms_per_step"] * 1e-3,
+                       "seconds_per_volume_e2e": head["e2e"]["ms_per_step"] * 1e-3 if "e2e" in head else None,
                        "window": list(B.ROI), "overlap": B.OVERLAP, "tta": tta, "passes_evaluated": head["passes_evaluated"], "blend": "constant",
                        "components": head["components"],
                        "layers_per_rank": head["layers_per_rank"], "windows_per_rank": head["windows_per_rank"],
@@ -1060,7 +1068,7 @@ def bench_main(args, rank, local_rank, world):
                        "timing": "CUDA events on the library stream between barriers, max over ranks",
                        "l2": "inputs larger than L2 (slab + accumulator >> 126 MB)"},
             "gpu_launches": head["launches"], "clocks": head["clocks"],
-            "e2e": {k: v for k, v in head["e2e"].items() if k != "ms_per_step"},
+            "e2e": {k: v for k, v in head["e2e"].items() if k != "ms_per_step"} if "e2e" in head else None,
             "roofline": head["roofline"],
         }
         out["roofline"]["non_conv_share_of_step"] = head["non_conv_share"]
