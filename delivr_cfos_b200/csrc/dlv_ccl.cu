@@ -61,8 +61,10 @@ struct BgBox { int zmin, zmax, ymin, ymax, xmin, xmax; };
 // kInitSegs mask loads are issued before any of them is used, so every thread keeps that many loads in flight
 // (one load per thread and iteration left the kernel latency-bound at 2.6 TB/s).
 constexpr int kInitSegs = 4;
+// `prezeroed`: L was cleared by a memset (full-rate write); the kernel then stores only the 16 B groups that hold
+// foreground - on blob masks (a few % foreground) that is < 10 % of the label array instead of all of it.
 __global__ void __launch_bounds__(256, 5) ccl_init_kernel(const uint8_t* __restrict__ mask, CclGeom g, uint32_t* __restrict__ bits,
-                                uint32_t* __restrict__ L, int* __restrict__ bgbox) {
+                                uint32_t* __restrict__ L, int* __restrict__ bgbox, int prezeroed) {
     const int lane = threadIdx.x & 31;
     const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(256, 5) ccl_init_kernel(const uint8_t* __restr
                     const int nbg = bgn != 0;
                     const int bx0 = static_cast<int>(x0) + (__ffs(bgn) - 1), bx1 = static_cast<int>(x0) + (31 - __clz(bgn));
                     if (vec) {
-                        __stcs(reinterpret_cast<uint4*>(L + base + x0), make_uint4(lab[0], lab[1], lab[2], lab[3]));
+                        if (!prezeroed || nibs[u]) __stcs(reinterpret_cast<uint4*>(L + base + x0), make_uint4(lab[0], lab[1], lab[2], lab[3]));
                     } else {
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
@@ -169,15 +171,28 @@ __global__ void __launch_bounds__(256, 5) ccl_init_kernel(const uint8_t* __restr
 // each; through the queue the same round trips run side by side.  Pairs beyond the queue capacity (dense masks)
 // are executed in place.  Union-find results do not depend on the order of the unions.
 constexpr int kMergeThreads = 256;
+constexpr int kMergeWords = 4;          // bitmask words per thread: a block scans 1024 words
 constexpr int kMergeQueue = 3072;
+// The words are scanned first and the non-zero ones COMPACTED into a per-block list; the enumeration below then runs
+// on dense warps (one listed word per thread) instead of on the ~5 lanes per warp that happen to own a non-zero word.
 __global__ void __launch_bounds__(kMergeThreads) ccl_merge_kernel(CclGeom g, const uint32_t* __restrict__ bits, uint32_t* __restrict__ L) {
     __shared__ uint2 queue[kMergeQueue];
-    __shared__ unsigned qn;
-    if (threadIdx.x == 0) qn = 0;
+    __shared__ uint16_t wlist[kMergeThreads * kMergeWords];
+    __shared__ unsigned qn, wn;
+    if (threadIdx.x == 0) { qn = 0; wn = 0; }
     __syncthreads();
-    const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const uint32_t cur = (t < g.rows * g.W) ? bits[t] : 0u;
-    if (cur) {
+    const int64_t nwords = g.rows * g.W;
+    const int64_t t0 = static_cast<int64_t>(blockIdx.x) * (kMergeThreads * kMergeWords);
+#pragma unroll
+    for (int k = 0; k < kMergeWords; ++k) {
+        const int li = k * kMergeThreads + threadIdx.x;                 // coalesced across the block
+        if (t0 + li < nwords && bits[t0 + li]) wlist[atomicAdd(&wn, 1u)] = static_cast<uint16_t>(li);
+    }
+    __syncthreads();
+    const unsigned nlist = wn;
+    for (unsigned li = threadIdx.x; li < nlist; li += kMergeThreads) {
+        const int64_t t = t0 + wlist[li];
+        const uint32_t cur = bits[t];
         auto push = [&](uint32_t a, uint32_t b) {
             const unsigned i = atomicAdd(&qn, 1u);
             if (i < kMergeQueue) queue[i] = make_uint2(a, b); else uf_union(L, a, b);
@@ -477,9 +492,12 @@ int ccl_run(Ctx* ctx, const uint8_t* mask, const int64_t shape[3], uint32_t* L, 
         {
             const int64_t total_warps = g.rows;     // one row per warp and iteration
             const unsigned grid = static_cast<unsigned>(std::min<int64_t>((total_warps + 7) / 8, static_cast<int64_t>(ctx->num_sms) * 32));
-            ccl_init_kernel<<<grid, 256, 0, ctx->stream>>>(mask, g, bits, L, bg_dev);
+            // aligned volumes: clear the labels at memset speed and let the kernel write foreground groups only
+            const int prezero = (g.X % 4) == 0 && (reinterpret_cast<uintptr_t>(mask) & 3u) == 0 && (reinterpret_cast<uintptr_t>(L) & 15u) == 0;
+            if (prezero) CK(cudaMemsetAsync(L, 0, static_cast<size_t>(n) * 4, ctx->stream));
+            ccl_init_kernel<<<grid, 256, 0, ctx->stream>>>(mask, g, bits, L, bg_dev, prezero);
         }
-        ccl_merge_kernel<<<nblocks(nwords, kMergeThreads), kMergeThreads, 0, ctx->stream>>>(g, bits, L);
+        ccl_merge_kernel<<<nblocks(nwords, kMergeThreads * kMergeWords), kMergeThreads, 0, ctx->stream>>>(g, bits, L);
         ccl_compress_kernel<<<nblocks(nwords, 256), 256, 0, ctx->stream>>>(g, bits, L, rootbits);
         scan_block_sums_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, ctx->stream>>>(rootbits, nwords, bsum);
         scan_of_block_sums_kernel<<<1, kScanBlock, 0, ctx->stream>>>(bsum, nb, n_dev);
