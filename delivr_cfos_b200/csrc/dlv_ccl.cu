@@ -60,7 +60,7 @@ struct BgBox { int zmin, zmax, ymin, ymax, xmin, xmax; };
 // One warp handles kInitSegs x 128 consecutive voxels per iteration (4 per lane and segment, 16 B label stores); the
 // kInitSegs mask loads are issued before any of them is used, so every thread keeps that many loads in flight
 // (one load per thread and iteration left the kernel latency-bound at 2.6 TB/s).
-constexpr int kInitSegs = 4;
+constexpr int kInitSegs = 4;      // 8 measured the same (the pass is instruction-bound: IPC 2.3, issue slots 57 % busy, DRAM 17 %; profiles/r02_r_ccl_init_merge_sol.txt)
 // `prezeroed`: L was cleared by a memset (full-rate write); the kernel then stores only the 16 B groups that hold
 // foreground - on blob masks (a few % foreground) that is < 10 % of the label array instead of all of it.
 __global__ void __launch_bounds__(256, 5) ccl_init_kernel(const uint8_t* __restrict__ mask, CclGeom g, uint32_t* __restrict__ bits,
@@ -100,6 +100,19 @@ __global__ void __launch_bounds__(256, 5) ccl_init_kernel(const uint8_t* __restr
                 const int sg = sg0 + u;
                 if (sg >= segs) break;                         // warp-uniform
                 const int64_t x0 = static_cast<int64_t>(sg) * 128 + lane * 4;
+                if (vec && __ballot_sync(0xffffffffu, nibs[u] != 0u) == 0u) {
+                    // 128 background voxels (about half of the segments of a blob mask): zero labels, zero bitmask words
+                    // and the background box - none of the run arithmetic below
+                    const int wi = sg * 4 + (lane >> 3);
+                    if ((lane & 7) == 0 && wi < g.W) bits[r * g.W + wi] = 0u;
+                    if (x0 < g.X) {
+                        if (!prezeroed) __stcs(reinterpret_cast<uint4*>(L + base + x0), make_uint4(0u, 0u, 0u, 0u));
+                        bb.zmin = min(bb.zmin, z); bb.zmax = max(bb.zmax, z);
+                        bb.ymin = min(bb.ymin, y); bb.ymax = max(bb.ymax, y);
+                        bb.xmin = min(bb.xmin, static_cast<int>(x0)); bb.xmax = max(bb.xmax, static_cast<int>(x0 + 3 < g.X ? x0 + 3 : g.X - 1));
+                    }
+                    continue;
+                }
                 // assemble the 32-bit word of this lane's 8-lane group
                 uint32_t word = nibs[u] << (4 * (lane & 7));
                 word |= __shfl_xor_sync(0xffffffffu, word, 1);
@@ -143,6 +156,103 @@ __global__ void __launch_bounds__(256, 5) ccl_init_kernel(const uint8_t* __restr
         }
     }
     // warp-reduce the background box, one set of atomics per warp
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        bb.zmin = min(bb.zmin, __shfl_xor_sync(0xffffffffu, bb.zmin, o)); bb.zmax = max(bb.zmax, __shfl_xor_sync(0xffffffffu, bb.zmax, o));
+        bb.ymin = min(bb.ymin, __shfl_xor_sync(0xffffffffu, bb.ymin, o)); bb.ymax = max(bb.ymax, __shfl_xor_sync(0xffffffffu, bb.ymax, o));
+        bb.xmin = min(bb.xmin, __shfl_xor_sync(0xffffffffu, bb.xmin, o)); bb.xmax = max(bb.xmax, __shfl_xor_sync(0xffffffffu, bb.xmax, o));
+    }
+    if (lane == 0 && bb.zmax >= 0) {
+        atomicMin(bgbox + 0, bb.zmin); atomicMax(bgbox + 1, bb.zmax);
+        atomicMin(bgbox + 2, bb.ymin); atomicMax(bgbox + 3, bb.ymax);
+        atomicMin(bgbox + 4, bb.xmin); atomicMax(bgbox + 5, bb.xmax);
+    }
+}
+
+// ---- P1, 1024 voxels per warp and iteration, for rows that are whole 32-voxel words (X % 32 == 0, 16 B aligned buffers:
+// cfg2 / cfg3 / cfg4).  Every global access is a fully coalesced 16 B per lane: two loads bring the warp's 1024 mask
+// bytes (lane l: voxels 16 l .. 16 l + 15 of each half), eight stores write its 4 KB of labels (store k, lane l: the
+// 4 labels of 16 B chunk 32 k + l); the bitmask words travel between the two layouts by shuffle.  ~250 instructions per
+// 1024 voxels where the nibble-per-lane form above spends ~800: that form is instruction-bound (IPC 2.3, DRAM 17 %,
+// profiles/r02_r_ccl_init_merge_sol.txt), this one is bound by the 4 B/voxel label write.
+__device__ __forceinline__ uint32_t nonzero_nibble(uint32_t m) {          // bit j <- byte j of m is non-zero
+    return ((__vcmpne4(m, 0u) & 0x08040201u) * 0x01010101u) >> 24;
+}
+__global__ void __launch_bounds__(256) ccl_init_words_kernel(const uint8_t* __restrict__ mask, CclGeom g, unsigned long long w_magic,
+                                                            unsigned long long y_magic, uint32_t* __restrict__ bits,
+                                                            uint32_t* __restrict__ L, int* __restrict__ bgbox) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwords = g.rows * g.W;
+    const int64_t ngroups = (nwords + 31) / 32;                       // groups of 32 words = 1024 voxels
+    const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    BgBox bb = {INT_MAX, -1, INT_MAX, -1, INT_MAX, -1};
+    for (int64_t grp = warp0; grp < ngroups; grp += nwarps) {
+        const int64_t t0 = grp * 32;                                    // first word of the group
+        const int nw = (nwords - t0 < 32) ? static_cast<int>(nwords - t0) : 32; // words in this group (< 32 only in the last one)
+        // half h of the group = words 16 h .. 16 h + 15; lane l loads bytes 16 l .. of that half: word 16 h + l / 2, half l % 2
+        uint32_t wh[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            uint32_t part = 0u;
+            if (16 * h + (lane >> 1) < nw) {
+                const uint4 m = __ldcs(reinterpret_cast<const uint4*>(mask + (t0 + 16 * h) * 32) + lane);
+                part = (nonzero_nibble(m.x) | (nonzero_nibble(m.y) << 4) | (nonzero_nibble(m.z) << 8) | (nonzero_nibble(m.w) << 12)) << (16 * (lane & 1));
+            }
+            wh[h] = part | __shfl_xor_sync(0xffffffffu, part, 1);      // lanes 2 j and 2 j + 1 both hold word 16 h + j
+        }
+        if ((lane & 1) == 0) {
+            if ((lane >> 1) < nw) bits[t0 + (lane >> 1)] = wh[0];
+            if (16 + (lane >> 1) < nw) bits[t0 + 16 + (lane >> 1)] = wh[1];
+        }
+        uint4* dst = reinterpret_cast<uint4*>(L + t0 * 32);
+        if (__ballot_sync(0xffffffffu, (wh[0] | wh[1]) != 0u) == 0u) {
+            // 1024 background voxels
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k * 4 + (lane >> 3) < nw) __stcs(dst + k * 32 + lane, make_uint4(0u, 0u, 0u, 0u));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                // chunk 32 k + l = 4 voxels of word wi = 4 k + l / 8, bits 4 (l % 8) ..
+                const int wi = k * 4 + (lane >> 3);
+                const uint32_t word = __shfl_sync(0xffffffffu, (k < 4) ? wh[0] : wh[1], 2 * (wi & 15));
+                if (wi < nw) {
+                    const uint32_t wbase = static_cast<uint32_t>((t0 + wi) * 32);    // 0-based voxel index of bit 0 (rows are whole words)
+                    const int b0 = 4 * (lane & 7);
+                    const uint32_t zeros_below = ~word & ((1u << b0) - 1u);
+                    int run = zeros_below ? (32 - __clz(zeros_below)) : 0;           // start bit of the x-run in progress (inside this word)
+                    uint32_t lab[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const bool fg = (word >> (b0 + j)) & 1u;
+                        lab[j] = fg ? wbase + run + 1u : 0u;
+                        run = fg ? run : b0 + j + 1;
+                    }
+                    __stcs(dst + k * 32 + lane, make_uint4(lab[0], lab[1], lab[2], lab[3]));
+                }
+            }
+        }
+        // background box (table row 0), once per word on the even lanes: (z, y) of the row by exact 64-bit magic division
+        if ((lane & 1) == 0) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int wi = 16 * h + (lane >> 1);
+                const uint32_t bgw = ~wh[h];
+                if (wi < nw && bgw) {
+                    const int64_t t = t0 + wi;
+                    const uint32_t r = static_cast<uint32_t>(__umul64hi(static_cast<unsigned long long>(t), w_magic));
+                    const int w = static_cast<int>(t - static_cast<int64_t>(r) * g.W);
+                    const int z = static_cast<int>(__umul64hi(static_cast<unsigned long long>(r), y_magic));
+                    const int y = static_cast<int>(r - static_cast<uint32_t>(z) * static_cast<uint32_t>(g.Y));
+                    const int bx0 = w * 32 + (__ffs(bgw) - 1), bx1 = w * 32 + (31 - __clz(bgw));
+                    bb.zmin = min(bb.zmin, z); bb.zmax = max(bb.zmax, z);
+                    bb.ymin = min(bb.ymin, y); bb.ymax = max(bb.ymax, y);
+                    bb.xmin = min(bb.xmin, bx0); bb.xmax = max(bb.xmax, bx1);
+                }
+            }
+        }
+    }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
         bb.zmin = min(bb.zmin, __shfl_xor_sync(0xffffffffu, bb.zmin, o)); bb.zmax = max(bb.zmax, __shfl_xor_sync(0xffffffffu, bb.zmax, o));
@@ -239,14 +349,29 @@ __global__ void __launch_bounds__(kMergeThreads) ccl_merge_kernel(CclGeom g, con
     for (unsigned i = threadIdx.x; i < n; i += kMergeThreads) uf_union(L, queue[i].x, queue[i].y);
 }
 
-// ---- P3: resolve roots per run, flag roots
-__global__ void ccl_compress_kernel(CclGeom g, const uint32_t* __restrict__ bits, uint32_t* __restrict__ L,
-                                    uint32_t* __restrict__ rootbits) {
-    const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (t >= g.rows * g.W) return;
-    const uint32_t cur = bits[t];
-    uint32_t rb = 0;
-    if (cur) {
+// ---- P3: resolve roots per run, flag roots (non-zero words compacted per block like in the merge pass)
+__global__ void __launch_bounds__(kMergeThreads) ccl_compress_kernel(CclGeom g, const uint32_t* __restrict__ bits, uint32_t* __restrict__ L,
+                                                                    uint32_t* __restrict__ rootbits) {
+    __shared__ uint16_t wlist[kMergeThreads * kMergeWords];
+    __shared__ unsigned wn;
+    if (threadIdx.x == 0) wn = 0;
+    __syncthreads();
+    const int64_t nwords = g.rows * g.W;
+    const int64_t t0 = static_cast<int64_t>(blockIdx.x) * (kMergeThreads * kMergeWords);
+#pragma unroll
+    for (int k = 0; k < kMergeWords; ++k) {
+        const int li = k * kMergeThreads + threadIdx.x;
+        if (t0 + li < nwords) {
+            if (bits[t0 + li]) wlist[atomicAdd(&wn, 1u)] = static_cast<uint16_t>(li);
+            else rootbits[t0 + li] = 0u;
+        }
+    }
+    __syncthreads();
+    const unsigned nlist = wn;
+    for (unsigned li = threadIdx.x; li < nlist; li += kMergeThreads) {
+        const int64_t t = t0 + wlist[li];
+        const uint32_t cur = bits[t];
+        uint32_t rb = 0;
         const int64_t r = static_cast<uint32_t>(t) / static_cast<uint32_t>(g.W);
         const int w = static_cast<int>(t - r * g.W);
         const int64_t vb0 = r * g.X + static_cast<int64_t>(w) * 32;     // 0-based index of bit 0
@@ -256,8 +381,8 @@ __global__ void ccl_compress_kernel(CclGeom g, const uint32_t* __restrict__ bits
             if (root == lbl) rb |= 1u << a;
             else L[vb0 + a] = root;          // shortcut; only run starts are ever traversed
         }
+        rootbits[t] = rb;
     }
-    rootbits[t] = rb;
 }
 
 // ---- P4: exclusive scan of popcounts (three small kernels)
@@ -327,36 +452,49 @@ __global__ void scan_apply_kernel(const uint32_t* __restrict__ rootbits, int64_t
 }
 
 // ---- P5: final labels + statistics, one reduction per x-run
-__global__ void ccl_relabel_stats_kernel(CclGeom g, const uint32_t* __restrict__ bits, uint32_t* __restrict__ L,
+__global__ void __launch_bounds__(kMergeThreads) ccl_relabel_stats_kernel(CclGeom g, const uint32_t* __restrict__ bits, uint32_t* __restrict__ L,
                                          const uint32_t* __restrict__ rootbits, const uint32_t* __restrict__ wprefix,
                                          unsigned long long* __restrict__ cnt, unsigned long long* __restrict__ sums,
                                          int* __restrict__ bbox) {
-    const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (t >= g.rows * g.W) return;
-    const uint32_t cur = bits[t];
-    if (!cur) return;
-    const int64_t r = static_cast<uint32_t>(t) / static_cast<uint32_t>(g.W);
-    const int w = static_cast<int>(t - r * g.W);
-    const int z = static_cast<int>(static_cast<uint32_t>(r) / static_cast<uint32_t>(g.Y)), y = static_cast<int>(r - static_cast<int64_t>(z) * g.Y);
-    const int64_t vb0 = r * g.X + static_cast<int64_t>(w) * 32;
-    DLV_FOR_RUNS64(static_cast<unsigned long long>(cur), a, len) {
-        const uint32_t lbl = static_cast<uint32_t>(vb0 + a) + 1u;
-        const uint32_t root = ((rootbits[t] >> a) & 1u) ? lbl : L[vb0 + a];
-        const int64_t ri = static_cast<int64_t>(root) - 1;
-        const int64_t rr = static_cast<uint32_t>(ri) / static_cast<uint32_t>(g.X);
-        const int rx = static_cast<int>(ri - rr * g.X);
-        const int64_t rw = rr * g.W + (rx >> 5);
-        const uint32_t rank = wprefix[rw] + __popc(rootbits[rw] & ((1u << (rx & 31)) - 1u)) + 1u;
-        for (int j = 0; j < len; ++j) L[vb0 + a + j] = rank;
-        const int xa = w * 32 + a, xb = xa + len - 1;
-        atomicAdd(cnt + rank, static_cast<unsigned long long>(len));
-        atomicAdd(sums + 3ull * rank + 0, static_cast<unsigned long long>(z) * len);
-        atomicAdd(sums + 3ull * rank + 1, static_cast<unsigned long long>(y) * len);
-        atomicAdd(sums + 3ull * rank + 2, static_cast<unsigned long long>(xa + xb) * len / 2ull);
-        int* b = bbox + 6ull * rank;
-        atomicMin(b + 0, z); atomicMax(b + 1, z);
-        atomicMin(b + 2, y); atomicMax(b + 3, y);
-        atomicMin(b + 4, xa); atomicMax(b + 5, xb);
+    __shared__ uint16_t wlist[kMergeThreads * kMergeWords];
+    __shared__ unsigned wn;
+    if (threadIdx.x == 0) wn = 0;
+    __syncthreads();
+    const int64_t nwords = g.rows * g.W;
+    const int64_t t0 = static_cast<int64_t>(blockIdx.x) * (kMergeThreads * kMergeWords);
+#pragma unroll
+    for (int k = 0; k < kMergeWords; ++k) {
+        const int li = k * kMergeThreads + threadIdx.x;
+        if (t0 + li < nwords && bits[t0 + li]) wlist[atomicAdd(&wn, 1u)] = static_cast<uint16_t>(li);
+    }
+    __syncthreads();
+    const unsigned nlist = wn;
+    for (unsigned li = threadIdx.x; li < nlist; li += kMergeThreads) {
+        const int64_t t = t0 + wlist[li];
+        const uint32_t cur = bits[t];
+        const int64_t r = static_cast<uint32_t>(t) / static_cast<uint32_t>(g.W);
+        const int w = static_cast<int>(t - r * g.W);
+        const int z = static_cast<int>(static_cast<uint32_t>(r) / static_cast<uint32_t>(g.Y)), y = static_cast<int>(r - static_cast<int64_t>(z) * g.Y);
+        const int64_t vb0 = r * g.X + static_cast<int64_t>(w) * 32;
+        DLV_FOR_RUNS64(static_cast<unsigned long long>(cur), a, len) {
+            const uint32_t lbl = static_cast<uint32_t>(vb0 + a) + 1u;
+            const uint32_t root = ((rootbits[t] >> a) & 1u) ? lbl : L[vb0 + a];
+            const int64_t ri = static_cast<int64_t>(root) - 1;
+            const int64_t rr = static_cast<uint32_t>(ri) / static_cast<uint32_t>(g.X);
+            const int rx = static_cast<int>(ri - rr * g.X);
+            const int64_t rw = rr * g.W + (rx >> 5);
+            const uint32_t rank = wprefix[rw] + __popc(rootbits[rw] & ((1u << (rx & 31)) - 1u)) + 1u;
+            for (int j = 0; j < len; ++j) L[vb0 + a + j] = rank;
+            const int xa = w * 32 + a, xb = xa + len - 1;
+            atomicAdd(cnt + rank, static_cast<unsigned long long>(len));
+            atomicAdd(sums + 3ull * rank + 0, static_cast<unsigned long long>(z) * len);
+            atomicAdd(sums + 3ull * rank + 1, static_cast<unsigned long long>(y) * len);
+            atomicAdd(sums + 3ull * rank + 2, static_cast<unsigned long long>(xa + xb) * len / 2ull);
+            int* b = bbox + 6ull * rank;
+            atomicMin(b + 0, z); atomicMax(b + 1, z);
+            atomicMin(b + 2, y); atomicMax(b + 3, y);
+            atomicMin(b + 4, xa); atomicMax(b + 5, xb);
+        }
     }
 }
 
@@ -492,13 +630,23 @@ int ccl_run(Ctx* ctx, const uint8_t* mask, const int64_t shape[3], uint32_t* L, 
         {
             const int64_t total_warps = g.rows;     // one row per warp and iteration
             const unsigned grid = static_cast<unsigned>(std::min<int64_t>((total_warps + 7) / 8, static_cast<int64_t>(ctx->num_sms) * 32));
-            // aligned volumes: clear the labels at memset speed and let the kernel write foreground groups only
-            const int prezero = (g.X % 4) == 0 && (reinterpret_cast<uintptr_t>(mask) & 3u) == 0 && (reinterpret_cast<uintptr_t>(L) & 15u) == 0;
-            if (prezero) CK(cudaMemsetAsync(L, 0, static_cast<size_t>(n) * 4, ctx->stream));
-            ccl_init_kernel<<<grid, 256, 0, ctx->stream>>>(mask, g, bits, L, bg_dev, prezero);
+            // rows of whole 32-voxel words in 16 B aligned buffers: one lane per word; anything else: the general form
+            const bool words = (g.X % 32) == 0 && (reinterpret_cast<uintptr_t>(mask) & 15u) == 0 && (reinterpret_cast<uintptr_t>(L) & 15u) == 0;
+            if (words) {
+                const unsigned long long w_magic = ~0ull / static_cast<unsigned long long>(g.W) + 1ull;     // ceil(2^64 / W) for W > 1
+                const unsigned long long y_magic = ~0ull / static_cast<unsigned long long>(g.Y) + 1ull;
+                if (g.W > 1 && g.Y > 1) {
+                    const unsigned wgrid = static_cast<unsigned>(std::min<int64_t>((nwords + 255) / 256, static_cast<int64_t>(ctx->num_sms) * 16));   // 8 warps x 32 words per block and iteration
+                    ccl_init_words_kernel<<<wgrid, 256, 0, ctx->stream>>>(mask, g, w_magic, y_magic, bits, L, bg_dev);
+                } else {
+                    ccl_init_kernel<<<grid, 256, 0, ctx->stream>>>(mask, g, bits, L, bg_dev, 0);
+                }
+            } else {
+                ccl_init_kernel<<<grid, 256, 0, ctx->stream>>>(mask, g, bits, L, bg_dev, 0);
+            }
         }
         ccl_merge_kernel<<<nblocks(nwords, kMergeThreads * kMergeWords), kMergeThreads, 0, ctx->stream>>>(g, bits, L);
-        ccl_compress_kernel<<<nblocks(nwords, 256), 256, 0, ctx->stream>>>(g, bits, L, rootbits);
+        ccl_compress_kernel<<<nblocks(nwords, kMergeThreads * kMergeWords), kMergeThreads, 0, ctx->stream>>>(g, bits, L, rootbits);
         scan_block_sums_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, ctx->stream>>>(rootbits, nwords, bsum);
         scan_of_block_sums_kernel<<<1, kScanBlock, 0, ctx->stream>>>(bsum, nb, n_dev);
         scan_apply_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, ctx->stream>>>(rootbits, nwords, bsum, wprefix);
@@ -533,7 +681,7 @@ int ccl_run(Ctx* ctx, const uint8_t* mask, const int64_t shape[3], uint32_t* L, 
             CK(cudaMemsetAsync(totals, 0, 32, ctx->stream));
             CK(cudaEventRecord(e2, ctx->stream));
             bbox_init_kernel<<<nblocks(rows, 256), 256, 0, ctx->stream>>>(bbox, rows, static_cast<int>(g.Z), static_cast<int>(g.Y), static_cast<int>(g.X));
-            ccl_relabel_stats_kernel<<<nblocks(nwords, 256), 256, 0, ctx->stream>>>(g, bits, L, rootbits, wprefix, cnt, sums, bbox);
+            ccl_relabel_stats_kernel<<<nblocks(nwords, kMergeThreads * kMergeWords), kMergeThreads, 0, ctx->stream>>>(g, bits, L, rootbits, wprefix, cnt, sums, bbox);
             ccl_table_finish_kernel<<<nblocks(rows, 256), 256, 0, ctx->stream>>>(rows, cnt, sums, bbox, bbox64, cent, totals);
             launches += 3;
             CK(cudaGetLastError());

@@ -34,6 +34,9 @@ def _compare(mask):
     ((40, 64, 128), "blobs", 0), ((33, 70, 90), "blobs", 0), ((20, 50, 61), "bernoulli", 0.08),
     ((16, 40, 200), "bernoulli", 0.5), ((8, 33, 257), "bernoulli", 0.3), ((64, 256, 256), "blobs", 0),
     ((5, 7, 3), "bernoulli", 0.4), ((1, 1, 1), "bernoulli", 1.0), ((3, 5, 1000), "bernoulli", 0.9),
+    # rows of whole 32-voxel words take the word-per-lane init pass (W = 1 or Y = 1: the general one)
+    ((10, 20, 64), "bernoulli", 0.5), ((6, 1, 64), "bernoulli", 0.7), ((7, 9, 32), "bernoulli", 0.9), ((5, 12, 96), "bernoulli", 0.05),
+    ((3, 4, 2048), "bernoulli", 0.97),
 ])
 def test_ccl_random(shape, kind, p):
     _compare(P.synth_mask(shape, 1003, kind=kind, p=p))
