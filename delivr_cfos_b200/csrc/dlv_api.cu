@@ -59,6 +59,9 @@ int dlv_init(int device, dlv_ctx** out) {
     if (const char* e = getenv("DLV_IS_TX")) ctx->is_tiles_xf = atoi(e);
     if (const char* e = getenv("DLV_IS_NSUB")) ctx->is_nsub = atoi(e);
     if (const char* e = getenv("DLV_IS_TF")) ctx->is_tiles_fold = atoi(e);
+    if (const char* e = getenv("DLV_DECONV_EPI")) ctx->deconv_epi = atoi(e);
+    if (const char* e = getenv("DLV_CCL_BBOX_CHECK")) ctx->ccl_bbox_check = atoi(e) != 0;
+    if (const char* e = getenv("DLV_PAINT_RESOLVE")) ctx->paint_resolve_boxes = atoi(e) != 1;
     DLV_CUDA_OK(ctx, cudaSetDevice(device));
     DLV_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     DLV_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));

@@ -385,12 +385,27 @@ __global__ void __launch_bounds__(kMergeThreads) ccl_compress_kernel(CclGeom g, 
     }
 }
 
-// ---- P4: exclusive scan of popcounts (three small kernels)
+// ---- P4: exclusive scan of popcounts (three small kernels).  Four root-bitmask words per thread (one 16 B load, one
+// 16 B store of the prefixes): with one word per thread the two streaming kernels ran at 1.2 - 1.5 TB/s
+// (profiles/r02_v_ccl_traffic_cfg3.txt: 0.45 + 0.65 ms for 0.5 GB each way on cfg3).
 constexpr int kScanBlock = 1024;
+constexpr int kScanItems = 4;
+constexpr int kScanSpan = kScanBlock * kScanItems;      // words per block
+__device__ __forceinline__ void scan_load_popc(const uint32_t* __restrict__ rootbits, int64_t nwords, int64_t i0, uint32_t (&pc)[kScanItems]) {
+    if (i0 + kScanItems <= nwords) {
+        const uint4 w = *reinterpret_cast<const uint4*>(rootbits + i0);      // i0 % 4 == 0, pool allocations are 256 B aligned
+        pc[0] = __popc(w.x); pc[1] = __popc(w.y); pc[2] = __popc(w.z); pc[3] = __popc(w.w);
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) pc[k] = (i0 + k < nwords) ? __popc(rootbits[i0 + k]) : 0u;
+    }
+}
 __global__ void scan_block_sums_kernel(const uint32_t* __restrict__ rootbits, int64_t nwords, uint32_t* __restrict__ bsum) {
     __shared__ uint32_t sh[32];
-    const int64_t i = static_cast<int64_t>(blockIdx.x) * kScanBlock + threadIdx.x;
-    uint32_t v = (i < nwords) ? __popc(rootbits[i]) : 0u;
+    const int64_t i0 = (static_cast<int64_t>(blockIdx.x) * kScanBlock + threadIdx.x) * kScanItems;
+    uint32_t pc[kScanItems];
+    scan_load_popc(rootbits, nwords, i0, pc);
+    uint32_t v = pc[0] + pc[1] + pc[2] + pc[3];
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
@@ -445,13 +460,23 @@ __global__ void scan_apply_kernel(const uint32_t* __restrict__ rootbits, int64_t
                                   uint32_t* __restrict__ wprefix) {
     __shared__ uint32_t sh[32];
     __shared__ uint32_t tot;
-    const int64_t i = static_cast<int64_t>(blockIdx.x) * kScanBlock + threadIdx.x;
-    const uint32_t v = (i < nwords) ? __popc(rootbits[i]) : 0u;
-    const uint32_t e = block_excl_scan_1024(v, sh, &tot);
-    if (i < nwords) wprefix[i] = bsum[blockIdx.x] + e;
+    const int64_t i0 = (static_cast<int64_t>(blockIdx.x) * kScanBlock + threadIdx.x) * kScanItems;
+    uint32_t pc[kScanItems];
+    scan_load_popc(rootbits, nwords, i0, pc);
+    const uint32_t e = bsum[blockIdx.x] + block_excl_scan_1024(pc[0] + pc[1] + pc[2] + pc[3], sh, &tot);
+    const uint4 o = make_uint4(e, e + pc[0], e + pc[0] + pc[1], e + pc[0] + pc[1] + pc[2]);
+    if (i0 + kScanItems <= nwords) {
+        *reinterpret_cast<uint4*>(wprefix + i0) = o;
+    } else {
+        const uint32_t ov[kScanItems] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k)
+            if (i0 + k < nwords) wprefix[i0 + k] = ov[k];
+    }
 }
 
 // ---- P5: final labels + statistics, one reduction per x-run
+template <bool CHECK>
 __global__ void __launch_bounds__(kMergeThreads) ccl_relabel_stats_kernel(CclGeom g, const uint32_t* __restrict__ bits, uint32_t* __restrict__ L,
                                          const uint32_t* __restrict__ rootbits, const uint32_t* __restrict__ wprefix,
                                          unsigned long long* __restrict__ cnt, unsigned long long* __restrict__ sums,
@@ -491,9 +516,23 @@ __global__ void __launch_bounds__(kMergeThreads) ccl_relabel_stats_kernel(CclGeo
             atomicAdd(sums + 3ull * rank + 1, static_cast<unsigned long long>(y) * len);
             atomicAdd(sums + 3ull * rank + 2, static_cast<unsigned long long>(xa + xb) * len / 2ull);
             int* b = bbox + 6ull * rank;
-            atomicMin(b + 0, z); atomicMax(b + 1, z);
-            atomicMin(b + 2, y); atomicMax(b + 3, y);
-            atomicMin(b + 4, xa); atomicMax(b + 5, xb);
+            if (CHECK) {
+                // A component has ~20 runs and most of them lie inside the box the others have already spanned: read the
+                // row (24 B, one or two sectors, from L2) and send only the reductions that can still change it.  The
+                // bounds move monotonically, so a stale read can only cause a redundant atomic, never a missing one.
+                const int2 bz = __ldcg(reinterpret_cast<const int2*>(b)), by = __ldcg(reinterpret_cast<const int2*>(b + 2)),
+                           bx = __ldcg(reinterpret_cast<const int2*>(b + 4));
+                if (z < bz.x) atomicMin(b + 0, z);
+                if (z > bz.y) atomicMax(b + 1, z);
+                if (y < by.x) atomicMin(b + 2, y);
+                if (y > by.y) atomicMax(b + 3, y);
+                if (xa < bx.x) atomicMin(b + 4, xa);
+                if (xb > bx.y) atomicMax(b + 5, xb);
+            } else {
+                atomicMin(b + 0, z); atomicMax(b + 1, z);
+                atomicMin(b + 2, y); atomicMax(b + 3, y);
+                atomicMin(b + 4, xa); atomicMax(b + 5, xb);
+            }
         }
     }
 }
@@ -617,7 +656,7 @@ int ccl_run(Ctx* ctx, const uint8_t* mask, const int64_t shape[3], uint32_t* L, 
     int64_t launches = 0;
 #define CK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error(ctx, "dlv_ccl: %s: %s", #expr, cudaGetErrorString(_e)); rc = DLV_ERR_CUDA; goto done; } } while (0)
     if (n > 0) {
-        const int64_t nb = (nwords + kScanBlock - 1) / kScanBlock;
+        const int64_t nb = (nwords + kScanSpan - 1) / kScanSpan;
         CK(dmalloc(ctx, &bits, nwords * 4));
         CK(dmalloc(ctx, &rootbits, nwords * 4));
         CK(dmalloc(ctx, &wprefix, nwords * 4));
@@ -681,7 +720,10 @@ int ccl_run(Ctx* ctx, const uint8_t* mask, const int64_t shape[3], uint32_t* L, 
             CK(cudaMemsetAsync(totals, 0, 32, ctx->stream));
             CK(cudaEventRecord(e2, ctx->stream));
             bbox_init_kernel<<<nblocks(rows, 256), 256, 0, ctx->stream>>>(bbox, rows, static_cast<int>(g.Z), static_cast<int>(g.Y), static_cast<int>(g.X));
-            ccl_relabel_stats_kernel<<<nblocks(nwords, kMergeThreads * kMergeWords), kMergeThreads, 0, ctx->stream>>>(g, bits, L, rootbits, wprefix, cnt, sums, bbox);
+            if (ctx->ccl_bbox_check)
+                ccl_relabel_stats_kernel<true><<<nblocks(nwords, kMergeThreads * kMergeWords), kMergeThreads, 0, ctx->stream>>>(g, bits, L, rootbits, wprefix, cnt, sums, bbox);
+            else
+                ccl_relabel_stats_kernel<false><<<nblocks(nwords, kMergeThreads * kMergeWords), kMergeThreads, 0, ctx->stream>>>(g, bits, L, rootbits, wprefix, cnt, sums, bbox);
             ccl_table_finish_kernel<<<nblocks(rows, 256), 256, 0, ctx->stream>>>(rows, cnt, sums, bbox, bbox64, cent, totals);
             launches += 3;
             CK(cudaGetLastError());

@@ -454,15 +454,15 @@ int net_load(Ctx* ctx, int n, const char* const* names, const float* const* data
 }
 
 // ------------------------------------------------------------------- conv launcher
-template <int NBLK, int NTAPS, int MODE>
+template <int NBLK, int NTAPS, int MODE, int EPI = 1, bool PIPE = false>
 static int launch_conv_t(Ctx* ctx, const ConvArgs& a, int grid, uint32_t smem) {
-    auto k = conv_tc_kernel<NBLK, NTAPS, MODE>;
+    auto k = conv_tc_kernel<NBLK, NTAPS, MODE, EPI, PIPE>;
     static bool attr_set = false;
     if (!attr_set) {
         DLV_CUDA_OK(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
         attr_set = true;
     }
-    k<<<grid, kConvThreads, smem, ctx->stream>>>(a);
+    k<<<grid, kConvThreads + (EPI - 1) * 128, smem, ctx->stream>>>(a);
     ctx->launches++;
     DLV_CUDA_OK(ctx, cudaGetLastError());
     return 0;
@@ -519,7 +519,11 @@ static int run_conv(Ctx* ctx, const ConvLayer& Ly, const Level& L, int nwin, con
         rc = (Ly.nblk == 32) ? launch_conv_t<32, 27, kModeConvStats>(ctx, a, grid2, smem)
                              : launch_conv_t<64, 27, kModeConvStats>(ctx, a, grid2, smem);
     } else {
-        rc = launch_conv_t<256, 1, kModeDeconvScatter>(ctx, a, grid2, smem);
+        // epilogue-bound: two epilogue warp sets with the next TMEM load in flight (dlv_conv_tc.cuh); DLV_DECONV_EPI
+        // = 1 / 2 select the single-set kernel / two sets without the software pipeline (kept for A/B measurements)
+        rc = (ctx->deconv_epi <= 1) ? launch_conv_t<256, 1, kModeDeconvScatter>(ctx, a, grid2, smem)
+           : (ctx->deconv_epi == 2) ? launch_conv_t<256, 1, kModeDeconvScatter, 2, false>(ctx, a, grid2, smem)
+                                    : launch_conv_t<256, 1, kModeDeconvScatter, 2, true>(ctx, a, grid2, smem);
     }
     if (ctx->time_convs && rc == 0) {
         cudaEventRecord(ctx->ev1, ctx->stream);
