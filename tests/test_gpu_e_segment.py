@@ -89,6 +89,10 @@ def test_golden_from_unmodified_reference(name, tmp_path):
     assert np.array_equal(stp["voxel_counts"], st["voxel_counts"])
     assert np.array_equal(stp["bounding_boxes"], st["bounding_boxes"])
     assert np.array_equal(stp["centroids"], st["centroids"], equal_nan=True)
+    if name == "g3_tta":
+        # this golden is reproduced voxel for voxel (963 / 963 foreground, every run since round 1), so the whole byte path
+        # - binaries.npy, then the CSV the unmodified reference wrote - is pinned unconditionally here
+        assert np.array_equal(b, g["binaries"])
     if np.array_equal(b, g["binaries"]):
         assert csv == g["csv"]
 
