@@ -452,11 +452,13 @@ def run_cfg3(args, rank, local_rank, world):
     labels = torch.empty(shape, dtype=torch.int32, device=dev)
     stream = torch.cuda.ExternalStream(ctx._L.dlv_stream(ctx._h), device=dev)
     torch.cuda.synchronize()
-    t_w = time.perf_counter()
     for _ in range(max(args.warmup, 1)):
         tb = ctx.ccl(mask, shape, labels_out=labels)
     torch.cuda.synchronize()
-    est_ms = (time.perf_counter() - t_w) * 1e3 / max(args.warmup, 1)
+    t_w = time.perf_counter()           # one more untimed call to size the timed region (the first calls pay the allocations)
+    tb = ctx.ccl(mask, shape, labels_out=labels)
+    torch.cuda.synchronize()
+    est_ms = (time.perf_counter() - t_w) * 1e3
     # a call lasts ~15 ms: the timed region is stretched to >= 1.5 s so that the 200 ms clock sampler sees it
     # (a 3-step region gave ONE nvidia-smi sample); `steps` in the line is the number of calls actually timed
     min_ms = float(os.environ.get("DLV_BENCH_CFG3_MIN_MS", 1500.0))       # 0 under ncu: exactly --steps calls
@@ -496,11 +498,11 @@ def run_cfg3(args, rank, local_rank, world):
     torch.cuda.synchronize()
     pms = p0.elapsed_time(p1) / psteps
     painted = int((rgb[0] > 0).sum())
-    paint = {"ms_per_call": pms, "calls_timed": psteps, "resolve": os.environ.get("DLV_PAINT_RESOLVE", "2 (memset + box walk)"), "boxes": n, "channels": 3, "painted_voxels": painted, "foreground_voxels": fg,
+    paint = {"ms_per_call": pms, "calls_timed": psteps, "boxes": n, "channels": 3, "painted_voxels": painted, "foreground_voxels": fg,
              "gbs_algorithmic": 4.0 * nvox / (pms * 1e-3) / 1e9, "frac_of_hbm": 4.0 * nvox / (pms * 1e-3) / 1e9 / hbm_peak}
     emit({
         "metric": "Gvoxels/s CC+table", "value": nvox / (ms * 1e-3) / 1e9, "unit": "Gvoxels/s", "n_gpus": 1, "steps": steps,
-        "steps_requested": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "steps_requested": args.steps, "warmup": max(args.warmup, 1) + 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": CFG3["name"], "components": tb["n"], "foreground_fraction": fg / nvox,
                    "l2": "inputs larger than L2 (4.2 GB mask, 16.8 GB labels)"},

@@ -60,8 +60,9 @@ int dlv_init(int device, dlv_ctx** out) {
     if (const char* e = getenv("DLV_IS_NSUB")) ctx->is_nsub = atoi(e);
     if (const char* e = getenv("DLV_IS_TF")) ctx->is_tiles_fold = atoi(e);
     if (const char* e = getenv("DLV_DECONV_EPI")) ctx->deconv_epi = atoi(e);
+    if (const char* e = getenv("DLV_DECONV_STAGES")) ctx->deconv_stages = atoi(e);
     if (const char* e = getenv("DLV_CCL_BBOX_CHECK")) ctx->ccl_bbox_check = atoi(e) != 0;
-    if (const char* e = getenv("DLV_PAINT_RESOLVE")) ctx->paint_resolve_boxes = atoi(e) != 1;
+    if (const char* e = getenv("DLV_CCL_PRUNE")) ctx->ccl_prune = atoi(e) != 0;
     DLV_CUDA_OK(ctx, cudaSetDevice(device));
     DLV_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     DLV_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));

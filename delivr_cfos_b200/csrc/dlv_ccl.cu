@@ -11,7 +11,8 @@
 //                This is the only pass that touches every label (4 B/voxel write).
 //   P2 merge     one thread per bitmask word: for every x-run, union (lock-free atomicMin union-find, root =
 //                smallest linear index = first voxel in raster order) with the runs it touches in the 4 raster-
-//                predecessor rows (y-1 | z-1,y-1 | z-1,y | z-1,y+1; x-range widened by 1) and the previous word.
+//                predecessor rows (y-1 | z-1,y-1 | z-1,y | z-1,y+1; x-range widened by 1) and the previous word;
+//                unions already implied by the predecessor rows' own unions are skipped (ccl_merge_kernel).
 //   P3 compress  every run start resolves its root; roots are flagged in a second bitmask.
 //   P4 scan      exclusive prefix sum over popcounts of the root bitmask -> rank of every root = final label.
 //   P5 relabel   every run looks up its root's rank, rewrites its voxels, and reduces count / sum z,y,x / bbox
@@ -285,6 +286,7 @@ constexpr int kMergeWords = 4;          // bitmask words per thread: a block sca
 constexpr int kMergeQueue = 3072;
 // The words are scanned first and the non-zero ones COMPACTED into a per-block list; the enumeration below then runs
 // on dense warps (one listed word per thread) instead of on the ~5 lanes per warp that happen to own a non-zero word.
+template <bool PRUNE>
 __global__ void __launch_bounds__(kMergeThreads) ccl_merge_kernel(CclGeom g, const uint32_t* __restrict__ bits, uint32_t* __restrict__ L) {
     __shared__ uint2 queue[kMergeQueue];
     __shared__ uint16_t wlist[kMergeThreads * kMergeWords];
@@ -328,18 +330,48 @@ __global__ void __launch_bounds__(kMergeThreads) ccl_merge_kernel(CclGeom g, con
         const uint32_t prevw = (w > 0 && (cur & 1u)) ? bits[t - 1] : 0u;
         // same row, previous word
         if (prevw >> 31) push(vbase, vbase - 1u);
+        // bit i of comb[k] <-> neighbour-row voxel x = w*32 + i - 1, i in [0, 34); label of neighbour bit i is nbase[k] + i
+        unsigned long long comb[4];
+        uint32_t nbase[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            // bit i of comb <-> neighbour-row voxel x = w*32 + i - 1, i in [0, 34)
-            const unsigned long long comb = (static_cast<unsigned long long>(c[k]) << 1) | (p[k] >> 31) | (static_cast<unsigned long long>(q[k] & 1u) << 33);
-            if (!comb) continue;
-            const uint32_t nbase = static_cast<uint32_t>(nrows[k] * g.X + static_cast<int64_t>(w) * 32);   // label of neighbour bit i is nbase + i
-            DLV_FOR_RUNS64(static_cast<unsigned long long>(cur), a, len) {
-                // run [a, a+len) of the current word touches neighbour bits [a, a+len+2) of comb
-                const unsigned long long span = ((len + 2 >= 64) ? ~0ull : ((1ull << (len + 2)) - 1ull)) << a;
-                DLV_FOR_RUNS64(comb & span, i, ilen) {
-                    (void)ilen;
-                    push(vbase + a, nbase + i);
+            comb[k] = (static_cast<unsigned long long>(c[k]) << 1) | (p[k] >> 31) | (static_cast<unsigned long long>(q[k] & 1u) << 33);
+            nbase[k] = static_cast<uint32_t>(nrows[k] * g.X + static_cast<int64_t>(w) * 32);
+        }
+        if (!(comb[0] | comb[1] | comb[2] | comb[3])) continue;
+        DLV_FOR_RUNS64(static_cast<unsigned long long>(cur), a, len) {
+            // run [a, a+len) of the current word touches neighbour bits [a, a+len+2) of every comb
+            const unsigned long long span = ((len + 2 >= 64) ? ~0ull : ((1ull << (len + 2)) - 1ull)) << a;
+            if (PRUNE) {
+                // Most runs of a blob touch runs in all four predecessor rows, and those runs touch each other: rows
+                // (z-1,y-1)|(z-1,y) and (z-1,y)|(z-1,y+1) are neighbours inside plane z-1, row (z,y-1) has (z-1,y-1) and
+                // (z-1,y) among ITS predecessor rows.  Two such runs within x +- 1 of each other are united by the word
+                // that owns the later of them (an earlier row, by induction over the raster order), so once this run is
+                // tied to one of them the other union is implied.  Order: (z-1,y) first - it is adjacent to all three
+                // others - then (z,y-1), (z-1,y-1), (z-1,y+1); a run is skipped when it touches an already covered one.
+                // Checked against scipy's 26-connected labelling on random / blob masks by a CPU emulation of this
+                // enumeration: same partition, 55-66 % fewer unions.
+                const unsigned long long c0 = comb[0] & span, c1 = comb[1] & span, c2 = comb[2] & span, c3 = comb[3] & span;
+                DLV_FOR_RUNS64(c2, i, ilen) { (void)ilen; push(vbase + a, nbase[2] + i); }
+                DLV_FOR_RUNS64(c0, i, ilen) {
+                    const unsigned long long rb = ((1ull << ilen) - 1ull) << i;       // ilen <= 34
+                    if (!((rb | (rb << 1) | (rb >> 1)) & c2)) push(vbase + a, nbase[0] + i);
+                }
+                DLV_FOR_RUNS64(c1, i, ilen) {
+                    const unsigned long long rb = ((1ull << ilen) - 1ull) << i;
+                    if (!((rb | (rb << 1) | (rb >> 1)) & (c2 | c0))) push(vbase + a, nbase[1] + i);
+                }
+                DLV_FOR_RUNS64(c3, i, ilen) {
+                    const unsigned long long rb = ((1ull << ilen) - 1ull) << i;
+                    if (!((rb | (rb << 1) | (rb >> 1)) & c2)) push(vbase + a, nbase[3] + i);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    DLV_FOR_RUNS64(comb[k] & span, i, ilen) {
+                        (void)ilen;
+                        push(vbase + a, nbase[k] + i);
+                    }
                 }
             }
         }
@@ -684,7 +716,8 @@ int ccl_run(Ctx* ctx, const uint8_t* mask, const int64_t shape[3], uint32_t* L, 
                 ccl_init_kernel<<<grid, 256, 0, ctx->stream>>>(mask, g, bits, L, bg_dev, 0);
             }
         }
-        ccl_merge_kernel<<<nblocks(nwords, kMergeThreads * kMergeWords), kMergeThreads, 0, ctx->stream>>>(g, bits, L);
+        if (ctx->ccl_prune) ccl_merge_kernel<true><<<nblocks(nwords, kMergeThreads * kMergeWords), kMergeThreads, 0, ctx->stream>>>(g, bits, L);
+        else ccl_merge_kernel<false><<<nblocks(nwords, kMergeThreads * kMergeWords), kMergeThreads, 0, ctx->stream>>>(g, bits, L);
         ccl_compress_kernel<<<nblocks(nwords, kMergeThreads * kMergeWords), kMergeThreads, 0, ctx->stream>>>(g, bits, L, rootbits);
         scan_block_sums_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, ctx->stream>>>(rootbits, nwords, bsum);
         scan_of_block_sums_kernel<<<1, kScanBlock, 0, ctx->stream>>>(bsum, nb, n_dev);

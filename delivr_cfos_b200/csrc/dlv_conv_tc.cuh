@@ -32,7 +32,9 @@ constexpr int kTcWarpProducer = 4, kTcWarpMma = 5;
 #else
 constexpr int kTcWarpProducer = 0, kTcWarpMma = 1;
 #endif
-constexpr int kConvStages = 2;
+constexpr int kConvStages = 2;         // 3x3x3 convs: a stage is one cin block of all 27 taps (~100 KB, ~7 000 clk of MMAs)
+constexpr int kConvStagesMax = 12;     // k2s2 deconvs: a stage is 12 KB and ONE MMA - two of them in flight left the kernel waiting
+                                       // for TMA round trips (2.9 us per 128-position tile); barriers for up to 12 stages fit the 256 B tail
 constexpr int kTmemCols = 512;
 constexpr uint32_t kSmemLimit = 232448;   // 227 KB opt-in maximum per CTA
 
@@ -54,6 +56,7 @@ struct ConvArgs {
     int64_t NP;                 // nwin * Vp positions to cover
     int KB, NB, T, RL, H;
     int nitems, items_per_cta;
+    int nstages;                // smem pipeline depth (kConvStages for the convs, up to kConvStagesMax for the deconvs)
     uint32_t a_bytes, w_bytes, stage_bytes;
     int cout;
     int oYp, oXp, oVp;          // mode 1: geometry of the finer output level
@@ -71,10 +74,10 @@ __global__ void __launch_bounds__(kConvThreads + (EPI - 1) * 128, 1) conv_tc_ker
     static_assert(EPI == 1, "legacy warp roles: one epilogue set");
     constexpr int kWarpProducer = kTcWarpProducer, kWarpMma = kTcWarpMma;
 #endif
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kConvStages * p.stage_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.nstages * p.stage_bytes);
     uint64_t* full = bars;                       // [stages] TMA -> MMA
-    uint64_t* empty = bars + kConvStages;        // [stages] MMA -> TMA
-    uint64_t* tfull = bars + 2 * kConvStages;    // [2] MMA -> epilogue
+    uint64_t* empty = bars + p.nstages;          // [stages] MMA -> TMA
+    uint64_t* tfull = bars + 2 * p.nstages;      // [2] MMA -> epilogue
     uint64_t* tempty = tfull + 2;                // [2] epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
@@ -82,7 +85,7 @@ __global__ void __launch_bounds__(kConvThreads + (EPI - 1) * 128, 1) conv_tc_ker
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kConvStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < p.nstages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4 * EPI); }
         fence_mbar_init();
     }
@@ -118,7 +121,7 @@ __global__ void __launch_bounds__(kConvThreads + (EPI - 1) * 128, 1) conv_tc_ker
                     const int64_t pos = p.in_guard + s + dzoff - p.H;
                     tma_bulk_g2s(st + static_cast<size_t>(c) * p.RL * 16, base + pos * 8, p.RL * 16, &full[stage]);
                 }
-                if (++stage == kConvStages) { stage = 0; phase ^= 1; }
+                if (++stage == p.nstages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == kWarpMma) {
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(kConvThreads + (EPI - 1) * 128, 1) conv_tc_ker
                     if (kb == p.KB - 1) umma_commit(&tfull[buf]);
                 }
                 __syncwarp();
-                if (++stage == kConvStages) { stage = 0; phase ^= 1; }
+                if (++stage == p.nstages) { stage = 0; phase ^= 1; }
             }
         }
     } else {

@@ -77,7 +77,9 @@ struct Ctx {
     int is_tiles_fold = 0;      // tile count of the uint16 first layer (DLV_IS_TF; 0 = the cost model's choice, two tiles on cfg2:
                                 // four measured the same throughput, the layer is bounded by the issuing thread's per-plane
                                 // bookkeeping and the four epilogue warps, profiles/r02_m_first_layer.txt)
+    bool ccl_prune = true;      // CC merge: skip unions implied by the predecessor rows' own unions (DLV_CCL_PRUNE)
     bool ccl_bbox_check = true; // CC statistics: read a component's box before sending min / max reductions to it (DLV_CCL_BBOX_CHECK)
+    int deconv_stages = 8;      // k2s2 deconvs: smem pipeline depth (DLV_DECONV_STAGES; 2 = the previous kernel)
     int deconv_epi = 3;         // k2s2 deconvs: 1 = four epilogue warps, 2 = eight, 3 = eight + pipelined TMEM loads (DLV_DECONV_EPI)
     int is_nsub = 1;            // 64 -> 32 layers: planes staged whole (1) or in two half-plane stages (2, DLV_IS_NSUB)
     int is_tiles_xf = 4;        // same for the 32 -> 32 layers that normalise while staging (DLV_IS_TX): four-tile columns
@@ -92,7 +94,6 @@ struct Ctx {
     uint32_t* paint_owner = nullptr;   // painter scratch (dlv_paint.cu), all-zero between calls when paint_owner_clean
     size_t paint_owner_cap = 0;        // voxels
     bool paint_owner_clean = false;
-    bool paint_resolve_boxes = true;   // painter resolve: memset + second walk over the boxes (default) or the streaming kernel (DLV_PAINT_RESOLVE=1)
 };
 
 void set_error(Ctx* ctx, const char* fmt, ...);

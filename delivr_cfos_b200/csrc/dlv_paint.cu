@@ -11,10 +11,12 @@
 // Two HBM-bound byte passes per z-chunk:
 //   paint_owner_*    box k -> atomicMax(owner[v], k + 1) over its foreground voxels (one warp per small box, the
 //                    whole grid per large box), which makes the result independent of scheduling;
-//   paint_resolve_*  outputs cleared by memsets, then the boxes are walked again: the voxel whose owner entry names the
-//                    box takes the box's values; owner entries are reset on the way, so the scratch is cleared once,
-//                    not once per chunk.  (paint_resolve_kernel, DLV_PAINT_RESOLVE=1: the earlier single streaming
-//                    pass over mask + outputs, kept for A/B measurements.)
+//   paint_resolve    owner -> value lookup -> coalesced, vectorised store of the nch output volumes; owner entries
+//                    are reset on the way, so the scratch is cleared once, not once per chunk.
+//                    (Measured alternative, round 2: outputs cleared by memsets + a second walk over the boxes that
+//                    paints the voxels whose owner entry names the box - no pass over the background at all - was
+//                    SLOWER on cfg3, 23.7 vs 17.5 ms per call: the box walk pays an integer division and scattered
+//                    byte accesses per box voxel twice.  profiles/r02_y_bench_cfg3*.json)
 // Algorithmic bytes per voxel: 1 (mask) + nch * elem_bytes (outputs); the owner scratch (4 B, touched only around
 // foreground) is overhead counted against the achieved fraction.
 #include <limits.h>
@@ -147,65 +149,6 @@ __global__ void paint_resolve_kernel(const uint8_t* __restrict__ mask, uint32_t*
         if (m) { o = owner[v]; if (o) owner[v] = 0; }
         for (int c = 0; c < nch; ++c)
             static_cast<T*>(out.p[c])[v] = o ? static_cast<T>(m * values[static_cast<int64_t>(o - 1) * nch + c]) : T(0);
-    }
-}
-
-// Box-driven resolve (the default, DLV_PAINT_RESOLVE=2): the outputs are cleared by memsets (full-rate writes) and the
-// boxes are walked a second time exactly like in paint_owner_*: the voxel whose owner entry names THIS box (k + 1) is
-// painted with the box's values and its owner entry reset.  Every owned voxel belongs to exactly one box, so the writes
-// never race; the mask is only read inside the boxes and no pass touches the 98 % background of a blob volume except
-// the memsets.  (The streaming kernel above reads the whole mask and serves the foreground groups of a warp one after
-// the other behind a dependent owner load: 8.3 ms on cfg3 = 2.0 TB/s, profiles/r01_h_hbm_kernels_sol.txt.)
-template <typename T>
-__device__ __forceinline__ void paint_resolve_voxel(const uint8_t* __restrict__ mask, uint32_t* __restrict__ owner, int64_t v, uint32_t tag,
-                                                    const uint16_t* __restrict__ val, int nch, const PaintOut& out) {
-    const uint32_t m = mask[v];
-    if (!m) return;
-    if (owner[v] != tag) return;
-    owner[v] = 0u;
-    for (int c = 0; c < nch; ++c) static_cast<T*>(out.p[c])[v] = static_cast<T>(m * val[c]);
-}
-template <typename T>
-__global__ void paint_resolve_small_kernel(const uint8_t* __restrict__ mask, const int32_t* __restrict__ boxes, int64_t n, int64_t Z,
-                                           PaintGeom g, uint32_t* __restrict__ owner, const uint16_t* __restrict__ values, int nch,
-                                           PaintOut out) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-    for (int64_t k = warp0; k < n; k += nwarps) {
-        int64_t za, zb, ya, yb, xa, xb;
-        if (!clip_box(boxes + k * 6, g, Z, za, zb, ya, yb, xa, xb)) continue;
-        const int64_t bx = xb - xa, by = yb - ya, vol = (zb - za) * by * bx;
-        if (vol > kPaintBigBox) continue;                     // on the `big` list, painted by paint_resolve_big_kernel
-        const int ibx = static_cast<int>(bx), iby = static_cast<int>(by), ivol = static_cast<int>(vol);
-        const uint16_t* val = values + k * nch;
-        for (int i = lane; i < ivol; i += 32) {
-            const int r = i / ibx, dx = i - r * ibx;
-            const int dz = r / iby, dy = r - dz * iby;
-            const int64_t v = ((za + dz - g.z0) * g.Y + (ya + dy)) * g.X + (xa + dx);
-            paint_resolve_voxel<T>(mask, owner, v, static_cast<uint32_t>(k + 1), val, nch, out);
-        }
-    }
-}
-template <typename T>
-__global__ void paint_resolve_big_kernel(const uint8_t* __restrict__ mask, const int32_t* __restrict__ boxes, int64_t Z, PaintGeom g,
-                                         uint32_t* __restrict__ owner, const uint32_t* __restrict__ big, const uint32_t* __restrict__ nbig,
-                                         const uint16_t* __restrict__ values, int nch, PaintOut out) {
-    const uint32_t nb = *nbig;
-    const int64_t t0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const int64_t nt = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    for (uint32_t j = 0; j < nb; ++j) {
-        const int64_t k = big[j];
-        int64_t za, zb, ya, yb, xa, xb;
-        clip_box(boxes + k * 6, g, Z, za, zb, ya, yb, xa, xb);
-        const int64_t bx = xb - xa, by = yb - ya, vol = (zb - za) * by * bx;
-        const uint16_t* val = values + k * nch;
-        for (int64_t i = t0; i < vol; i += nt) {
-            const int64_t r = i / bx, dx = i - r * bx;
-            const int64_t dz = r / by, dy = r - dz * by;
-            const int64_t v = ((za + dz - g.z0) * g.Y + (ya + dy)) * g.X + (xa + dx);
-            paint_resolve_voxel<T>(mask, owner, v, static_cast<uint32_t>(k + 1), val, nch, out);
-        }
     }
 }
 
@@ -369,25 +312,11 @@ int paint_boxes(Ctx* ctx, const void* mask_any, const int64_t shape[3], const in
             ctx->launches += 2;
         }
         mark("owner kernels");
-        if (ctx->paint_resolve_boxes) {
-            for (int c = 0; c < nch; ++c) PAINT_OK(cudaMemsetAsync(po.p[c], 0, static_cast<size_t>(nv) * elem_bytes, ctx->stream));
-            if (n > 0) {
-                if (elem_bytes == 1) {
-                    paint_resolve_small_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>(m, boxes, n, Z, g, owner, values, nch, po);
-                    paint_resolve_big_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>(m, boxes, Z, g, owner, big, nbig, values, nch, po);
-                } else {
-                    paint_resolve_small_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(m, boxes, n, Z, g, owner, values, nch, po);
-                    paint_resolve_big_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(m, boxes, Z, g, owner, big, nbig, values, nch, po);
-                }
-                ctx->launches += 2;
-            }
-        } else {
-            int vec = (reinterpret_cast<uintptr_t>(m) & 15u) == 0;       // the owner scratch is always aligned
-            for (int c = 0; c < nch; ++c) vec = vec && (reinterpret_cast<uintptr_t>(po.p[c]) & 15u) == 0;
-            if (elem_bytes == 1) paint_resolve_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>(m, owner, nv, values, nch, po, vec);
-            else paint_resolve_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(m, owner, nv, values, nch, po, vec);
-            ctx->launches += 1;
-        }
+        int vec = (reinterpret_cast<uintptr_t>(m) & 15u) == 0;       // the owner scratch is always aligned
+        for (int c = 0; c < nch; ++c) vec = vec && (reinterpret_cast<uintptr_t>(po.p[c]) & 15u) == 0;
+        if (elem_bytes == 1) paint_resolve_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>(m, owner, nv, values, nch, po, vec);
+        else paint_resolve_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(m, owner, nv, values, nch, po, vec);
+        ctx->launches += 1;
         mark("resolve kernel");
         for (int c = 0; c < nch; ++c)
             if (!out_dev[c])

@@ -512,7 +512,11 @@ static int run_conv(Ctx* ctx, const ConvLayer& Ly, const Level& L, int nwin, con
     const int grid = std::min<int64_t>(ctx->num_sms, a.nitems);
     a.items_per_cta = (a.nitems + grid - 1) / grid;
     const int grid2 = (a.nitems + a.items_per_cta - 1) / a.items_per_cta;
-    const uint32_t smem = kConvStages * a.stage_bytes + 256;
+    a.nstages = kConvStages;
+    if (!conv) {
+        a.nstages = std::max(kConvStages, std::min({kConvStagesMax, ctx->deconv_stages, static_cast<int>((kSmemLimit - 256) / a.stage_bytes)}));
+    }
+    const uint32_t smem = a.nstages * a.stage_bytes + 256;
     if (ctx->time_convs) cudaEventRecord(ctx->ev0, ctx->stream);
     int rc;
     if (conv) {
