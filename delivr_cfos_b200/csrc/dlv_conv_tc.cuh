@@ -13,12 +13,14 @@
 //   * B operand: weights pre-packed on the host into the same canonical layout, one bulk copy per stage.
 //   * D: fp32 accumulators in TMEM, T tiles x NBLK columns, double-buffered (2 x 256 columns) so the
 //     epilogue of item i overlaps the MMAs of item i+1.
-// Warp roles: one TMA producer warp, one MMA issuer warp (one thread), 4 x EPI epilogue warps
-// (TMEM -> registers -> bf16 global stores + InstanceNorm partial sums).  The k2s2 transposed convolutions are one
-// N = 256 MMA per cin block and 512 B of output per input voxel: their epilogue, not the MMA, is the critical path
-// (4 500 - 6 200 clk per 128-position tile with four warps = 3.6 TB/s on the last one), so they run with EPI = 2 (two
-// warps per TMEM lane quadrant, each draining half of the 256 columns) and keep the next tcgen05.ld in flight while
-// the current 32 columns are converted and stored.
+// Warp roles: one TMA producer warp, one MMA issuer warp (one thread), 4 epilogue warps
+// (TMEM -> registers -> bf16 global stores + InstanceNorm partial sums).
+// The k2s2 transposed convolutions are one N = 256 MMA per cin block and 512 B of output per input voxel.  Measured in
+// round 2 (profiles/r02_y_*, r02_z_*): eight epilogue warps (two per TMEM lane quadrant) and a software-pipelined
+// tcgen05.ld changed nothing on the large last deconv (1.49 -> 1.63 ms: its 4.8 GB of 1 KB output rows run at 3.6-3.8 TB/s
+// whatever the epilogue does) and were removed again; a deeper shared-memory pipeline (8 stages of 12 KB instead of 2)
+// takes 8-20 % off the three small deconvs, which wait for TMA round trips, and slows the large one (more 1 KB write
+// streams in flight) - so the depth is chosen per launch (ConvArgs::nstages).
 #pragma once
 #include "dlv_common.cuh"
 
@@ -62,18 +64,11 @@ struct ConvArgs {
     int oYp, oXp, oVp;          // mode 1: geometry of the finer output level
 };
 
-template <int NBLK, int NTAPS, int MODE, int EPI = 1, bool PIPE = false>
-__global__ void __launch_bounds__(kConvThreads + (EPI - 1) * 128, 1) conv_tc_kernel(const ConvArgs p) {
+template <int NBLK, int NTAPS, int MODE>
+__global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int NRUNS = (NTAPS == 27) ? 3 : 1;
-    static_assert(EPI == 1 || (EPI == 2 && MODE == kModeDeconvScatter && NBLK == 256), "second epilogue warp set: deconv only");
-#ifndef DLV_IS_LEGACY_ROLES
-    // epilogue warps 0 .. 4*EPI-1 (TMEM lane quadrant = warp & 3), then the producer and the MMA issuer
-    constexpr int kWarpProducer = 4 * EPI, kWarpMma = 4 * EPI + 1;
-#else
-    static_assert(EPI == 1, "legacy warp roles: one epilogue set");
     constexpr int kWarpProducer = kTcWarpProducer, kWarpMma = kTcWarpMma;
-#endif
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.nstages * p.stage_bytes);
     uint64_t* full = bars;                       // [stages] TMA -> MMA
     uint64_t* empty = bars + p.nstages;          // [stages] MMA -> TMA
@@ -86,7 +81,7 @@ __global__ void __launch_bounds__(kConvThreads + (EPI - 1) * 128, 1) conv_tc_ker
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.nstages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4 * EPI); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
         fence_mbar_init();
     }
     if (warp == kWarpMma) tmem_alloc(tmem_slot, kTmemCols);
@@ -174,9 +169,8 @@ __global__ void __launch_bounds__(kConvThreads + (EPI - 1) * 128, 1) conv_tc_ker
             }
         }
     } else {
-        // ------------------------------------------------------------ epilogue (4 warps = 4 TMEM lane quadrants, x EPI)
+        // ------------------------------------------------------------ epilogue (4 warps = 4 TMEM lane quadrants)
         const int q = warp & 3;
-        const int eset = (EPI == 2) ? (warp >> 2) : 0;      // which half of the accumulator columns this warp drains
         int it = 0;
         int cur_key = -1;           // win * NB + nb of the running statistics
         double run_s[NBLK / 32], run_q[NBLK / 32];
@@ -251,25 +245,13 @@ __global__ void __launch_bounds__(kConvThreads + (EPI - 1) * 128, 1) conv_tc_ker
                     // transposed conv k2 s2: the N = 256 accumulator of this input voxel holds all 8 output
                     // sub-positions; block h = (a, b, jp) carries chunks j = 2 jp, 2 jp + 1, each as the x-even
                     // and x-odd output voxel side by side (pack_deconv) -> 2 x 16 B contiguous stores per chunk.
-                    // Two register sets: the load of block h + 1 is in flight while block h is converted and stored.
-                    constexpr int HPS = NBLK / 32 / EPI;        // 32-column blocks per epilogue warp
-                    const int h0 = eset * HPS;
                     const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 256 + t * NBLK;
                     const int64_t Pw = static_cast<int64_t>(win) * p.oVp;
-                    uint32_t r[PIPE ? 2 : 1][32];
-                    if (PIPE) tmem_ld32_issue(tcol + h0 * 32, r[0]);
 #pragma unroll
-                    for (int hh = 0; hh < HPS; ++hh) {
-                        constexpr int kSets = PIPE ? 2 : 1;
-                        if (PIPE) {
-                            tmem_ld32_fence(r[hh % kSets]);
-                            if (hh + 1 < HPS) tmem_ld32_issue(tcol + (h0 + hh + 1) * 32, r[(hh + 1) % kSets]);
-                        } else {
-                            tmem_ld32_issue(tcol + (h0 + hh) * 32, r[0]);
-                            tmem_ld32_fence(r[0]);
-                        }
+                    for (int h = 0; h < NBLK / 32; ++h) {
+                        float v[32];
+                        tmem_ld32(tcol + h * 32, v);
                         if (valid) {
-                            const int h = h0 + hh;
                             const int a = h >> 2, b = (h >> 1) & 1, jp = h & 1;
                             const int oz = 2 * (zp - 1) + a + 1;
                             const int oy = 2 * (yp - 1) + b + 1;
@@ -281,13 +263,13 @@ __global__ void __launch_bounds__(kConvThreads + (EPI - 1) * 128, 1) conv_tc_ker
                                 __nv_bfloat16* o = p.out + (static_cast<int64_t>(nb * 4 + j) * p.outS + p.out_guard + Po) * 8;
 #pragma unroll
                                 for (int c = 0; c < 2; ++c) {
-                                    const uint32_t* vv = r[hh % kSets] + (jl * 2 + c) * 8;
+                                    const float* vv = v + (jl * 2 + c) * 8;
                                     const float* bb = bsr + j * 8;
                                     uint4 u;
-                                    u.x = pack_bf16x2(__uint_as_float(vv[0]) + bb[0], __uint_as_float(vv[1]) + bb[1]);
-                                    u.y = pack_bf16x2(__uint_as_float(vv[2]) + bb[2], __uint_as_float(vv[3]) + bb[3]);
-                                    u.z = pack_bf16x2(__uint_as_float(vv[4]) + bb[4], __uint_as_float(vv[5]) + bb[5]);
-                                    u.w = pack_bf16x2(__uint_as_float(vv[6]) + bb[6], __uint_as_float(vv[7]) + bb[7]);
+                                    u.x = pack_bf16x2(vv[0] + bb[0], vv[1] + bb[1]);
+                                    u.y = pack_bf16x2(vv[2] + bb[2], vv[3] + bb[3]);
+                                    u.z = pack_bf16x2(vv[4] + bb[4], vv[5] + bb[5]);
+                                    u.w = pack_bf16x2(vv[6] + bb[6], vv[7] + bb[7]);
                                     *reinterpret_cast<uint4*>(o + c * 8) = u;
                                 }
                             }

@@ -96,7 +96,7 @@ struct PaintOut {
 
 // Resolve.  Each lane takes 16 consecutive voxels: one 16 B mask load and 16 B (uint8) / 2 x 16 B (uint16) streaming
 // ZERO stores per channel - 98 % of a blob volume is background and this is all that happens there.  Lanes whose 16
-// voxels contain foreground are then served one after the other by the first 16 lanes of the warp, one voxel per
+// voxels contain foreground are then served two at a time by the two half-warps, one voxel per
 // lane: owner lookup + reset, value lookup, element store over the zeros (ordered by __syncwarp).  Doing the 16 x nch
 // conditional look-ups inside the lane that owns the group made nearly every warp walk ~600 predicated instructions
 // (1.5-1.8 TB/s, instruction-bound).  `n16` whole groups when every pointer of the chunk is 16 B aligned (vec),
@@ -124,21 +124,39 @@ __global__ void paint_resolve_kernel(const uint8_t* __restrict__ mask, uint32_t*
         if (!pending) continue;
         __syncwarp();                                        // the zero stores above precede the element stores below
         while (pending) {
-            const int src = __ffs(pending) - 1;
-            pending &= pending - 1;
-            const uint32_t mx = __shfl_sync(0xffffffffu, m4.x, src), my = __shfl_sync(0xffffffffu, m4.y, src);
-            const uint32_t mz = __shfl_sync(0xffffffffu, m4.z, src), mw = __shfl_sync(0xffffffffu, m4.w, src);
-            if (lane < 16) {
-                const uint32_t word = (lane & 8) ? ((lane & 4) ? mw : mz) : ((lane & 4) ? my : mx);
-                const uint32_t mb = (word >> (8 * (lane & 3))) & 0xFFu;
-                if (mb) {
-                    const int64_t v = ((qb + src) << 4) + lane;
-                    const uint32_t o = owner[v];
-                    if (o) {
-                        owner[v] = 0u;
-                        for (int c = 0; c < nch; ++c)
-                            static_cast<T*>(out.p[c])[v] = static_cast<T>(mb * values[static_cast<int64_t>(o - 1) * nch + c]);
-                    }
+            // Two groups per round, one per half-warp, and kRounds rounds per pass: the owner loads of a pass are all
+            // issued before the first of them is used.  A round is a dependent chain (owner load -> value load ->
+            // store) of DRAM / L2 round trips, so the number of chains walked one after the other - not the work in
+            // them - is what the foreground costs (one group per round: 8.5 ms on cfg3, 2.9 TB/s).
+            constexpr int kRounds = 4;
+            uint32_t o[kRounds], mbv[kRounds];
+            int64_t vv[kRounds];
+#pragma unroll
+            for (int r = 0; r < kRounds; ++r) {
+                o[r] = 0u; mbv[r] = 0u; vv[r] = 0;
+                if (!pending) continue;                              // warp-uniform
+                const int s0 = __ffs(pending) - 1;
+                pending &= pending - 1;
+                const int s1 = pending ? __ffs(pending) - 1 : -1;
+                if (s1 >= 0) pending &= pending - 1;
+                const int src = (lane < 16) ? s0 : s1;
+                const int from = src < 0 ? lane : src;
+                const uint32_t mx = __shfl_sync(0xffffffffu, m4.x, from), my = __shfl_sync(0xffffffffu, m4.y, from);
+                const uint32_t mz = __shfl_sync(0xffffffffu, m4.z, from), mw = __shfl_sync(0xffffffffu, m4.w, from);
+                if (src >= 0) {
+                    const int l16 = lane & 15;
+                    const uint32_t word = (l16 & 8) ? ((l16 & 4) ? mw : mz) : ((l16 & 4) ? my : mx);
+                    mbv[r] = (word >> (8 * (l16 & 3))) & 0xFFu;
+                    vv[r] = ((qb + src) << 4) + l16;
+                    if (mbv[r]) o[r] = owner[vv[r]];
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < kRounds; ++r) {
+                if (o[r]) {
+                    owner[vv[r]] = 0u;
+                    for (int c = 0; c < nch; ++c)
+                        static_cast<T*>(out.p[c])[vv[r]] = static_cast<T>(mbv[r] * values[static_cast<int64_t>(o[r] - 1) * nch + c]);
                 }
             }
         }

@@ -454,15 +454,15 @@ int net_load(Ctx* ctx, int n, const char* const* names, const float* const* data
 }
 
 // ------------------------------------------------------------------- conv launcher
-template <int NBLK, int NTAPS, int MODE, int EPI = 1, bool PIPE = false>
+template <int NBLK, int NTAPS, int MODE>
 static int launch_conv_t(Ctx* ctx, const ConvArgs& a, int grid, uint32_t smem) {
-    auto k = conv_tc_kernel<NBLK, NTAPS, MODE, EPI, PIPE>;
+    auto k = conv_tc_kernel<NBLK, NTAPS, MODE>;
     static bool attr_set = false;
     if (!attr_set) {
         DLV_CUDA_OK(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
         attr_set = true;
     }
-    k<<<grid, kConvThreads + (EPI - 1) * 128, smem, ctx->stream>>>(a);
+    k<<<grid, kConvThreads, smem, ctx->stream>>>(a);
     ctx->launches++;
     DLV_CUDA_OK(ctx, cudaGetLastError());
     return 0;
@@ -514,7 +514,13 @@ static int run_conv(Ctx* ctx, const ConvLayer& Ly, const Level& L, int nwin, con
     const int grid2 = (a.nitems + a.items_per_cta - 1) / a.items_per_cta;
     a.nstages = kConvStages;
     if (!conv) {
-        a.nstages = std::max(kConvStages, std::min({kConvStagesMax, ctx->deconv_stages, static_cast<int>((kSmemLimit - 256) / a.stage_bytes)}));
+        // Deconv stages are 12 KB and one MMA each.  The small launches wait for TMA round trips with two of them in flight
+        // (8 stages: 78 -> 72, 117 -> 92, 292 -> 248 us per 128-window batch of cfg2); the one that writes the level-0
+        // tensor (4.8 GB) is bound by its 1 KB write streams and slows down with more of them in flight (1.49 -> 1.80 ms),
+        // so the depth follows the size of the output per window (profiles/r02_z_launches_cfg2.txt vs r02_h_launches_cfg2.txt).
+        const double out_bytes_per_window = static_cast<double>(L.Vp) * 8.0 * Ly.cout * 2.0;      // 42 MB vs 5.9 / 1.8 / 0.6 MB on 96x96x64 windows
+        const int want = ctx->deconv_stages > 0 ? ctx->deconv_stages : (out_bytes_per_window > 16e6 ? kConvStages : 8);
+        a.nstages = std::max(kConvStages, std::min({kConvStagesMax, want, static_cast<int>((kSmemLimit - 256) / a.stage_bytes)}));
     }
     const uint32_t smem = a.nstages * a.stage_bytes + 256;
     if (ctx->time_convs) cudaEventRecord(ctx->ev0, ctx->stream);
@@ -523,11 +529,7 @@ static int run_conv(Ctx* ctx, const ConvLayer& Ly, const Level& L, int nwin, con
         rc = (Ly.nblk == 32) ? launch_conv_t<32, 27, kModeConvStats>(ctx, a, grid2, smem)
                              : launch_conv_t<64, 27, kModeConvStats>(ctx, a, grid2, smem);
     } else {
-        // epilogue-bound: two epilogue warp sets with the next TMEM load in flight (dlv_conv_tc.cuh); DLV_DECONV_EPI
-        // = 1 / 2 select the single-set kernel / two sets without the software pipeline (kept for A/B measurements)
-        rc = (ctx->deconv_epi <= 1) ? launch_conv_t<256, 1, kModeDeconvScatter>(ctx, a, grid2, smem)
-           : (ctx->deconv_epi == 2) ? launch_conv_t<256, 1, kModeDeconvScatter, 2, false>(ctx, a, grid2, smem)
-                                    : launch_conv_t<256, 1, kModeDeconvScatter, 2, true>(ctx, a, grid2, smem);
+        rc = launch_conv_t<256, 1, kModeDeconvScatter>(ctx, a, grid2, smem);
     }
     if (ctx->time_convs && rc == 0) {
         cudaEventRecord(ctx->ev1, ctx->stream);
