@@ -60,6 +60,7 @@ int dlv_init(int device, dlv_ctx** out) {
     if (const char* e = getenv("DLV_IS_NSUB")) ctx->is_nsub = atoi(e);
     if (const char* e = getenv("DLV_IS_TF")) ctx->is_tiles_fold = atoi(e);
     if (const char* e = getenv("DLV_DECONV_STAGES")) ctx->deconv_stages = atoi(e);
+    if (const char* e = getenv("DLV_DECONV_XSTORE")) ctx->deconv_xstore = atoi(e) != 0;
     if (const char* e = getenv("DLV_CCL_BBOX_CHECK")) ctx->ccl_bbox_check = atoi(e) != 0;
     if (const char* e = getenv("DLV_CCL_PRUNE")) ctx->ccl_prune = atoi(e) != 0;
     DLV_CUDA_OK(ctx, cudaSetDevice(device));

@@ -64,7 +64,7 @@ struct ConvArgs {
     int oYp, oXp, oVp;          // mode 1: geometry of the finer output level
 };
 
-template <int NBLK, int NTAPS, int MODE>
+template <int NBLK, int NTAPS, int MODE, bool XSTORE = false>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int NRUNS = (NTAPS == 27) ? 3 : 1;
@@ -246,6 +246,57 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvArgs
                     // sub-positions; block h = (a, b, jp) carries chunks j = 2 jp, 2 jp + 1, each as the x-even
                     // and x-odd output voxel side by side (pack_deconv) -> 2 x 16 B contiguous stores per chunk.
                     const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 256 + t * NBLK;
+                    if (XSTORE) {
+                        // Lane l holds the 32 B (x-even | x-odd output voxel) of input voxel l for every output row; stored as
+                        // two 16 B halves per lane, a warp store covers 1 KB in half-used sectors (8 wavefronts, 32 partial
+                        // sector writes) and the store queue, not HBM, bounded the large deconv (ncu: L1/TEX 64 % busy, the
+                        // next LDTM waiting for the stores to drain, DRAM 46 %).  Here the halves are exchanged by shuffles so
+                        // that every store instruction writes 512 contiguous bytes: instruction cp serves the input voxels of
+                        // lanes 16 cp .. 16 cp + 15, lane l writes half (l & 1) of source lane 16 cp + l / 2.
+                        const int half = lane & 1;
+                        int64_t sbase[2];       // output position of source voxel's (a = 0, b = 0, x-even) corner, + half
+                        bool svalid[2];
+#pragma unroll
+                        for (int cp = 0; cp < 2; ++cp) {
+                            const int src = 16 * cp + (lane >> 1);
+                            const int swin = __shfl_sync(0xffffffffu, win, src), szp = __shfl_sync(0xffffffffu, zp, src);
+                            const int syp = __shfl_sync(0xffffffffu, yp, src), sxp = __shfl_sync(0xffffffffu, xp, src);
+                            svalid[cp] = (vmask >> src) & 1u;
+                            sbase[cp] = static_cast<int64_t>(swin) * p.oVp + (static_cast<int64_t>(2 * (szp - 1) + 1) * p.oYp + (2 * (syp - 1) + 1)) * p.oXp
+                                        + (2 * (sxp - 1) + 1) + half;
+                        }
+#pragma unroll
+                        for (int h = 0; h < NBLK / 32; ++h) {
+                            float v[32];
+                            tmem_ld32(tcol + h * 32, v);
+                            const int a = h >> 2, b = (h >> 1) & 1, jp = h & 1;
+                            const int64_t orow = (static_cast<int64_t>(a) * p.oYp + b) * p.oXp;
+#pragma unroll
+                            for (int jl = 0; jl < 2; ++jl) {
+                                const int j = jp * 2 + jl;
+                                const float* bb = bsr + j * 8;
+                                uint32_t u[2][4];       // [x-even | x-odd][4 packed channel pairs] of this lane's input voxel
+#pragma unroll
+                                for (int c = 0; c < 2; ++c) {
+                                    const float* vv = v + (jl * 2 + c) * 8;
+#pragma unroll
+                                    for (int w = 0; w < 4; ++w) u[c][w] = pack_bf16x2(vv[2 * w] + bb[2 * w], vv[2 * w + 1] + bb[2 * w + 1]);
+                                }
+                                __nv_bfloat16* orow_ptr = p.out + (static_cast<int64_t>(nb * 4 + j) * p.outS + p.out_guard + orow) * 8;
+#pragma unroll
+                                for (int cp = 0; cp < 2; ++cp) {
+                                    const int src = 16 * cp + (lane >> 1);
+                                    uint32_t x[4];
+#pragma unroll
+                                    for (int w = 0; w < 4; ++w) {
+                                        const uint32_t e = __shfl_sync(0xffffffffu, u[0][w], src), o = __shfl_sync(0xffffffffu, u[1][w], src);
+                                        x[w] = half ? o : e;
+                                    }
+                                    if (svalid[cp]) *reinterpret_cast<uint4*>(orow_ptr + sbase[cp] * 8) = make_uint4(x[0], x[1], x[2], x[3]);
+                                }
+                            }
+                        }
+                    } else {
                     const int64_t Pw = static_cast<int64_t>(win) * p.oVp;
 #pragma unroll
                     for (int h = 0; h < NBLK / 32; ++h) {
@@ -274,6 +325,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvArgs
                                 }
                             }
                         }
+                    }
                     }
                 }
             }

@@ -79,6 +79,7 @@ struct Ctx {
                                 // bookkeeping and the four epilogue warps, profiles/r02_m_first_layer.txt)
     bool ccl_prune = true;      // CC merge: skip unions implied by the predecessor rows' own unions (DLV_CCL_PRUNE)
     bool ccl_bbox_check = true; // CC statistics: read a component's box before sending min / max reductions to it (DLV_CCL_BBOX_CHECK)
+    bool deconv_xstore = true;  // k2s2 deconvs: output halves exchanged by shuffles so that every store covers 512 contiguous bytes (DLV_DECONV_XSTORE)
     int deconv_stages = 0;      // k2s2 deconvs: smem pipeline depth; 0 = by output size (2 or 8), DLV_DECONV_STAGES forces it
     int is_nsub = 1;            // 64 -> 32 layers: planes staged whole (1) or in two half-plane stages (2, DLV_IS_NSUB)
     int is_tiles_xf = 4;        // same for the 32 -> 32 layers that normalise while staging (DLV_IS_TX): four-tile columns

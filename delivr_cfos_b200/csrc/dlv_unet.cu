@@ -454,9 +454,9 @@ int net_load(Ctx* ctx, int n, const char* const* names, const float* const* data
 }
 
 // ------------------------------------------------------------------- conv launcher
-template <int NBLK, int NTAPS, int MODE>
+template <int NBLK, int NTAPS, int MODE, bool XSTORE = false>
 static int launch_conv_t(Ctx* ctx, const ConvArgs& a, int grid, uint32_t smem) {
-    auto k = conv_tc_kernel<NBLK, NTAPS, MODE>;
+    auto k = conv_tc_kernel<NBLK, NTAPS, MODE, XSTORE>;
     static bool attr_set = false;
     if (!attr_set) {
         DLV_CUDA_OK(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
@@ -529,7 +529,8 @@ static int run_conv(Ctx* ctx, const ConvLayer& Ly, const Level& L, int nwin, con
         rc = (Ly.nblk == 32) ? launch_conv_t<32, 27, kModeConvStats>(ctx, a, grid2, smem)
                              : launch_conv_t<64, 27, kModeConvStats>(ctx, a, grid2, smem);
     } else {
-        rc = launch_conv_t<256, 1, kModeDeconvScatter>(ctx, a, grid2, smem);
+        rc = ctx->deconv_xstore ? launch_conv_t<256, 1, kModeDeconvScatter, true>(ctx, a, grid2, smem)
+                                : launch_conv_t<256, 1, kModeDeconvScatter, false>(ctx, a, grid2, smem);
     }
     if (ctx->time_convs && rc == 0) {
         cudaEventRecord(ctx->ev1, ctx->stream);
