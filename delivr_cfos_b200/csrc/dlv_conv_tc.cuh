@@ -15,12 +15,16 @@
 //     epilogue of item i overlaps the MMAs of item i+1.
 // Warp roles: one TMA producer warp, one MMA issuer warp (one thread), 4 epilogue warps
 // (TMEM -> registers -> bf16 global stores + InstanceNorm partial sums).
-// The k2s2 transposed convolutions are one N = 256 MMA per cin block and 512 B of output per input voxel.  Measured in
-// round 2 (profiles/r02_y_*, r02_z_*): eight epilogue warps (two per TMEM lane quadrant) and a software-pipelined
-// tcgen05.ld changed nothing on the large last deconv (1.49 -> 1.63 ms: its 4.8 GB of 1 KB output rows run at 3.6-3.8 TB/s
-// whatever the epilogue does) and were removed again; a deeper shared-memory pipeline (8 stages of 12 KB instead of 2)
-// takes 8-20 % off the three small deconvs, which wait for TMA round trips, and slows the large one (more 1 KB write
-// streams in flight) - so the depth is chosen per launch (ConvArgs::nstages).
+// The k2s2 transposed convolutions are one N = 256 MMA per cin block and 512 B of output per input voxel; their epilogue
+// is the critical path.  Measured in round 2 on one 128-window batch of cfg2 (profiles/r02_y_*, r02_z_*, r02_aa_*, r02_ab_*):
+//   * eight epilogue warps and a software-pipelined tcgen05.ld: no gain (the next LDTM was waiting for the STOREs of the
+//     previous block to drain, not for TMEM) - removed again;
+//   * ncu --set full of the large (level 1 -> 0) deconv: L1/TEX 64 % busy, DRAM 46 %; each lane stored its 32 B as two
+//     16 B halves, so a warp store covered 1 KB in half-used sectors.  With the halves exchanged by shuffles (XSTORE)
+//     every store writes 512 contiguous bytes: 1.49 -> 1.39 ms, 248 -> 212 us on the next smaller one;
+//   * shared-memory pipeline 8 stages deep instead of 2 (a stage is 12 KB and one MMA): 8-20 % off the three small
+//     deconvs, which wait for TMA round trips, but the large one slows down (1.39 -> 1.48 ms: more 1 KB write streams in
+//     flight) - the depth is chosen per launch (ConvArgs::nstages).
 #pragma once
 #include "dlv_common.cuh"
 
@@ -247,12 +251,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const ConvArgs
                     // and x-odd output voxel side by side (pack_deconv) -> 2 x 16 B contiguous stores per chunk.
                     const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 256 + t * NBLK;
                     if (XSTORE) {
-                        // Lane l holds the 32 B (x-even | x-odd output voxel) of input voxel l for every output row; stored as
-                        // two 16 B halves per lane, a warp store covers 1 KB in half-used sectors (8 wavefronts, 32 partial
-                        // sector writes) and the store queue, not HBM, bounded the large deconv (ncu: L1/TEX 64 % busy, the
-                        // next LDTM waiting for the stores to drain, DRAM 46 %).  Here the halves are exchanged by shuffles so
-                        // that every store instruction writes 512 contiguous bytes: instruction cp serves the input voxels of
-                        // lanes 16 cp .. 16 cp + 15, lane l writes half (l & 1) of source lane 16 cp + l / 2.
+                        // Lane l holds the 32 B (x-even | x-odd output voxel) of input voxel l for every output row.  The halves
+                        // are exchanged by shuffles so that every store instruction writes 512 contiguous bytes: instruction
+                        // cp serves the input voxels of lanes 16 cp .. 16 cp + 15, lane l writes half (l & 1) of source
+                        // lane 16 cp + l / 2 (see the header comment for the measurement).
                         const int half = lane & 1;
                         int64_t sbase[2];       // output position of source voxel's (a = 0, b = 0, x-even) corner, + half
                         bool svalid[2];
