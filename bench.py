@@ -158,6 +158,21 @@ SAMPLE_DESC = (f"{CPU_SAMPLE[0]}x{CPU_SAMPLE[1]}x{CPU_SAMPLE[2]} crop-sized volu
                "1 pass + binarise + CC")
 
 
+def reference_input(workload):
+    """What the CPU arm runs for a workload -> (padded uint16 volume, real shape, description, same_config).
+    cfg1 (BASELINE.json configs[0], the reference's own CPU-runnable case) is small enough to run WHOLE: the same volume,
+    window, overlap and passes as the product arm's `--workload cfg1` line, so the ratio of the two lines is a
+    same-configuration ratio.  Every other workload is represented by the bounded crop (a whole cfg2 pass would take the
+    16 host cores about 25 minutes)."""
+    wl = WORKLOADS[workload]
+    if workload == "cfg1":
+        from delivr_cfos_b200.synth import synth_volume_cuda        # input data only - the same generator as the product arm's
+        dev = "cuda" if torch.cuda.is_available() else "cpu"
+        vol = synth_volume_cuda(wl["shape"], wl["seed"], roi=ROI, device=dev).cpu().numpy()
+        return vol, tuple(wl["shape"]), f"the WHOLE workload ({wl['name']}, padded to {'x'.join(map(str, vol.shape))}), 1 pass + binarise + CC", True
+    return make_cpu_sample(wl["seed"]), CPU_SAMPLE, SAMPLE_DESC, False
+
+
 class CpuReference:
     """The reference's CPU implementation of the path, timed on a bounded sample.  kind "reference": the reference's
     own files (inference/inference.py::run_inference + count_blobs.py::count_blobs, unmodified, staged under
@@ -176,20 +191,21 @@ class CpuReference:
             self.net.load_state_dict(unet_ref.strip_module_prefix(sd), strict=True)
             self.net.eval()
 
-    def step(self, vol):
-        """-> seconds for one pass over the sample volume."""
+    def step(self, vol, shape_real=None):
+        """-> seconds for one pass over the (padded) sample volume."""
         if self.runner is None:
             return cpu_reference_step(vol, self.net, self.threads)
-        r = self.runner.run(vol, vol.shape, ROI, WEIGHTS, tta=False, sw_batch=2)
+        r = self.runner.run(vol, tuple(shape_real or vol.shape), ROI, WEIGHTS, tta=False, sw_batch=2)
         return r["t_inference"] + r["t_count"]
 
-    def describe(self, vol, t, workload=None):
-        v = vol.size / t / 1e9
+    def describe(self, vol, t, workload=None, shape_real=None, desc=SAMPLE_DESC, same_config=False):
+        v = float(np.prod(shape_real or vol.shape)) / t / 1e9
         d = {"value": v, "unit": "Gvoxels/s", "cores": self.threads, "kind": self.kind,
-             "sample": f"{SAMPLE_DESC}, {t:.1f} s per pass"
-                       + ("; unmodified reference run_inference + count_blobs through oracle/shims" if self.kind == "reference" else "; oracle port")}
+             "sample": f"{desc}, {t:.1f} s per pass"
+                       + ("; unmodified reference run_inference + count_blobs through oracle/shims" if self.kind == "reference" else "; oracle port"),
+             "same_config": bool(same_config)}
         wl = WORKLOADS.get(workload or "", {})
-        if wl.get("active_windows"):
+        if wl.get("active_windows") and not same_config:
             # the sample runs 2.0 active patch-voxels per counted voxel, the workload itself more (every voxel is covered
             # by up to 8 windows): the same CPU rate expressed at the workload's own window density
             dens_s = 6 * ROI[0] * ROI[1] * ROI[2] / vol.size
@@ -206,12 +222,12 @@ def run_reference(args, rank, world):
     sd, wdesc = state_dict()
     ref = CpuReference(sd)
     wl = WORKLOADS[args.workload]
-    vol = make_cpu_sample(wl["seed"])
+    vol, shape_real, desc, same = reference_input(args.workload)
     for _ in range(args.warmup):
-        ref.step(vol)
-    ts = [ref.step(vol) for _ in range(args.steps)]
+        ref.step(vol, shape_real)
+    ts = [ref.step(vol, shape_real) for _ in range(args.steps)]
     t = sum(ts) / len(ts)
-    cb = ref.describe(vol, t, args.workload)
+    cb = ref.describe(vol, t, args.workload, shape_real, desc, same)
     v = cb["value"]
     emit(({
         "impl": "reference", "metric": "Gvoxels/s seg+CC", "value": v, "unit": "Gvoxels/s", "n_gpus": args.gpus,
@@ -219,7 +235,7 @@ def run_reference(args, rank, world):
         "vs_baseline": None, "dtype": "f32", "data": f"synthetic; {wdesc}",
         "config": {"workload": wl["name"], "window": list(ROI), "overlap": OVERLAP, "tta": False,
                    "note": ("the reference's own inference/inference.py + count_blobs.py, unmodified, on the host CPU (fp32 torch, scipy erosion, "
-                            "cc3d stand-in) over a bounded sample per step" if ref.kind == "reference" else
+                            "cc3d stand-in) over " + ("the whole workload per step" if same else "a bounded sample per step") if ref.kind == "reference" else
                             "oracle port of the reference CPU path (torch fp32 U-Net, C erosion + CCL as cc3d stand-in)")},
         "cpu_baseline": cb,
         "e2e": {"value": v, "unit": "Gvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -412,8 +428,8 @@ def main():
             cb["ours_tflops_whole_forward"] = flop / (st["ms_unet"] * 1e-3) / 1e12
         out["roofline"]["cudnn_baseline"] = cb
         ref = CpuReference(sd)
-        sv = make_cpu_sample(wl["seed"])
-        out["cpu_baseline"] = ref.describe(sv, ref.step(sv), args.workload)
+        sv, sreal, sdesc, same = reference_input(args.workload)
+        out["cpu_baseline"] = ref.describe(sv, ref.step(sv, sreal), args.workload, sreal, sdesc, same)
     emit(out)
 
 
