@@ -74,6 +74,23 @@ def load():
     return _MODS
 
 
+class _cpu_only:
+    """The reference picks `cuda` whenever torch sees a GPU (inference.py:156,209) and wraps the model in DataParallel
+    (:217-219), which would move every window batch to the GPU: on a GPU box the "CPU baseline" silently ran its U-Net
+    through cuDNN.  While the reference runs, torch.cuda.is_available() answers False - device = cpu, DataParallel
+    degenerates to a plain call of the module - so the whole path really runs on the host cores."""
+
+    def __enter__(self):
+        import torch
+        self._orig = torch.cuda.is_available
+        torch.cuda.is_available = lambda: False
+
+    def __exit__(self, *exc):
+        import torch
+        torch.cuda.is_available = self._orig
+        return False
+
+
 def run(volume_pad, shape_real, roi, weights, tta=False, sw_batch=4, load_all_ram=True, quiet=True):
     """One full pass of the reference's two stages over one padded uint16 volume.
     -> dict(t_inference, t_count (seconds), binaries, csv, n)."""
@@ -101,9 +118,10 @@ def run(volume_pad, shape_real, roi, weights, tta=False, sw_batch=4, load_all_ra
                     "postprocessing": {"output_location": post_dir}, "FLAGS": {"SAVE_ACTIVATED_OUTPUT": False, "LOAD_ALL_RAM": load_all_ram}}
         t0 = time.perf_counter()
         try:
-            session = ref_inf.run_inference(niftis=[Path(os.path.join(nif_dir, "masked_nifti.npy"))], output_folder=out_dir,
-                                            stack_shape=(1, 1, *shape_real), model_weights=weights, tta=tta, comment=brain,
-                                            load_all_ram=load_all_ram, settings=settings)
+            with _cpu_only():
+                session = ref_inf.run_inference(niftis=[Path(os.path.join(nif_dir, "masked_nifti.npy"))], output_folder=out_dir,
+                                                stack_shape=(1, 1, *shape_real), model_weights=weights, tta=tta, comment=brain,
+                                                load_all_ram=load_all_ram, settings=settings)
         finally:
             os.chdir(cwd)
         t1 = time.perf_counter()
