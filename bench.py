@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py - DELiVR blob_detection hot path on B200: Gvoxels/s of segmentation + connected components.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|small]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|small|cfg3|cfg4|cfg5] [--tta]
 
 A "step" is one full pass of the hot path over one synthetic uint16 volume: sliding-window 3-D U-Net
 (window 96x96x64, overlap 0.5, one pass) -> averaging -> sigmoid/threshold + eroded-mask gate -> 26-connected
@@ -11,8 +11,13 @@ components + size/centroid table.  Metric: unpadded volume voxels / time (BASELI
 * ``e2e``: the same through host buffers (pinned volume in, binaries + table out), copies inside the timing.
 * ``roofline``: the tcgen05 convolution kernels (the one dense contraction): algorithmic FLOP of the active
   windows / summed conv-kernel device time, against MEASURED_PEAKS.json bf16_tflops_sustained.
-* ``cpu_baseline`` / ``--impl reference``: the CPU restatement of the reference (oracle/, torch-fp32 U-Net +
-  C erosion/CCL) on a bounded sample of the same workload, all host threads.
+* ``cpu_baseline`` / ``--impl reference``: the reference's OWN files (inference/inference.py, sliding_window_inferer.py,
+  count_blobs.py; staged unmodified under baseline/_ref by build(), third-party imports through oracle/shims) on the
+  host cores, all threads, with the GPU hidden from them - on a bounded crop of the workload, or on the whole workload
+  for cfg1 (same_config: true).  The oracle port is only the fall-back when the files were not staged (kind "port").
+* N >= 2 (torchrun): weak scaling of cfg2 for the headline plus a ``config.cfg4`` leg (one whole-brain volume sharded
+  over the ranks, TTA off and on); ``--workload cfg5``: the window / overlap sweep; ``--workload cfg3``: CC + table +
+  painter alone (HBM roofline).
 """
 import argparse
 import json
