@@ -143,7 +143,11 @@ class CudaEngine:
         return t.cpu().numpy()
 
 
-_ENGINE_FACTORY = CudaEngine        # tests swap this (or name a factory in DLV_ENGINE for spawned ranks)
+# Test seam, not a fallback: the CPU tests of the host logic (chunking, rank start-up, file contract) install their own
+# engine here - or name its factory in DLV_ENGINE for the rank processes run_inference spawns - so that this module can be
+# exercised without a GPU.  Nothing in the package ever sets either; with neither set the engine is the CUDA library, and
+# a missing .so / non-sm_100 device raises DlvError at the first call (tests/test_cpu_library.py checks both).
+_ENGINE_FACTORY = CudaEngine
 
 
 def _engine_factory():

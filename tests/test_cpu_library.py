@@ -43,6 +43,21 @@ def test_no_cpu_fallback_without_gpu():
         DelivrNet(state_dict={})
 
 
+def test_default_engine_is_the_cuda_library(monkeypatch):
+    """The engine seam of the drop-in (used by the CPU tests of the host logic) is never set by the package itself:
+    without DLV_ENGINE the factory is the CUDA engine, and building it on a box without a GPU raises."""
+    import torch
+    from delivr_cfos_b200.inference import inference as inf
+    monkeypatch.delenv("DLV_ENGINE", raising=False)
+    assert inf._engine_factory() is inf.CudaEngine
+    if not torch.cuda.is_available():
+        from delivr_cfos_b200 import DlvError
+        with pytest.raises(DlvError):
+            inf.CudaEngine("no-such-checkpoint.tar", 0)
+    src = "".join(open(os.path.join(dp, f)).read() for dp, _, fs in os.walk(os.path.join(ROOT, "delivr_cfos_b200")) for f in fs if f.endswith(".py"))
+    assert src.count('"DLV_ENGINE"') == 1 and "_ENGINE_FACTORY =" in src and src.count("_ENGINE_FACTORY = ") == 1
+
+
 def test_product_does_not_import_oracle():
     """The oracle is test infrastructure: nothing under delivr_cfos_b200/ may reference it."""
     for dirpath, _, files in os.walk(os.path.join(ROOT, "delivr_cfos_b200")):
