@@ -288,23 +288,28 @@ class TorchComm:
 
 
 def pack_table(table):
-    """Statistics table -> one int64 [N+1, 10] array (count, 3 coordinate sums, 6 box bounds; uint64 bit patterns kept)."""
+    """Statistics table -> ONE int64 vector of 10 (N + 1) entries, column blocks [counts | 3 coordinate sums | 6 box
+    bounds] (uint64 bit patterns kept).  Column blocks, not rows: the receiving side then takes its three arrays as
+    contiguous views of the gathered buffer (a row-interleaved [N + 1, 10] layout cost 0.2 s of strided copies per step
+    for the 2.5 M components of a whole brain on 8 ranks)."""
     if table is None:
-        return np.zeros((0, 10), dtype=np.int64)
+        return np.zeros(0, dtype=np.int64)
     n1 = int(table["n"]) + 1
-    out = np.empty((n1, 10), dtype=np.int64)
-    out[:, 0] = np.asarray(table["voxel_counts"]).view(np.int64)
-    out[:, 1:4] = np.asarray(table["sums"]).view(np.int64).reshape(n1, 3)
-    out[:, 4:10] = np.asarray(table["bounding_boxes"]).reshape(n1, 6)
+    out = np.empty(n1 * 10, dtype=np.int64)
+    out[:n1] = np.asarray(table["voxel_counts"]).reshape(-1).view(np.int64)
+    out[n1:4 * n1] = np.asarray(table["sums"]).reshape(-1).view(np.int64)
+    out[4 * n1:] = np.asarray(table["bounding_boxes"]).reshape(-1)
     return out
 
 
-def unpack_table(rows):
-    if len(rows) == 0:
+def unpack_table(vec):
+    """Inverse of pack_table, without copies: views of ``vec``."""
+    if len(vec) == 0:
         return None
-    rows = np.ascontiguousarray(rows)
-    return {"n": len(rows) - 1, "voxel_counts": rows[:, 0].copy().view(np.uint64),
-            "sums": np.ascontiguousarray(rows[:, 1:4]).view(np.uint64), "bounding_boxes": np.ascontiguousarray(rows[:, 4:10])}
+    vec = np.ascontiguousarray(vec)
+    n1 = len(vec) // 10
+    return {"n": n1 - 1, "voxel_counts": vec[:n1].view(np.uint64), "sums": vec[n1:4 * n1].view(np.uint64).reshape(n1, 3),
+            "bounding_boxes": vec[4 * n1:].reshape(n1, 6)}
 
 
 # ------------------------------------------------------------------------------------------- overlapped slab upload
