@@ -256,3 +256,63 @@ def test_virtual_slabs_random_configs(seed):
         assert np.array_equal(np.concatenate([w.binaries.numpy() for w in ws]), w1.binaries.numpy()), (shape, roi, overlap, world)
         assert np.array_equal(np.concatenate([w.labels.numpy() for w in ws]), w1.labels.numpy())
         assert t["n"] == t1["n"] and np.array_equal(t["voxel_counts"], t1["voxel_counts"])
+
+
+def test_table_merge_threaded_path_matches_numpy():
+    """dlv_table_merge splits the global rows over host threads above 200 000 rows: every field against a plain numpy
+    merge (scatter adds / min / max), with merged components, empty rows (neutral boxes) and a rank without planes."""
+    rng = np.random.default_rng(11)
+    world, n_per = 4, 90000
+    counts = [n_per, 0, n_per, n_per]
+    pairs = [np.zeros((0, 2), np.uint32), np.zeros((0, 2), np.uint32),
+             np.stack([rng.integers(1, n_per + 1, 5000), rng.integers(1, n_per + 1, 5000)], 1).astype(np.uint32),
+             np.stack([rng.integers(1, n_per + 1, 5000), rng.integers(1, n_per + 1, 5000)], 1).astype(np.uint32)]
+    order = [0, 2, 3]
+    luts_o, n = slabs.resolve_global_labels([counts[q] for q in order], [pairs[0], pairs[2], pairs[3]])
+    assert n + 1 > 200000
+    luts = [luts_o[0], np.zeros(1, np.uint32), luts_o[1], luts_o[2]]
+
+    def table(k):
+        vc = rng.integers(0, 50, k + 1).astype(np.uint64)
+        sums = (rng.integers(0, 10 ** 6, (k + 1, 3)).astype(np.uint64)) * vc[:, None]
+        bb = np.zeros((k + 1, 6), np.int64)
+        bb[:, 0::2] = rng.integers(0, 100, (k + 1, 3))
+        bb[:, 1::2] = bb[:, 0::2] + rng.integers(0, 9, (k + 1, 3))
+        empty = vc == 0
+        bb[empty] = [100, -1, 100, -1, 100, -1]              # neutral box of a row without voxels
+        return {"n": k, "voxel_counts": vc, "sums": sums, "bounding_boxes": bb}
+
+    tabs = [table(n_per), None, table(n_per), table(n_per)]
+    zoff = [0, 40, 40, 90]
+    shape = (150, 100, 100)
+    got = slabs.merge_tables(tabs, luts, zoff, n, shape)
+    vc = np.zeros(n + 1, np.uint64)
+    sm = np.zeros((n + 1, 3), np.uint64)
+    bb = np.tile(np.array([shape[0], -1, shape[1], -1, shape[2], -1], np.int64), (n + 1, 1))
+    for t, lut, z0 in zip(tabs, luts, zoff):
+        if t is None:
+            continue
+        g = lut.astype(np.int64)
+        np.add.at(vc, g, t["voxel_counts"])
+        s = t["sums"].copy()
+        s[:, 0] += t["voxel_counts"] * np.uint64(z0)
+        for k in range(3):
+            np.add.at(sm[:, k], g, s[:, k])
+        ok = t["bounding_boxes"][:, 1] >= 0
+        b = t["bounding_boxes"][ok].copy()
+        b[:, 0:2] += z0
+        for k in (0, 2, 4):
+            np.minimum.at(bb[:, k], g[ok], b[:, k])
+            np.maximum.at(bb[:, k + 1], g[ok], b[:, k + 1])
+    assert got["n"] == n
+    assert np.array_equal(got["voxel_counts"], vc)
+    assert np.array_equal(got["sums"], sm)
+    assert np.array_equal(got["bounding_boxes"], bb)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        assert np.array_equal(got["centroids"], sm.astype(np.float64) / vc.astype(np.float64)[:, None], equal_nan=True)
+    # the column-block wire format round-trips without copies
+    vec = slabs.pack_table(tabs[2])
+    back = slabs.unpack_table(vec)
+    for k in ("voxel_counts", "sums", "bounding_boxes"):
+        assert np.array_equal(back[k], tabs[2][k]) and np.shares_memory(back[k], vec)
+    assert slabs.unpack_table(slabs.pack_table(None)) is None
