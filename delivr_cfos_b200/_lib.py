@@ -55,7 +55,7 @@ EXPORTS = [
     "dlv_synchronize", "dlv_set_conv_timing", "dlv_conv_time_ms", "dlv_stage_time_ms", "dlv_load_weights", "dlv_segment", "dlv_ccl", "dlv_table_free",
     "dlv_ccl_last_timing", "dlv_unet_forward", "dlv_op_conv3d", "dlv_op_deconv", "dlv_op_finalise",
     "dlv_window_grid", "dlv_windows_active", "dlv_seg_accumulate", "dlv_seg_average", "dlv_op_finalise_slab",
-    "dlv_ccl_boundary_pairs", "dlv_relabel", "dlv_table_merge", "dlv_resolve_labels", "dlv_tiff_info", "dlv_tiff_read_u16", "dlv_tiff_last_error",
+    "dlv_ccl_boundary_pairs", "dlv_relabel", "dlv_table_merge", "dlv_table_csv", "dlv_resolve_labels", "dlv_tiff_info", "dlv_tiff_read_u16", "dlv_tiff_last_error",
     "dlv_load_tiff_planes", "dlv_tiff_write_planes", "dlv_tiff_write_last_error", "dlv_paint_boxes", "dlv_edt",
 ]
 
@@ -141,12 +141,14 @@ def load_library():
     L.dlv_tiff_write_last_error.argtypes = []
     L.dlv_resolve_labels.restype = ctypes.c_int
     L.dlv_resolve_labels.argtypes = [ctypes.c_int, P(c_i64), P(c_vp), P(c_i64), P(c_vp), P(c_i64)]
+    L.dlv_table_csv.restype = c_i64
+    L.dlv_table_csv.argtypes = [c_vp, c_vp, c_i64, c_vp, c_i64]
     L.dlv_table_merge.restype = ctypes.c_int
     L.dlv_table_merge.argtypes = [c_i64, ctypes.c_int, P(c_i64), P(c_vp), P(c_vp), P(c_vp), P(c_vp), P(c_i64), P(c_i64),
                                   c_vp, c_vp, c_vp, c_vp]
     L.dlv_edt.restype = ctypes.c_int
     L.dlv_edt.argtypes = [c_vp, c_vp, P(c_i64), P(ctypes.c_double), c_vp]
-    if L.dlv_abi_version() != 3:
+    if L.dlv_abi_version() != 4:
         raise DlvError("libdelivr_b200.so ABI version mismatch")
     _lib = L
     return L
@@ -522,6 +524,25 @@ def table_merge(tables, luts, z_offsets, n_global, shape_real):
     if rc != 0:
         raise DlvError(f"dlv_table_merge failed ({rc}): a label map points outside rows 0..{n}")
     return {"n": n, "voxel_counts": counts, "sums": sums, "bounding_boxes": bbox, "centroids": cent}
+
+
+def table_csv(centroids, voxel_counts, n):
+    """dlv_table_csv (host only): the per-cell CSV text of count_blobs.py:101-114 for table rows 1..n-1 -> str."""
+    L = load_library()
+    n = int(n)
+    cent = np.ascontiguousarray(centroids, dtype=np.float64)
+    cnt = np.ascontiguousarray(voxel_counts, dtype=np.uint64)
+    if cent.shape != (len(cnt), 3) or len(cnt) < max(n, 1):
+        raise ValueError(f"table_csv: centroids {cent.shape} / voxel_counts {cnt.shape} do not hold rows 0..{n - 1}")
+    cap = 32 + max(n - 1, 0) * 96                 # typical rows are ~60 bytes; the call reports the size it needs
+    while True:
+        buf = ctypes.create_string_buffer(cap)
+        need = int(L.dlv_table_csv(cent.ctypes.data, cnt.ctypes.data, n, buf, cap))
+        if need < 0:
+            raise DlvError(f"dlv_table_csv failed ({need})")
+        if need <= cap:
+            return buf.raw[:need].decode("ascii")
+        cap = need
 
 
 def window_grid(shape_pad, roi, overlap):

@@ -2,6 +2,10 @@
 // window grid, per-slab accumulate / average / finalise, boundary label pairs and relabelling for the
 // cross-slab component merge.  The host side that strings these together is delivr_cfos_b200/slabs.py.
 #include <algorithm>
+#include <charconv>
+#include <cmath>
+#include <cstring>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -234,6 +238,103 @@ int dlv_table_merge(int64_t n_global, int ntables, const int64_t* rows, const ui
     for (int k = 0; k < nthr; ++k)
         if (bad[k]) return DLV_ERR_ARG;
     return DLV_OK;
+}
+
+/* ---- CSV text of the per-cell table (see include/delivr_b200.h) */
+namespace {
+// Python's repr(float) (float_repr_style 'short'): shortest digits that round-trip, fixed notation with at least one
+// decimal unless the decimal point falls at or before 1e-4 or beyond 16 digits, then d[.ddd]e+XX / e-XX.
+char* py_float_repr(double x, char* out) {
+    if (x != x) { memcpy(out, "nan", 3); return out + 3; }
+    if (x == 0.0) { if (std::signbit(x)) *out++ = '-'; memcpy(out, "0.0", 3); return out + 3; }
+    if (std::isinf(x)) { if (x < 0) *out++ = '-'; memcpy(out, "inf", 3); return out + 3; }
+    char sci[40];
+    const auto r = std::to_chars(sci, sci + sizeof(sci), x, std::chars_format::scientific);   // shortest: d[.ddd]e[+-]XX
+    const char* p = sci;
+    if (*p == '-') { *out++ = '-'; ++p; }
+    char digits[24];
+    int nd = 0;
+    for (; p < r.ptr && *p != 'e'; ++p)
+        if (*p != '.') digits[nd++] = *p;
+    int e10 = 0;
+    if (p < r.ptr) {
+        ++p;
+        const bool neg = (*p == '-');
+        if (*p == '+' || *p == '-') ++p;
+        for (; p < r.ptr; ++p) e10 = e10 * 10 + (*p - '0');
+        if (neg) e10 = -e10;
+    }
+    const int decpt = e10 + 1;                       // value = 0.d1d2... x 10^decpt
+    if (decpt <= -4 || decpt > 16) {
+        *out++ = digits[0];
+        if (nd > 1) { *out++ = '.'; memcpy(out, digits + 1, nd - 1); out += nd - 1; }
+        *out++ = 'e';
+        int e = decpt - 1;
+        *out++ = e < 0 ? '-' : '+';
+        if (e < 0) e = -e;
+        if (e < 10) *out++ = '0';
+        const auto re = std::to_chars(out, out + 8, e);
+        return re.ptr;
+    }
+    if (decpt <= 0) {
+        *out++ = '0'; *out++ = '.';
+        for (int i = 0; i < -decpt; ++i) *out++ = '0';
+        memcpy(out, digits, nd);
+        return out + nd;
+    }
+    if (decpt >= nd) {
+        memcpy(out, digits, nd); out += nd;
+        for (int i = 0; i < decpt - nd; ++i) *out++ = '0';
+        *out++ = '.'; *out++ = '0';
+        return out;
+    }
+    memcpy(out, digits, decpt); out += decpt;
+    *out++ = '.';
+    memcpy(out, digits + decpt, nd - decpt);
+    return out + (nd - decpt);
+}
+}  // namespace
+
+int64_t dlv_table_csv(const double* centroids, const uint64_t* voxel_counts, int64_t n, char* buf, int64_t cap) {
+    if (!centroids || !voxel_counts || n < 0 || cap < 0 || (cap > 0 && !buf)) return DLV_ERR_ARG;
+    static const char header[] = ",Blob,Coords,Size\n";
+    const int64_t nrows = n > 1 ? n - 1 : 0;         // labels 1 .. n-1
+    const int nthr = nrows > 50000 ? static_cast<int>(std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()))) : 1;
+    std::vector<std::string> part(static_cast<size_t>(nthr));
+    auto work = [&](int k) {
+        const int64_t i0 = 1 + nrows * k / nthr, i1 = 1 + nrows * (k + 1) / nthr;
+        std::string& s = part[k];
+        s.reserve(static_cast<size_t>(i1 - i0) * 72);
+        char line[192];
+        for (int64_t i = i0; i < i1; ++i) {
+            char* o = line;
+            *o++ = '0'; *o++ = ',';
+            o = std::to_chars(o, o + 20, static_cast<long long>(i)).ptr;
+            *o++ = ','; *o++ = '"'; *o++ = '[';
+            for (int a = 0; a < 3; ++a) {
+                if (a) { *o++ = ','; *o++ = ' '; }
+                o = py_float_repr(centroids[3 * i + a], o);
+            }
+            *o++ = ']'; *o++ = '"'; *o++ = ',';
+            o = std::to_chars(o, o + 24, static_cast<unsigned long long>(voxel_counts[i])).ptr;
+            *o++ = '\n';
+            s.append(line, static_cast<size_t>(o - line));
+        }
+    };
+    if (nthr == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int k = 0; k < nthr; ++k) th.emplace_back(work, k);
+        for (auto& x : th) x.join();
+    }
+    int64_t total = static_cast<int64_t>(sizeof(header) - 1);
+    for (const auto& s : part) total += static_cast<int64_t>(s.size());
+    if (total <= cap) {
+        char* o = buf;
+        memcpy(o, header, sizeof(header) - 1); o += sizeof(header) - 1;
+        for (const auto& s : part) { memcpy(o, s.data(), s.size()); o += s.size(); }
+    }
+    return total;
 }
 
 /* Host-only: global component numbering from per-slab counts and seam pairs (see include/delivr_b200.h). */

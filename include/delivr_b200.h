@@ -35,7 +35,7 @@ typedef struct dlv_ctx dlv_ctx;
 #define DLV_ERR_STATE (-3)
 #define DLV_ERR_UNSUPPORTED (-4)
 
-#define DLV_ABI_VERSION 3
+#define DLV_ABI_VERSION 4
 
 /* ---- lifecycle -------------------------------------------------------- */
 int dlv_abi_version(void);
@@ -218,6 +218,16 @@ int dlv_table_merge(int64_t n_global, int ntables, const int64_t* rows, const ui
                     const uint64_t* const* counts, const uint64_t* const* sums, const int64_t* const* bbox,
                     const int64_t* z_offsets, const int64_t shape[3], uint64_t* counts_out, uint64_t* sums_out,
                     int64_t* bbox_out, double* centroids_out);
+
+/* Host-only (no ctx, no GPU): the per-cell CSV text of count_blobs.py:101-114 - what pandas writes for the DataFrame
+ * the reference builds row by row: header ",Blob,Coords,Size", then for every label i = 1..n-1 (the reference's
+ * range(1, N): the last component is not listed) the line  0,i,"[z, y, x]",size  with the centroid coordinates as
+ * Python float repr (shortest digits that round-trip; exponent form below 1e-4 and from 1e16; "nan" / "inf") and the
+ * voxel count in decimal.  centroids [n+1][3], voxel_counts [n+1] (table rows 0..n).  Formats on all host threads
+ * (a whole brain has 2.5 M rows = 180 MB of text).  Returns the length of the text in bytes and copies it into buf when
+ * it fits cap (no terminating NUL); a larger return value than cap means: call again with that much room.  Negative:
+ * bad arguments. */
+int64_t dlv_table_csv(const double* centroids, const uint64_t* voxel_counts, int64_t n, char* buf, int64_t cap);
 
 /* ---- raw TIFF planes -> device-resident masked volume ----
  * Replaces the masked_nifti.npy producer loop (downsample/downsample_and_mask.py:398-414: cv2.imread(plane, -1),

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", LIB_PATH], capture_output=True, text=True).stdout
     exported = sorted(set(re.findall(r" T (dlv_[a-z0-9_]+)", out)))
     assert exported == declared
-    assert lib.dlv_abi_version() == 3
+    assert lib.dlv_abi_version() == 4
 
 
 def test_no_cpu_fallback_without_gpu():
