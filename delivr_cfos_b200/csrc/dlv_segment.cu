@@ -67,7 +67,9 @@ struct AvgArgs {
     int passes;
 };
 
-__global__ void average_kernel(const int32_t* __restrict__ acc, float* __restrict__ avg, AvgArgs a) {
+// `acc` and `avg` are the SAME buffer in the library's calls (the average overwrites the sums in place, element by
+// element, by the thread that read it): no __restrict__ on them.
+__global__ void average_kernel(const int32_t* acc, float* avg, AvgArgs a) {
     const int64_t x = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t y = blockIdx.y, z = blockIdx.z;
     if (x >= a.PX) return;
@@ -111,7 +113,7 @@ __global__ void cell_table_kernel(CellArgs c, float2* __restrict__ table) {
             }
     table[i] = make_float2(wsum, wskip);
 }
-__global__ void average_const_kernel(const int4* __restrict__ acc, float4* __restrict__ avg, int64_t PY, int64_t PX4, int64_t gz0,
+__global__ void average_const_kernel(const int4* acc, float4* avg /* same buffer, see average_kernel */, int64_t PY, int64_t PX4, int64_t gz0,
                                      const int32_t* __restrict__ cid_z, const int32_t* __restrict__ cid_y,
                                      const int4* __restrict__ cid_x4, int ncy, int ncx, const float2* __restrict__ table, int passes) {
     const int64_t x4 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
